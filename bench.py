@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- HistoGAN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): RGBuvHistBlock forward + Hellinger loss +
+backward on a synthetic batch of 32 x 3 x 256 x 256 images per GPU, h = 64,
+insz = 256 (all 65 536 pixels enter the histogram -- the heaviest setting; the
+Trainer's insz = 150 is reported alongside).  One "step" = one such pass.  The
+batch shards across ranks with no collective (images are independent), so the
+multi-GPU run is weak scaling.
+
+One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in
+HBM; `e2e` = the same through the public API from pinned HOST buffers (H2D of
+images + targets, D2H of loss, histogram and image gradient inside the timed
+region).  `--impl reference` times the reference's CPU algorithm (the torch-CPU
+restatement in oracle/, kind "port": the reference itself is Python and does
+not travel to the GPU box) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+B_PER_GPU = 32
+S = 256
+H_BINS = 64
+INSZ = 256
+ALPHA = 2.0
+L2_FLUSH_BYTES = 256 << 20
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+# --------------------------------------------------------------------- data --
+
+def make_inputs(rank, B=B_PER_GPU, device="cpu"):
+    """generator-like images relu(randn*0.5+0.3) and oracle-free random targets."""
+    g = torch.Generator().manual_seed(rank)
+    x = torch.relu(torch.randn(B, 3, S, S, generator=g) * 0.5 + 0.3)
+    t = torch.rand(B, 3, H_BINS, H_BINS, generator=g)
+    t = t / t.sum(dim=(1, 2, 3), keepdim=True)
+    return x.to(device), t.to(device)
+
+
+# ------------------------------------------------------------ clock sampler --
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    reasons.add(n)
+        if sm:
+            sm_sorted = sorted(sm)
+            # median of the samples under load (upper half)
+            out["sm_mhz"] = sm_sorted[len(sm_sorted) * 3 // 4]
+            out["sm_max_mhz"] = max(smax)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# -------------------------------------------------------------- our arm ------
+
+def run_ours(args):
+    import torch.distributed as dist
+    from histogan_b200 import RGBuvHistBlock, hellinger_loss, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    _lib.check(lib.hg_device_check(local_rank), "hg_device_check")
+
+    x_host, t_host = make_inputs(rank)
+    x_pin, t_pin = x_host.pin_memory(), t_host.pin_memory()
+    x_dev, t_dev = x_pin.to(dev), t_pin.to(dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    blk = RGBuvHistBlock(h=H_BINS, insz=INSZ, device=dev)
+    blk150 = RGBuvHistBlock(h=H_BINS, insz=150, device=dev)
+
+    def step(xd, td, block=blk):
+        xg = xd.detach().requires_grad_(True)
+        hist = block(F.relu(xg))                     # histoGAN/histoGAN.py:955
+        loss = hellinger_loss(td, hist, ALPHA)       # :957-960
+        loss.backward()
+        return loss, hist, xg.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """sum of per-step CUDA-event durations; L2 flushed between steps
+        (outside the event windows); returns seconds (max over ranks)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(steps)]
+        for s, e in evs:
+            flush.zero_()
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        tot = sum(s.elapsed_time(e) for s, e in evs) * 1e-3
+        if world > 1:
+            tt = torch.tensor([tot], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tot = tt.item()
+        return tot
+
+    # ---- headline: inputs resident in HBM
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    n0 = lib.hg_launch_count()
+    t_dev_total = timed(lambda: step(x_dev, t_dev), args.steps, args.warmup)
+    launches = (lib.hg_launch_count() - n0) // (args.steps + args.warmup) * args.steps
+    clocks = sampler.stop() if sampler else {}
+
+    # ---- e2e: host buffers in, host results out, through the public API
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+    hist_h = torch.empty(B_PER_GPU, 3, H_BINS, H_BINS).pin_memory()
+    grad_h = torch.empty(B_PER_GPU, 3, S, S).pin_memory()
+
+    def e2e_step():
+        xd = x_pin.to(dev, non_blocking=True)
+        td = t_pin.to(dev, non_blocking=True)
+        loss, hist, gx = step(xd, td)
+        loss_h.copy_(loss, non_blocking=True)
+        hist_h.copy_(hist.detach(), non_blocking=True)
+        grad_h.copy_(gx, non_blocking=True)
+
+    t_e2e_total = timed(e2e_step, args.steps, max(1, args.warmup // 2))
+    h2d = x_pin.numel() * 4 + t_pin.numel() * 4
+    d2h = 4 + hist_h.numel() * 4 + grad_h.numel() * 4
+
+    # ---- per-call kernel timing for the roofline (forward call / backward call)
+    def time_call(fn, reps=10):
+        fn(); fn()
+        torch.cuda.synchronize()
+        ds = []
+        for _ in range(reps):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); fn(); e.record()
+            torch.cuda.synchronize()
+            ds.append(s.elapsed_time(e) * 1e-3)
+        return sum(ds) / len(ds)
+
+    xg = x_dev.detach().requires_grad_(True)
+    hist_keep = blk(F.relu(xg))
+    g_up = torch.rand_like(hist_keep)
+    t_fwd = time_call(lambda: blk(x_dev))
+    t_bwd = time_call(lambda: torch.autograd.grad(hist_keep, xg, g_up, retain_graph=True))
+    t150 = timed(lambda: step(x_dev, t_dev, blk150), max(3, args.steps // 2), 2)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, bf16_peak, peak_kind = load_peaks()
+    n_imgs = B_PER_GPU * world * args.steps
+    N = S * S
+    # algorithmic work per image: bytes fwd+loss+bwd 2 555 904; flops 24 576*N fwd, 2x bwd
+    bytes_fwd, bytes_all = 835_584, 2_555_904
+    flops_fwd = 24_576 * N
+    bwd_bytes = bytes_all - bytes_fwd
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    fma_peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+    roof = {
+        "bound": "hbm", "kernel": "hist_bwd_fast_kernel (hg_hist_bwd call: prep + pixel + adjoint)",
+        "achieved": round(bwd_bytes * B_PER_GPU / t_bwd / 1e9, 2), "peak": hbm_peak,
+        "unit": "GB/s", "frac": round(bwd_bytes * B_PER_GPU / t_bwd / 1e9 / hbm_peak, 5),
+        "traffic": None, "peak_kind": peak_kind,
+        "note": "the op is compute-bound (1.9 kFLOP/B, SURVEY 8d): HBM fraction is capped near "
+                "1-2 %; see `compute`",
+        "compute": {
+            "pipe": "fp32 FMA (CUDA cores)", "fma_peak_tflops_at_measured_clock": round(fma_peak_tf, 1),
+            "fwd_ms": round(t_fwd * 1e3, 4), "bwd_ms": round(t_bwd * 1e3, 4),
+            "fwd_tflops": round(flops_fwd * B_PER_GPU / t_fwd / 1e12, 2),
+            "bwd_tflops": round(2 * flops_fwd * B_PER_GPU / t_bwd / 1e12, 2),
+            "fwd_frac_of_fma_peak": round(flops_fwd * B_PER_GPU / t_fwd / 1e12 / fma_peak_tf, 4),
+            "bwd_frac_of_fma_peak": round(2 * flops_fwd * B_PER_GPU / t_bwd / 1e12 / fma_peak_tf, 4),
+            "fwd_hbm_gbs": round(bytes_fwd * B_PER_GPU / t_fwd / 1e9, 2),
+        },
+    }
+    out = {
+        "metric": "images/sec", "value": round(n_imgs / t_dev_total, 2), "unit": "images/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(t_dev_total / args.steps * 1e3, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "RGBuvHistBlock fwd + Hellinger loss + bwd, 32x3x256x256 per GPU, "
+                               "h=64, insz=256 (N=65536 px/img), inverse-quadratic sigma=0.02",
+                   "global_batch": B_PER_GPU * world, "parallelism": f"dp{world} (no collective)",
+                   "l2_flush": "256 MiB memset between steps, outside the event windows",
+                   "us_per_image": round(t_dev_total / n_imgs * world * 1e6, 3),
+                   "insz150_images_per_s": round(B_PER_GPU * world * max(3, args.steps // 2) / t150, 2)},
+        "e2e": {"value": round(n_imgs / t_e2e_total, 2), "unit": "images/s",
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+    }
+    if world == 1:
+        out["cpu_baseline"] = cpu_baseline(sample_images=2, reps=2)
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------- reference / CPU arm --
+
+def cpu_step(x, t):
+    from oracle import hist_oracle as ho
+    return ho.hist_loss_and_grad(x, t, ALPHA, h=H_BINS, insz=INSZ)
+
+
+def cpu_baseline(sample_images=2, reps=2):
+    """the reference's algorithm (torch-CPU restatement) on a bounded sample."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    x, t = make_inputs(0, B=sample_images)
+    cpu_step(x, t)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_step(x, t)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": round(sample_images / dt, 3), "unit": "images/s",
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_images} of the 32 images per step (same 256x256, insz=256 "
+                      f"workload), {reps} reps after 1 warm-up"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    sample = 2
+    x, t = make_inputs(0, B=sample)
+    steps = min(args.steps, 5)
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(x, t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(x, t)
+    dt = time.perf_counter() - t0
+    val = round(sample * steps / dt, 3)
+    out = {
+        "impl": "reference", "metric": "images/sec", "value": val, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": round(dt / steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f64 soft-binning, as the reference)", "data": "synthetic",
+        "config": {"workload": "RGBuvHistBlock fwd + Hellinger loss + bwd, 256x256 images, h=64, "
+                               "insz=256; CPU restatement of the reference (oracle/hist_oracle.py)",
+                   "global_batch": sample},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": torch.get_num_threads(),
+                         "kind": "port",
+                         "sample": f"{sample} images per step (bounded sample of the 32-image batch)"},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,479 @@
+// hist_bwd.cu -- backward of the RGB-uv histogram block: what autograd derives
+// from RGBuvHistBlock.py:75-228, as three kernels:
+//
+//   1. prep     grad wrt the un-normalised histogram:
+//                 G = (g - <g, Hn>) / (S + eps)          (adjoint of :225-226)
+//               stored in the "primed" (un-flipped) layout of the fast path.
+//   2. pixel    per pixel, with the soft-binning kernels recomputed (never
+//               stored):   dE = G-weighted mat-vecs  ->  du, dIy  ->  dR,dG,dB
+//               written as gP (B,3,N): grad wrt the pre-processed pixels.
+//   3. adjoint  grad_x = clamp-mask(x) * resize^T(gP)    (adjoint of :76-99),
+//               gather formulation (deterministic, no atomics).
+#include "hg_common.cuh"
+
+namespace hg {
+
+bool hist_fast_path(const HistGeom& g, const hg_hist_params* p);   // hist_fwd.cu
+
+// ================================================================= prep =====
+// grid = B, block = 1024
+__global__ void __launch_bounds__(1024)
+hist_bwd_prep_kernel(const float* __restrict__ hist, const float* __restrict__ hist_sum,
+                     const float* __restrict__ grad_hist, const int E, const int h,
+                     const int primed, float* __restrict__ G) {
+  __shared__ float red[32];
+  __shared__ float s_dot;
+  const int b = blockIdx.x;
+  const float* hn = hist + (long long)b * E;
+  const float* gh = grad_hist + (long long)b * E;
+  float local = 0.f;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) local = fmaf(gh[e], hn[e], local);
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) s_dot = v;
+  }
+  __syncthreads();
+  const float dot = s_dot;
+  const float inv = 1.f / (hist_sum[b] + kEps);
+  float* Gb = G + (long long)b * E;
+  const int hh = h * h;
+  for (int e = threadIdx.x; e < E; e += blockDim.x) {
+    const float v = (gh[e] - dot) * inv;
+    int dst = e;
+    if (primed) {   // channel 1: flip rows; channel 2: flip rows and cols
+      const int c = e / hh, r = e - c * hh, i = r / h, j = r - i * h;
+      if (c == 1) dst = hh + (h - 1 - i) * h + j;
+      else if (c == 2) dst = 2 * hh + (h - 1 - i) * h + (h - 1 - j);
+    }
+    Gb[dst] = v;
+  }
+}
+
+// ============================================================ fast path =====
+constexpr int kBP = 128;          // pixels per tile
+constexpr int kBThreads = 512;
+
+struct BwdSmem {
+  float G[3][64][64];             // G'[m][i][j]
+  float GT[3][64][64];            // G'[m][j][i]
+  float E[3][64][kBP];            // E^T[m][bin][pixel]
+  float U[3][kBP];
+  float W[kBP];
+  float Pix[3][kBP];
+};
+
+template <int METHOD, bool INTENSITY>
+__global__ void __launch_bounds__(kBThreads, 1)
+hist_bwd_fast_kernel(const float* __restrict__ x, const HistGeom g, const HistTables t,
+                     const float* __restrict__ Gp, float* __restrict__ gP, const int chunks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdSmem& s = *reinterpret_cast<BwdSmem*>(smem_raw);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int tiles_total = (g.N + kBP - 1) / kBP;
+  const int tile0 = (int)((long long)chunk * tiles_total / chunks);
+  const int tile1 = (int)((long long)(chunk + 1) * tiles_total / chunks);
+  const float inv_s2 = g.inv_sigma2;
+
+  // stage G' and its transpose
+  {
+    const float* Gb = Gp + (long long)b * (3 * 64 * 64);
+    for (int e = tid; e < 3 * 64 * 64; e += kBThreads) {
+      const int m = e >> 12, a = (e >> 6) & 63, c = e & 63;
+      s.G[m][a][c] = Gb[e];
+      s.GT[m][a][c] = Gb[(m << 12) + (c << 6) + a];   // strided L2 read, conflict-free store
+    }
+  }
+
+  // phase-2 role
+  const int og = lane & 15;                 // outputs og*4 .. og*4+3
+  const int pg = warp * 2 + (lane >> 4);    // pixels  pg*4 .. pg*4+3
+  // phase-1 role
+  const int p1 = tid & (kBP - 1), g4 = tid >> 7;
+
+  for (int tile = tile0; tile < tile1; ++tile) {
+    const int p0 = tile * kBP;
+    __syncthreads();                         // previous tile fully consumed / G staged
+    if (tid < kBP) {
+      const int p = p0 + tid;
+      float w = 0.f, u0 = 0.f, u1 = 0.f, u2 = 0.f, r = 0.f, gg = 0.f, bb = 0.f;
+      if (p < g.N) {
+        load_pixel(x, g, t, b, p, r, gg, bb);
+        const PixelProj q = project_pixel(r, gg, bb, INTENSITY);
+        w = q.iy; u0 = q.u_rg; u1 = q.u_rb; u2 = q.u_gb;
+      }
+      s.W[tid] = w; s.U[0][tid] = u0; s.U[1][tid] = u1; s.U[2][tid] = u2;
+      s.Pix[0][tid] = r; s.Pix[1][tid] = gg; s.Pix[2][tid] = bb;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+      const float u = s.U[m][p1];
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        const int k = g4 * 16 + kk;
+        s.E[m][k][p1] = kernel_f32<METHOD>(u, t.c_hi[k], t.c_lo[k], inv_s2);
+      }
+    }
+    __syncthreads();
+
+    float W1[4][4], W2[4][4], V0[4][4], V12[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) W1[a][c] = W2[a][c] = V0[a][c] = V12[a][c] = 0.f;
+
+#pragma unroll 2
+    for (int k = 0; k < 64; ++k) {
+      const float4 erg4 = *reinterpret_cast<const float4*>(&s.E[0][k][pg * 4]);
+      const float4 erb4 = *reinterpret_cast<const float4*>(&s.E[1][k][pg * 4]);
+      const float4 egb4 = *reinterpret_cast<const float4*>(&s.E[2][k][pg * 4]);
+      const float4 g0r4 = *reinterpret_cast<const float4*>(&s.G[0][k][og * 4]);
+      const float4 g1r4 = *reinterpret_cast<const float4*>(&s.G[1][k][og * 4]);
+      const float4 g2r4 = *reinterpret_cast<const float4*>(&s.G[2][k][og * 4]);
+      const float4 g0c4 = *reinterpret_cast<const float4*>(&s.GT[0][k][og * 4]);
+      const float4 g1c4 = *reinterpret_cast<const float4*>(&s.GT[1][k][og * 4]);
+      const float4 g2c4 = *reinterpret_cast<const float4*>(&s.GT[2][k][og * 4]);
+      const float erg[4] = {erg4.x, erg4.y, erg4.z, erg4.w};
+      const float erb[4] = {erb4.x, erb4.y, erb4.z, erb4.w};
+      const float egb[4] = {egb4.x, egb4.y, egb4.z, egb4.w};
+      const float g0r[4] = {g0r4.x, g0r4.y, g0r4.z, g0r4.w};
+      const float g1r[4] = {g1r4.x, g1r4.y, g1r4.z, g1r4.w};
+      const float g2r[4] = {g2r4.x, g2r4.y, g2r4.z, g2r4.w};
+      const float g0c[4] = {g0c4.x, g0c4.y, g0c4.z, g0c4.w};
+      const float g1c[4] = {g1c4.x, g1c4.y, g1c4.z, g1c4.w};
+      const float g2c[4] = {g2c4.x, g2c4.y, g2c4.z, g2c4.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          // k plays the role of j for the W products and of i for the V products
+          W1[a][c] = fmaf(erb[a], g0c[c], W1[a][c]);
+          W1[a][c] = fmaf(egb[a], g1c[c], W1[a][c]);
+          W2[a][c] = fmaf(egb[a], g2c[c], W2[a][c]);
+          V0[a][c] = fmaf(erg[a], g0r[c], V0[a][c]);
+          V12[a][c] = fmaf(erg[a], g1r[c], V12[a][c]);
+          V12[a][c] = fmaf(erb[a], g2r[c], V12[a][c]);
+        }
+    }
+
+    // chain through the kernel derivative for this thread's 4 pixels x 4 bins
+    float du_rg[4] = {0.f, 0.f, 0.f, 0.f}, du_rb[4] = {0.f, 0.f, 0.f, 0.f};
+    float du_gb[4] = {0.f, 0.f, 0.f, 0.f}, d_iy[4] = {0.f, 0.f, 0.f, 0.f};
+    {
+      const float4 u04 = *reinterpret_cast<const float4*>(&s.U[0][pg * 4]);
+      const float4 u14 = *reinterpret_cast<const float4*>(&s.U[1][pg * 4]);
+      const float4 u24 = *reinterpret_cast<const float4*>(&s.U[2][pg * 4]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&s.W[pg * 4]);
+      const float u0[4] = {u04.x, u04.y, u04.z, u04.w};
+      const float u1[4] = {u14.x, u14.y, u14.z, u14.w};
+      const float u2[4] = {u24.x, u24.y, u24.z, u24.w};
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int o = og * 4 + c;
+        const float chi = t.c_hi[o], clo = t.c_lo[o];
+        const float4 e04 = *reinterpret_cast<const float4*>(&s.E[0][o][pg * 4]);
+        const float4 e14 = *reinterpret_cast<const float4*>(&s.E[1][o][pg * 4]);
+        const float4 e24 = *reinterpret_cast<const float4*>(&s.E[2][o][pg * 4]);
+        const float e0[4] = {e04.x, e04.y, e04.z, e04.w};
+        const float e1[4] = {e14.x, e14.y, e14.z, e14.w};
+        const float e2[4] = {e24.x, e24.y, e24.z, e24.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          const float w = wv[a];
+          du_rg[a] = fmaf(w * W1[a][c], kernel_grad_f32<METHOD>(u0[a], chi, clo, inv_s2, e0[a]), du_rg[a]);
+          du_rb[a] = fmaf(w * (V0[a][c] + W2[a][c]), kernel_grad_f32<METHOD>(u1[a], chi, clo, inv_s2, e1[a]), du_rb[a]);
+          du_gb[a] = fmaf(w * V12[a][c], kernel_grad_f32<METHOD>(u2[a], chi, clo, inv_s2, e2[a]), du_gb[a]);
+          if (INTENSITY) d_iy[a] = fmaf(e0[a], W1[a][c], fmaf(e1[a], W2[a][c], d_iy[a]));
+        }
+      }
+    }
+    // reduce over the 16 output groups (lanes with the same lane>>4)
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        du_rg[a] += __shfl_xor_sync(0xffffffffu, du_rg[a], o);
+        du_rb[a] += __shfl_xor_sync(0xffffffffu, du_rb[a], o);
+        du_gb[a] += __shfl_xor_sync(0xffffffffu, du_gb[a], o);
+        if (INTENSITY) d_iy[a] += __shfl_xor_sync(0xffffffffu, d_iy[a], o);
+      }
+    }
+    if (og == 0) {
+      float* out = gP + (long long)b * 3 * g.N;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int pl = pg * 4 + a, p = p0 + pl;
+        if (p < g.N) {
+          const float r = s.Pix[0][pl], gg = s.Pix[1][pl], bb = s.Pix[2][pl];
+          // u_RG = L_R - L_G, u_RB = L_R - L_B, u_GB = L_G - L_B ; dL/dI = 1/(I+eps)
+          float dr = (du_rg[a] + du_rb[a]) / (r + kEps);
+          float dg = (du_gb[a] - du_rg[a]) / (gg + kEps);
+          float db = (-du_rb[a] - du_gb[a]) / (bb + kEps);
+          if (INTENSITY) {
+            const float q = d_iy[a] / s.W[pl];      // dIy/dI = I/Iy
+            dr = fmaf(q, r, dr); dg = fmaf(q, gg, dg); db = fmaf(q, bb, db);
+          }
+          out[p] = dr; out[g.N + p] = dg; out[2 * g.N + p] = db;
+        }
+      }
+    }
+  }
+}
+
+// ========================================================= generic path =====
+// One thread per pixel; G of the current (image, channel) in shared memory,
+// soft-binning kernels and their derivatives in float64 as the reference's
+// autograd does.  Slow but general (any h <= 128, boundaries, green_only).
+constexpr int kGBThreads = 64;
+
+__device__ __forceinline__ double kernel_grad_f64(float u, double c, int method, double sigma2,
+                                                  double k) {
+  const double d = (double)u - c;
+  const double w = -2.0 * d / sigma2 * k;
+  return method == HG_METHOD_INVERSE_QUADRATIC ? w * k : w;
+}
+
+__global__ void __launch_bounds__(kGBThreads)
+hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const HistTables t,
+                        const float* __restrict__ Graw, float* __restrict__ gP) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int h = g.h;
+  float* sG = reinterpret_cast<float*>(smem_raw);            // [h][h]
+  float* sKv = sG + h * h;                                    // [h][threads]
+  float* sS = sKv + h * kGBThreads;                           // [h][threads]
+  __shared__ double sC[kMaxBins];
+
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int p = blockIdx.x * kGBThreads + tid;
+  const bool valid = p < g.N;
+  for (int i = tid; i < kMaxBins; i += kGBThreads) sC[i] = t.c[i];
+
+  float r = 0.f, gg = 0.f, bb = 0.f, lr = 0.f, lg = 0.f, lb = 0.f, w = 0.f;
+  if (valid) {
+    load_pixel(x, g, t, b, p, r, gg, bb);
+    const PixelProj q = project_pixel(r, gg, bb, g.intensity != 0);
+    w = q.iy;
+    lr = log_f32(__fadd_rn(r, kEps)); lg = log_f32(__fadd_rn(gg, kEps)); lb = log_f32(__fadd_rn(bb, kEps));
+  }
+  float dl[3] = {0.f, 0.f, 0.f};
+  float d_iy = 0.f;
+
+  for (int cc = 0; cc < g.nc; ++cc) {
+    const int ch = g.green_only ? 1 : cc;
+    __syncthreads();
+    const float* Gc = Graw + ((long long)b * g.nc + cc) * (h * h);
+    for (int e = tid; e < h * h; e += kGBThreads) sG[e] = Gc[e];
+    __syncthreads();
+    float u, v;
+    if (ch == 0) { u = __fadd_rn(lr, -lg); v = __fadd_rn(lr, -lb); }
+    else if (ch == 1) { u = __fadd_rn(lg, -lr); v = __fadd_rn(lg, -lb); }
+    else { u = __fadd_rn(lb, -lr); v = __fadd_rn(lb, -lg); }
+    for (int j = 0; j < h; ++j) {
+      sKv[j * kGBThreads + tid] = kernel_f64(v, sC[j], g.method, g.sigma2, g.thr_half);
+      sS[j * kGBThreads + tid] = 0.f;
+    }
+    float du = 0.f;
+    for (int i = 0; i < h; ++i) {
+      const float ku = kernel_f64(u, sC[i], g.method, g.sigma2, g.thr_half);
+      const float a = __fmul_rn(w, ku);
+      float ti = 0.f;
+      for (int j = 0; j < h; ++j) {
+        const float gij = sG[i * h + j];
+        ti = fmaf(gij, sKv[j * kGBThreads + tid], ti);
+        sS[j * kGBThreads + tid] = fmaf(a, gij, sS[j * kGBThreads + tid]);
+      }
+      d_iy = fmaf(ku, ti, d_iy);
+      du = fmaf(w * ti, (float)kernel_grad_f64(u, sC[i], g.method, g.sigma2, (double)ku), du);
+    }
+    float dv = 0.f;
+    for (int j = 0; j < h; ++j)
+      dv = fmaf(sS[j * kGBThreads + tid],
+                (float)kernel_grad_f64(v, sC[j], g.method, g.sigma2,
+                                       (double)sKv[j * kGBThreads + tid]), dv);
+    const int ia = ch == 0 ? 1 : 0;            // u-partner
+    const int ib = ch == 2 ? 1 : 2;            // v-partner
+    dl[ch] += du + dv;
+    dl[ia] -= du;
+    dl[ib] -= dv;
+  }
+  if (valid) {
+    float dr = dl[0] / (r + kEps), dg = dl[1] / (gg + kEps), db = dl[2] / (bb + kEps);
+    if (g.intensity) {
+      const float q = d_iy / w;
+      dr = fmaf(q, r, dr); dg = fmaf(q, gg, dg); db = fmaf(q, bb, db);
+    }
+    float* out = gP + (long long)b * 3 * g.N;
+    out[p] = dr; out[g.N + p] = dg; out[2 * g.N + p] = db;
+  }
+}
+
+// ============================================================== adjoint =====
+// grad_x[b,c,y,x] for every input element (c >= 3 -> 0).
+__global__ void __launch_bounds__(256)
+hist_bwd_adjoint_kernel(const float* __restrict__ x, const HistGeom g, const HistTables t,
+                        const float* __restrict__ gP, float* __restrict__ grad_x) {
+  const long long total = (long long)g.C * g.H * g.W;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int b = blockIdx.y;
+  const int c = (int)(e / ((long long)g.H * g.W));
+  const int rem = (int)(e - (long long)c * g.H * g.W);
+  const int y = rem / g.W, xx = rem - y * g.W;
+  const long long off = (long long)b * g.sb + (long long)c * g.sc + (long long)y * g.sh +
+                        (long long)xx * g.sw;
+  float v = 0.f;
+  if (c < 3) {
+    const float xv = x[off];
+    if (xv >= 0.f && xv <= 1.f) {              // torch.clamp backward mask (inclusive)
+      const float* gp = gP + ((long long)b * 3 + c) * g.N;
+      if (g.mode == kNone) {
+        v = gp[y * g.W + xx];
+      } else if (g.mode == kSampling) {
+        // rows[i] = trunc(i*H/h) is non-decreasing; collect every i with rows[i]==y
+        int i0 = (int)floorf((float)y * (float)g.h / (float)g.H) - 1;
+        int j0 = (int)floorf((float)xx * (float)g.h / (float)g.W) - 1;
+        if (i0 < 0) i0 = 0;
+        if (j0 < 0) j0 = 0;
+        for (int i = i0; i < g.h && t.rows[i] <= y; ++i) {
+          if (t.rows[i] != y) continue;
+          for (int j = j0; j < g.h && t.cols[j] <= xx; ++j)
+            if (t.cols[j] == xx) v += gp[i * g.OW + j];
+        }
+      } else {
+        int oy_lo = (int)floorf(((float)y - 0.5f) / g.scale_h - 0.5f) - 1;
+        int oy_hi = (int)ceilf(((float)y + 1.5f) / g.scale_h - 0.5f) + 1;
+        int ox_lo = (int)floorf(((float)xx - 0.5f) / g.scale_w - 0.5f) - 1;
+        int ox_hi = (int)ceilf(((float)xx + 1.5f) / g.scale_w - 0.5f) + 1;
+        if (oy_lo < 0) oy_lo = 0;
+        if (ox_lo < 0) ox_lo = 0;
+        if (oy_hi > g.OH - 1) oy_hi = g.OH - 1;
+        if (ox_hi > g.OW - 1) ox_hi = g.OW - 1;
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+          int y0, y1; float ly0, ly1;
+          bilinear_taps(g.scale_h, oy, g.H, y0, y1, ly0, ly1);
+          const float wy = (y0 == y ? ly0 : 0.f) + (y1 == y ? ly1 : 0.f);
+          if (wy == 0.f) continue;
+          for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+            int x0, x1; float lx0, lx1;
+            bilinear_taps(g.scale_w, ox, g.W, x0, x1, lx0, lx1);
+            const float wx = (x0 == xx ? lx0 : 0.f) + (x1 == xx ? lx1 : 0.f);
+            if (wx != 0.f) v = fmaf(wy * wx, gp[oy * g.OW + ox], v);
+          }
+        }
+      }
+    }
+  }
+  grad_x[off] = v;
+}
+
+__global__ void zero_strided_kernel(const HistGeom g, float* __restrict__ grad_x) {
+  const long long total = (long long)g.C * g.H * g.W;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int b = blockIdx.y;
+  const int c = (int)(e / ((long long)g.H * g.W));
+  const int rem = (int)(e - (long long)c * g.H * g.W);
+  const int y = rem / g.W, xx = rem - y * g.W;
+  grad_x[(long long)b * g.sb + (long long)c * g.sc + (long long)y * g.sh + (long long)xx * g.sw] = 0.f;
+}
+
+// ============================================================ host side =====
+struct BwdPlan {
+  bool fast;
+  int chunks, E;
+  size_t off_G, off_gP, total;
+};
+
+static BwdPlan make_bwd_plan(const HistGeom& g, const hg_hist_params* p) {
+  BwdPlan pl;
+  pl.fast = hist_fast_path(g, p);
+  pl.E = g.nc * g.h * g.h;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int tiles = (g.N + kBP - 1) / kBP;
+  int want = g.B > 0 ? (2 * sms) / g.B : 1;
+  if (want < 1) want = 1;
+  int max_chunks = tiles / 2;
+  if (max_chunks < 1) max_chunks = 1;
+  pl.chunks = want < max_chunks ? want : max_chunks;
+  size_t off = 0;
+  pl.off_G = off;  off = align_up(off + sizeof(float) * (size_t)g.B * pl.E, 256);
+  pl.off_gP = off; off = align_up(off + sizeof(float) * (size_t)g.B * 3 * g.N, 256);
+  pl.total = off;
+  return pl;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" size_t hg_hist_bwd_workspace_bytes(const hg_hist_params* p) {
+  HistGeom g;
+  if (make_hist_geom(p, &g, nullptr)) return 0;
+  return make_bwd_plan(g, p).total;
+}
+
+extern "C" int hg_hist_bwd(const float* x, const hg_hist_params* p, const float* hist,
+                           const float* hist_sum, const float* grad_hist, float* grad_x,
+                           void* ws, size_t ws_bytes, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  HistGeom g;
+  HistTables t;
+  int rc = make_hist_geom(p, &g, &t);
+  if (rc) return rc;
+  if (g.B == 0) return 0;
+  if (!x || !hist || !hist_sum || !grad_hist || !grad_x)
+    return set_error(HG_EINVAL, "null tensor pointer");
+  const long long per_img = (long long)g.C * g.H * g.W;
+  dim3 egrid((unsigned)((per_img + 255) / 256), g.B);
+  if (g.method == HG_METHOD_THRESHOLDING) {     // comparison op: no gradient
+    zero_strided_kernel<<<egrid, 256, 0, stream>>>(g, grad_x);
+    HG_LAUNCH_OK("zero_strided_kernel");
+    return 0;
+  }
+  const BwdPlan pl = make_bwd_plan(g, p);
+  if (!ws || ws_bytes < pl.total)
+    return set_error(HG_EWS, "workspace too small: %zu < %zu", ws_bytes, pl.total);
+  char* w = (char*)ws;
+  float* G = (float*)(w + pl.off_G);
+  float* gP = (float*)(w + pl.off_gP);
+
+  hist_bwd_prep_kernel<<<g.B, 1024, 0, stream>>>(hist, hist_sum, grad_hist, pl.E, g.h,
+                                                pl.fast ? 1 : 0, G);
+  HG_LAUNCH_OK("hist_bwd_prep_kernel");
+
+  if (pl.fast) {
+    const size_t smem = sizeof(BwdSmem);
+    dim3 grid(pl.chunks, g.B);
+    const bool iq = g.method == HG_METHOD_INVERSE_QUADRATIC;
+#define HG_BWD_LAUNCH(M, I)                                                                  \
+    do {                                                                                      \
+      HG_CUDA_OK(cudaFuncSetAttribute(hist_bwd_fast_kernel<M, I>,                             \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      hist_bwd_fast_kernel<M, I><<<grid, kBThreads, smem, stream>>>(x, g, t, G, gP, pl.chunks); \
+    } while (0)
+    if (iq && g.intensity) HG_BWD_LAUNCH(HG_METHOD_INVERSE_QUADRATIC, true);
+    else if (iq) HG_BWD_LAUNCH(HG_METHOD_INVERSE_QUADRATIC, false);
+    else if (g.intensity) HG_BWD_LAUNCH(HG_METHOD_RBF, true);
+    else HG_BWD_LAUNCH(HG_METHOD_RBF, false);
+#undef HG_BWD_LAUNCH
+    HG_LAUNCH_OK("hist_bwd_fast_kernel");
+  } else {
+    const size_t smem = sizeof(float) * ((size_t)g.h * g.h + 2 * (size_t)g.h * kGBThreads);
+    HG_CUDA_OK(cudaFuncSetAttribute(hist_bwd_generic_kernel,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((g.N + kGBThreads - 1) / kGBThreads, g.B);
+    hist_bwd_generic_kernel<<<grid, kGBThreads, smem, stream>>>(x, g, t, G, gP);
+    HG_LAUNCH_OK("hist_bwd_generic_kernel");
+  }
+  hist_bwd_adjoint_kernel<<<egrid, 256, 0, stream>>>(x, g, t, gP, grad_x);
+  HG_LAUNCH_OK("hist_bwd_adjoint_kernel");
+  return 0;
+}

@@ -1,0 +1,124 @@
+/*
+ * histogan_b200.h -- C ABI of libhistogan_b200.so (sm_100a CUDA kernels for the
+ * HistoGAN training hot path).
+ *
+ * The reference (mahmoudnafifi/HistoGAN) is pure Python/PyTorch: it has no FFI
+ * of its own, so this header DEFINES the boundary.  Every entry point cites the
+ * reference code it replaces (paths relative to the reference repo root); the
+ * Python classes in histogan_b200/ (same names / constructor kwargs / forward
+ * signatures as the reference classes) are thin callers of these functions via
+ * ctypes.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless the name ends in _host;
+ *    tensors are float32, owned by the caller, never retained;
+ *  - every call is asynchronous on `stream` (a cudaStream_t / CUstream);
+ *  - return value: 0 on success, otherwise a negative HG_E* code or a positive
+ *    cudaError_t; hg_last_error() returns a thread-local message;
+ *  - `ws` is a caller-provided scratch buffer of at least the size reported by
+ *    the matching *_workspace_bytes() call (16-byte aligned);
+ *  - no hidden allocations, no host synchronisation.
+ */
+#ifndef HISTOGAN_B200_H_
+#define HISTOGAN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HG_ABI_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define HG_EINVAL   (-1)   /* bad argument (message in hg_last_error)          */
+#define HG_ENOSUP   (-2)   /* configuration not supported by the CUDA path     */
+#define HG_EWS      (-3)   /* workspace too small                              */
+#define HG_EARCH    (-4)   /* device is not sm_100                             */
+
+typedef void* hg_stream_t;             /* cudaStream_t */
+
+int         hg_abi_version(void);
+const char* hg_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process
+ * (bench.py reports the per-step delta as "gpu_launches").                  */
+uint64_t    hg_launch_count(void);
+/* 0 when device `dev` can run the kernels (compute capability 10.x). */
+int         hg_device_check(int dev);
+
+/* ------------------------------------------------------------------------ *
+ * RGB-uv histogram block
+ *   replaces histogram_classes/RGBuvHistBlock.py:75-228 (forward) and the
+ *   autograd backward PyTorch derives from it.
+ * ------------------------------------------------------------------------ */
+
+enum { HG_RESIZE_INTERPOLATION = 0, HG_RESIZE_SAMPLING = 1 };
+enum { HG_METHOD_THRESHOLDING = 0, HG_METHOD_RBF = 1, HG_METHOD_INVERSE_QUADRATIC = 2 };
+
+typedef struct hg_hist_params {
+  /* input image batch x: (B, C>=3, H, W) float32, element strides sb/sc/sh/sw */
+  int32_t B, C, H, W;
+  int64_t sb, sc, sh, sw;
+  /* constructor arguments of RGBuvHistBlock (RGBuvHistBlock.py:29-73) */
+  int32_t h;                /* bins per axis (default 64)                     */
+  int32_t insz;             /* resize when H > insz or W > insz (default 150) */
+  int32_t resizing;         /* HG_RESIZE_*                                     */
+  int32_t method;           /* HG_METHOD_*                                     */
+  double  sigma;            /* kernel width (default 0.02)                    */
+  double  lo, hi;           /* sorted hist_boundary (default -3, 3)           */
+  int32_t intensity_scale;  /* bool                                            */
+  int32_t green_only;       /* bool: output has 1 channel (the G histogram)   */
+} hg_hist_params;
+
+/* number of pixels per image that enter the histogram after the optional
+ * resize (RGBuvHistBlock.py:77-95): H*W, insz*insz or h*h.  <0 on error. */
+int64_t hg_hist_num_pixels(const hg_hist_params* p);
+
+size_t  hg_hist_fwd_workspace_bytes(const hg_hist_params* p);
+size_t  hg_hist_bwd_workspace_bytes(const hg_hist_params* p);
+
+/* Forward.  Outputs (nc = green_only ? 1 : 3):
+ *   hist      (B, nc, h, h)  normalised histogram  == RGBuvHistBlock.forward(x)
+ *   hist_sum  (B)            per-image sum of the un-normalised histogram
+ *                            (saved for backward; RGBuvHistBlock.py:225-226)   */
+int hg_hist_fwd(const float* x, const hg_hist_params* p,
+                float* hist, float* hist_sum,
+                void* ws, size_t ws_bytes, hg_stream_t stream);
+
+/* Backward: grad_x (same geometry / strides as x, fully written, channels >= 3
+ * get zeros) = d<grad_hist, hist>/dx, i.e. what autograd produces for the
+ * reference forward given the upstream gradient grad_hist (B, nc, h, h).
+ * method == thresholding has no gradient: grad_x is zero-filled (as autograd
+ * does for the comparison op, RGBuvHistBlock.py:126-127).                       */
+int hg_hist_bwd(const float* x, const hg_hist_params* p,
+                const float* hist, const float* hist_sum,
+                const float* grad_hist, float* grad_x,
+                void* ws, size_t ws_bytes, hg_stream_t stream);
+
+/* Test/debug hooks used by the parity tests to separate kernel arithmetic from
+ * libm differences: the pre-processed pixels (clamp + resize + first 3
+ * channels; RGBuvHistBlock.py:76-99) as (B,3,N) and the float32 natural log
+ * the kernels use.                                                            */
+int hg_hist_preprocess(const float* x, const hg_hist_params* p, float* pixels,
+                       hg_stream_t stream);
+int hg_debug_logf(const float* in, float* out, int64_t n, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Hellinger histogram loss
+ *   replaces histoGAN/histoGAN.py:957-960 and ReHistoGAN/rehistoGAN.py:1011-1014
+ *     loss = alpha * (1/sqrt(2)) * sqrt(sum((sqrt(T) - sqrt(H))^2)) / B
+ * ------------------------------------------------------------------------ */
+
+/* loss, q: device scalars (q = the sum under the square root, saved for bwd). */
+int hg_hellinger_fwd(const float* target, const float* hist, int64_t numel, int32_t B,
+                     float alpha, float* loss, float* q, hg_stream_t stream);
+/* grad_hist / grad_target (either may be NULL) = grad_loss[0] * dloss/d(.)    */
+int hg_hellinger_bwd(const float* target, const float* hist, int64_t numel, int32_t B,
+                     float alpha, const float* q, const float* grad_loss,
+                     float* grad_hist, float* grad_target, hg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HISTOGAN_B200_H_ */

@@ -1,0 +1,102 @@
+"""Parity metrics and tolerances shared by the tests (see DESIGN.md "precision").
+
+Tolerances (north_star: histogram / loss within 1e-5 relative fp32):
+
+* STRICT (kernel arithmetic only: oracle fed the same float32 logs / resized
+  pixels the kernels used): max element-wise relative error <= 1e-5.
+* END-TO-END against the CPU oracle / reference goldens: Frobenius relative
+  <= 1e-6, loss relative <= 1e-5, 99.9 % of the elements within 1e-5 and every
+  element within 1e-4.  The element-wise maximum cannot be pushed below ~2e-5
+  by ANY implementation: torch's CPU logf (SLEEF) and a correctly rounded logf
+  disagree by 1 ulp on ~0.1 % of the pixels, and one such pixel moves the bins
+  it dominates by ~1e-5 (oracle-only experiment in DESIGN.md).
+* gradients: max |delta| <= 1e-3 * max |grad|, median element-wise relative
+  <= 1e-5 (the reference's own fp32 backward noise).
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+STRICT_MAX_REL = 1e-5
+E2E_FRO_REL = 1e-6
+E2E_MAX_REL = 1e-4
+E2E_P999_REL = 1e-5
+LOSS_REL = 1e-5
+GRAD_MAX_OVER_MAX = 1e-3
+GRAD_MEDIAN_REL = 1e-5
+
+
+def rel_err(a: torch.Tensor, ref: torch.Tensor, atol_frac=1e-9):
+    """element-wise |a-ref| / max(|ref|, atol_frac*max|ref|) (double)."""
+    a = a.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    floor = atol_frac * ref.abs().max().clamp_min(1e-300)
+    return (a - ref).abs() / ref.abs().clamp_min(floor)
+
+
+def fro_rel(a, ref):
+    a = a.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    return ((a - ref).norm() / ref.norm().clamp_min(1e-300)).item()
+
+
+def assert_hist_strict(a, ref, what=""):
+    r = rel_err(a, ref)
+    assert r.max().item() <= STRICT_MAX_REL, f"{what}: strict max rel {r.max().item():.3e}"
+
+
+def assert_hist_e2e(a, ref, what="", atol_frac=1e-9):
+    r = rel_err(a, ref, atol_frac)
+    fr = fro_rel(a, ref)
+    p999 = torch.quantile(r.flatten()[:: max(1, r.numel() // 1_000_000)], 0.999).item()
+    assert fr <= E2E_FRO_REL, f"{what}: Frobenius rel {fr:.3e}"
+    assert p999 <= E2E_P999_REL, f"{what}: 99.9th percentile rel {p999:.3e}"
+    assert r.max().item() <= E2E_MAX_REL, f"{what}: max rel {r.max().item():.3e}"
+    return dict(fro=fr, p999=p999, max=r.max().item())
+
+
+def assert_loss(a, ref, what=""):
+    a = float(a); ref = float(ref)
+    assert abs(a - ref) <= LOSS_REL * abs(ref), f"{what}: loss {a!r} vs {ref!r}"
+
+
+def assert_grad(a, ref, what=""):
+    a = a.detach().double().cpu()
+    ref = ref.detach().double().cpu()
+    nan = torch.isnan(ref)
+    if nan.any():   # the reference itself produces NaN (e.g. RBF + Hellinger: sqrt'(0))
+        assert torch.equal(torch.isnan(a), nan), f"{what}: NaN pattern differs from the reference"
+        if nan.all():
+            return dict(all_nan=True)
+        a, ref = a[~nan], ref[~nan]
+    gmax = ref.abs().max().item()
+    dmax = (a - ref).abs().max().item()
+    assert dmax <= GRAD_MAX_OVER_MAX * gmax, f"{what}: max|dgrad| {dmax:.3e} vs max|grad| {gmax:.3e}"
+    nz = ref != 0
+    assert torch.equal(a != 0, nz) or ((a != 0) ^ nz).float().mean().item() < 1e-4, \
+        f"{what}: zero pattern differs"
+    if nz.any():
+        rel = ((a - ref).abs() / ref.abs().clamp_min(1e-300))[nz]
+        med = rel.median().item()
+        assert med <= GRAD_MEDIAN_REL, f"{what}: median rel {med:.3e}"
+    return dict(dmax_over_gmax=dmax / max(gmax, 1e-300))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    out = {k: z[k] for k in z.files}
+    out["kwargs"] = json.loads(str(out["kwargs"]))
+    for k in ("x", "target", "hist", "grad_x", "grad_x_lin"):
+        if k in out:
+            out[k] = torch.from_numpy(out[k])
+    out["loss"] = float(out["loss"])
+    out["alpha"] = float(out["alpha"])
+    return out
+
+
+def golden_names(prefix):
+    return sorted(f[:-4] for f in os.listdir(GOLDEN_DIR) if f.startswith(prefix) and f.endswith(".npz"))

@@ -1,0 +1,67 @@
+"""GPU, BASELINE.json sizes (config 2: 32x3x256x256, h=64): size-independent
+properties instead of the (slow) CPU oracle, plus one oracle-checked image."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import hist_oracle as ho
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("insz", [256, 150])
+def test_full_size_properties(insz, cuda_device):
+    from histogan_b200 import RGBuvHistBlock, hellinger_loss
+    B, S = 32, 256
+    x = torch.relu(torch.randn(B, 3, S, S, generator=torch.Generator().manual_seed(0)) * 0.5 + 0.3).cuda()
+    blk = RGBuvHistBlock(insz=insz)
+    h = blk(x)
+    assert h.shape == (B, 3, 64, 64)
+    assert torch.isfinite(h).all() and (h > 0).all()
+    s = h.sum(dim=(1, 2, 3))
+    assert (s - 1).abs().max().item() < 1e-4                       # normalisation
+    # batch independence: any sub-batch gives the same rows
+    h2 = blk(x[5:8])
+    assert parity.fro_rel(h2, h[5:8]) < 1e-6
+    # determinism
+    assert torch.equal(blk(x), h)
+    if insz == 256:
+        # pixel-permutation invariance (no resize path)
+        perm = torch.randperm(S * S, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+        xp = x[:2].reshape(2, 3, -1)[:, :, perm].reshape(2, 3, S, S)
+        assert parity.fro_rel(blk(xp), h[:2]) < 1e-6
+        # channel symmetry: swapping R and B swaps hist0/hist2 and transposes hist1
+        xs = x[:2].flip(1)
+        hs = blk(xs)
+        assert parity.fro_rel(hs[:, 0], h[:2, 2]) < 1e-6
+        assert parity.fro_rel(hs[:, 2], h[:2, 0]) < 1e-6
+        assert parity.fro_rel(hs[:, 1], h[:2, 1].transpose(1, 2)) < 1e-6
+    # one image against the CPU oracle, full resolution, with loss + grad
+    t = ho.synth_random_target(1, seed=2)
+    rh, rl, rg = ho.hist_loss_and_grad(x[:1].cpu(), t, 2.0, insz=insz)
+    xc = x[:1].clone().requires_grad_(True)
+    hc = blk(F.relu(xc))
+    loss = hellinger_loss(t.cuda(), hc, 2.0)
+    loss.backward()
+    parity.assert_hist_e2e(hc, rh, f"full-size insz={insz}")
+    parity.assert_loss(loss.item(), rl.item())
+    parity.assert_grad(xc.grad, rg, f"full-size grad insz={insz}")
+
+
+def test_gradient_is_directional_derivative(cuda_device):
+    """finite-difference check of the fused backward at full size (float32 FD, loose)."""
+    from histogan_b200 import RGBuvHistBlock, hellinger_loss
+    x = (torch.rand(2, 3, 256, 256, generator=torch.Generator().manual_seed(5)) * 0.8 + 0.1).cuda()
+    t = ho.synth_random_target(2, seed=6).cuda()
+    blk = RGBuvHistBlock(insz=256)
+    xg = x.clone().requires_grad_(True)
+    hellinger_loss(t, blk(xg), 2.0).backward()
+    d = torch.randn_like(x)
+    d = d / d.norm()
+    eps = 2e-2
+    lp = hellinger_loss(t, blk(x + eps * d), 2.0).item()
+    lm = hellinger_loss(t, blk(x - eps * d), 2.0).item()
+    fd = (lp - lm) / (2 * eps)
+    an = (xg.grad * d).sum().item()
+    assert abs(fd - an) <= 0.05 * abs(an) + 1e-6, (fd, an)
