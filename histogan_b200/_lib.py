@@ -31,6 +31,20 @@ class HistParams(C.Structure):
     ]
 
 
+class ConvParams(C.Structure):
+    """struct hg_conv_params."""
+    _fields_ = [("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("Cin", C.c_int32),
+                ("Cout", C.c_int32), ("KH", C.c_int32), ("KW", C.c_int32), ("stride", C.c_int32),
+                ("pad", C.c_int32), ("OH", C.c_int32), ("OW", C.c_int32)]
+
+
+class ConvEpilogue(C.Structure):
+    """struct hg_conv_epilogue."""
+    _fields_ = [("scale", C.c_void_p), ("bias", C.c_void_p), ("noise", C.c_void_p),
+                ("noise_w", C.c_void_p), ("noise_b", C.c_void_p), ("residual", C.c_void_p),
+                ("noise_size", C.c_int32), ("flags", C.c_int32), ("lrelu_slope", C.c_float)]
+
+
 _SIGNATURES = {
     "hg_abi_version": (C.c_int, []),
     "hg_last_error": (C.c_char_p, []),
@@ -45,6 +59,10 @@ _SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "hg_hist_preprocess": (C.c_int, [C.c_void_p, C.POINTER(HistParams), C.c_void_p, C.c_void_p]),
     "hg_debug_logf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "hg_conv2d_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ConvParams),
+                                C.POINTER(ConvEpilogue), C.c_void_p]),
+    "hg_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_void_p]),
     "hg_hellinger_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "hg_hellinger_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,

@@ -1,0 +1,82 @@
+"""NHWC convolution primitives on the tcgen05 kernels (hg_conv2d_fwd).
+
+Tensors are float32 torch tensors in channels_last memory format: logically
+(B, C, H, W) like the reference, physically NHWC -- the layout the TMA boxes of
+the kernels walk.  These are raw (non-autograd) calls; the differentiable
+operators are built on top of them in ops.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+CONV_LRELU = 1
+CONV_ROUND_TF32 = 2
+
+
+def tf32_round(t: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest-even to TF32 (10-bit mantissa); torch-side twin of
+    hg::tf32_round used for small host-prepared tensors and in tests."""
+    i = t.contiguous().view(torch.int32)
+    r = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+    return r.view(torch.float32).view_as(t)
+
+
+def as_nhwc(x: torch.Tensor) -> torch.Tensor:
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
+    """hg_pack_conv_weight: OIHW -> [N][KH][KW][K] K-major TF32.  mode 1 = dgrad."""
+    lib = _lib.load()
+    _lib.require_cuda(w_oihw, "pack_weight")
+    w = w_oihw.detach().contiguous().float()
+    co, ci, kh, kw = w.shape
+    n, k = (ci, co) if mode else (co, ci)
+    out = torch.empty((n, kh, kw, k), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = lib.hg_pack_conv_weight(_lib.ptr(w), _lib.ptr(out), co, ci, kh, kw, int(mode),
+                                     _lib.current_stream_ptr(w.device))
+    _lib.check(rc, "hg_pack_conv_weight")
+    return out
+
+
+def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: int = 1, *,
+                scale=None, bias=None, noise=None, noise_w=None, noise_b=None, residual=None,
+                lrelu: bool = False, slope: float = 0.2, round_tf32: bool = False) -> torch.Tensor:
+    """y = epilogue(conv(x, w)); x (B,Cin,H,W) channels_last, w_packed [Cout][KH][KW][Cin].
+    Returns (B,Cout,OH,OW) channels_last."""
+    lib = _lib.load()
+    _lib.require_cuda(x, "conv2d_nhwc")
+    assert x.dtype == torch.float32 and x.dim() == 4
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    B, Cin, H, W = x.shape
+    Cout, KH, KW, Cin2 = w_packed.shape
+    assert Cin2 == Cin, (Cin2, Cin)
+    OH = (H + 2 * pad - KH) // stride + 1
+    OW = (W + 2 * pad - KW) // stride + 1
+    y = torch.empty((B, Cout, OH, OW), dtype=torch.float32, device=x.device,
+                    memory_format=torch.channels_last)
+    if residual is not None:
+        residual = as_nhwc(residual)
+        assert residual.shape == y.shape
+    p = _lib.ConvParams(B, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW)
+    flags = (CONV_LRELU if lrelu else 0) | (CONV_ROUND_TF32 if round_tf32 else 0)
+    keep = [t.contiguous() if t is not None else None for t in (scale, bias, noise, noise_w, noise_b)]
+    ep = _lib.ConvEpilogue(
+        keep[0].data_ptr() if keep[0] is not None else None,
+        keep[1].data_ptr() if keep[1] is not None else None,
+        keep[2].data_ptr() if keep[2] is not None else None,
+        keep[3].data_ptr() if keep[3] is not None else None,
+        keep[4].data_ptr() if keep[4] is not None else None,
+        residual.data_ptr() if residual is not None else None,
+        int(noise.shape[1]) if noise is not None else 0, flags, float(slope))
+    with torch.cuda.device(x.device):
+        rc = lib.hg_conv2d_fwd(_lib.ptr(x), _lib.ptr(w_packed), _lib.ptr(y), C.byref(p),
+                               C.byref(ep), _lib.current_stream_ptr(x.device))
+    _lib.check(rc, "hg_conv2d_fwd")
+    return y

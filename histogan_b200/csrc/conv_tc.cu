@@ -1,0 +1,348 @@
+// conv_tc.cu -- NHWC implicit-GEMM convolution on the 5th-gen tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM, operands staged by TMA).
+//
+// This one kernel is the dense contraction behind every conv of the StyleGAN2
+// style generator / discriminator of the reference:
+//   Conv2DMod.forward          histoGAN/histoGAN.py:420-440   (3x3 and 1x1, pad "same")
+//   DiscriminatorBlock convs   histoGAN/histoGAN.py:505-526   (3x3 s1, 3x3 s2, 1x1, bias)
+// and, with flipped/transposed weights, their input gradients.  The reference
+// materialises per-sample weights and runs a grouped conv (:423-437); here the
+// style modulation is applied to the ACTIVATIONS by the producer of `x`, the
+// weights are shared, and the demodulation is a per-(sample, out-channel) scale
+// in the epilogue -- algebraically identical (4e-7).
+//
+// GEMM view:  M = B*OH*OW (pixels), N = Cout, K = KH*KW*Cin.
+//   A tile: 128 pixels x 32 channels of ONE filter tap, fetched by a 4-D TMA box
+//           {32ch, TW, TH, TB} (TW*TH*TB = 128) at spatially shifted coordinates;
+//           out-of-bounds rows are zero-filled by TMA = the conv's zero padding.
+//   B tile: BLOCK_N out-channels x 32 channels of the same tap from the packed
+//           weight [Cout][KH*KW*Cin] (K-major).
+//   Both land in 128B-swizzled rows == the canonical K-major UMMA layout, so no
+//   thread ever touches operand data.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA
+// issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> fused
+// scale / bias / noise / LeakyReLU / residual -> NHWC global).
+#include "hg_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hg {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 32;                       // fp32 channels per k-block = 128 B rows
+constexpr int kABytes = kBlockM * kBlockK * 4;    // 16 KB
+constexpr int kConvThreads = 192;
+
+struct ConvArgs {
+  int B, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW;
+  int TB, TH, TW;                 // pixel tile (TB*TH*TW == 128)
+  int tiles_w, tiles_h;           // tiles per image row / column
+  int kc_per_tap;                 // Cin / 32
+  int flags;
+  float slope;
+  float* y;
+  const float* scale;             // [B][Cout]  demodulation          (or null)
+  const float* bias;              // [Cout]                            (or null)
+  const float* noise;             // [B][NS][NS] image noise           (or null)
+  const float* noise_w;           // [Cout]  to_noise Linear(1->Cout) weight
+  const float* noise_b;           // [Cout]  to_noise bias
+  const float* residual;          // NHWC like y, added after the activation (or null)
+  int noise_size;
+};
+
+template <int BLOCK_N, int STAGES>
+struct ConvSmem {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kConvThreads)
+conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
+                 const ConvArgs a) {
+  using SM = ConvSmem<BLOCK_N, STAGES>;
+  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * SM::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmx);
+    ptx::prefetch_tmap(&tmw);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      ptx::mbar_init(tmem_full_bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // tile coordinates
+  const int mt = blockIdx.x;
+  const int tw_i = mt % a.tiles_w;
+  const int th_i = (mt / a.tiles_w) % a.tiles_h;
+  const int tb_i = mt / (a.tiles_w * a.tiles_h);
+  const int ow0 = tw_i * a.TW, oh0 = th_i * a.TH, b0 = tb_i * a.TB;
+  const int n0 = blockIdx.y * BLOCK_N;
+  const int taps = a.KH * a.KW;
+  const int total_kb = taps * a.kc_per_tap;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int iw0 = ow0 * a.stride - a.pad, ih0 = oh0 * a.stride - a.pad;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int kh = tap / a.KW, kw = tap - kh * a.KW;
+        for (int kc = 0; kc < a.kc_per_tap; ++kc) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sA = base + stage * SM::kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
+          ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
+          ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Cin + kc * kBlockK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kBlockM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < total_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sA = ptx::smem_u32(base + stage * SM::kStageBytes);
+        const uint64_t a_desc = ptx::make_smem_desc(sA, 16, 1024, ptx::kLayoutSW128);
+        const uint64_t b_desc = ptx::make_smem_desc(sA + kABytes, 16, 1024, ptx::kLayoutSW128);
+#pragma unroll
+        for (int k = 0; k < kBlockK / 8; ++k) {
+          // advance 8 tf32 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
+          ptx::mma_tf32_ss(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                           (uint32_t)((kb | k) != 0));
+        }
+        ptx::tc_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      ptx::tc_commit(tmem_full_bar);                // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue --
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    const int tw = row % a.TW, th = (row / a.TW) % a.TH, tb = row / (a.TW * a.TH);
+    const int b = b0 + tb, oh = oh0 + th, ow = ow0 + tw;
+    const bool valid = b < a.B && oh < a.OH && ow < a.OW;
+    const long long pix = ((long long)b * a.OH + oh) * a.OW + ow;
+    float nz = 0.f;
+    if (a.noise && valid)                            // spatially transposed (histoGAN.py:466-467)
+      nz = a.noise[((long long)b * a.noise_size + ow) * a.noise_size + oh];
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+      ptx::tmem_ld_wait();
+      if (valid) {
+        const int n = n0 + c0;
+        float* yo = a.y + pix * a.Cout + n;
+        const float* ro = a.residual ? a.residual + pix * a.Cout + n : nullptr;
+        const float* sc = a.scale ? a.scale + (long long)b * a.Cout + n : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float t = __uint_as_float(v[j + e]);
+            if (sc) t *= __ldg(sc + j + e);
+            if (a.bias) t += __ldg(a.bias + n + j + e);
+            if (a.noise) t = fmaf(nz, __ldg(a.noise_w + n + j + e), t + __ldg(a.noise_b + n + j + e));
+            if (a.flags & HG_CONV_LRELU) t = t > 0.f ? t : t * a.slope;
+            if (ro) t += __ldg(ro + j + e);
+            if (a.flags & HG_CONV_ROUND_TF32) t = tf32_round(t);
+            o[e] = t;
+          }
+          *reinterpret_cast<float4*>(yo + j) = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------- weight packing kernel ----
+// OIHW parameter (state_dict layout of Conv2DMod.weight / nn.Conv2d.weight)
+//   -> [N][KH][KW][K] K-major, TF32-rounded.
+// mode 0 (forward):  N = Cout, K = Cin : out[co][kh][kw][ci] = w[co][ci][kh][kw]
+// mode 1 (dgrad):    N = Cin, K = Cout : out[ci][kh][kw][co] = w[co][ci][KH-1-kh][KW-1-kw]
+__global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout,
+                                   int Cin, int KH, int KW, int mode) {
+  const long long total = (long long)Cout * Cin * KH * KW;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int N = mode ? Cin : Cout, K = mode ? Cout : Cin;
+  const int k = (int)(e % K);
+  long long r = e / K;
+  const int kw = (int)(r % KW); r /= KW;
+  const int kh = (int)(r % KH); r /= KH;
+  const int n = (int)r;
+  (void)N;
+  float v;
+  if (mode == 0) v = w[(((long long)n * Cin + k) * KH + kh) * KW + kw];
+  else v = w[(((long long)k * Cin + n) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)];
+  out[e] = tf32_round(v);
+}
+
+// ------------------------------------------------------------ host side -----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_encodeTiled>(p);
+  }();
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                      const cuuint32_t* estr, CUtensorMapL2promotion promo) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return set_error(HG_EARCH, "cuTensorMapEncodeTiled not available from the driver");
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(ptr), dims,
+                  strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(HG_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
+                       int m_tiles, cudaStream_t stream) {
+  using SM = ConvSmem<BLOCK_N, STAGES>;
+  HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  dim3 grid(m_tiles, a.Cout / BLOCK_N);
+  conv_tf32_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
+  HG_LAUNCH_OK("conv_tf32_kernel");
+  return 0;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" int hg_pack_conv_weight(const float* w_oihw, float* w_packed, int32_t Cout, int32_t Cin,
+                                   int32_t KH, int32_t KW, int32_t mode, hg_stream_t stream_) {
+  if (!w_oihw || !w_packed) return set_error(HG_EINVAL, "null tensor pointer");
+  const long long total = (long long)Cout * Cin * KH * KW;
+  if (total <= 0) return set_error(HG_EINVAL, "empty weight");
+  pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      w_oihw, w_packed, Cout, Cin, KH, KW, mode);
+  HG_LAUNCH_OK("pack_weight_kernel");
+  return 0;
+}
+
+extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
+                             const hg_conv_params* p, const hg_conv_epilogue* ep,
+                             hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x || !w_packed || !y || !p) return set_error(HG_EINVAL, "null pointer");
+  if (p->B <= 0) return 0;
+  if (p->Cin % kBlockK != 0)
+    return set_error(HG_ENOSUP, "conv: Cin=%d must be a multiple of %d for the tensor-core path",
+                     p->Cin, kBlockK);
+  if (p->Cout % 32 != 0)
+    return set_error(HG_ENOSUP, "conv: Cout=%d must be a multiple of 32 for the tensor-core path",
+                     p->Cout);
+  if (p->stride < 1 || p->stride > 2) return set_error(HG_ENOSUP, "conv: stride must be 1 or 2");
+  const int OH = (p->H + 2 * p->pad - p->KH) / p->stride + 1;
+  const int OW = (p->W + 2 * p->pad - p->KW) / p->stride + 1;
+  if (OH != p->OH || OW != p->OW)
+    return set_error(HG_EINVAL, "conv: OH/OW (%d,%d) inconsistent with geometry (%d,%d)", p->OH,
+                     p->OW, OH, OW);
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) |
+       reinterpret_cast<uintptr_t>(y)) & 15)
+    return set_error(HG_EINVAL, "conv: pointers must be 16-byte aligned");
+
+  ConvArgs a{};
+  a.B = p->B; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout;
+  a.KH = p->KH; a.KW = p->KW; a.stride = p->stride; a.pad = p->pad; a.OH = OH; a.OW = OW;
+  // pixel tile: as wide as the row allows (<= 16), then rows, then images
+  int TW = 1; while (TW < 16 && TW < OW) TW <<= 1;
+  int TH = 1; while (TW * TH < kBlockM && TH < OH) TH <<= 1;
+  int TB = kBlockM / (TW * TH);
+  a.TW = TW; a.TH = TH; a.TB = TB;
+  a.tiles_w = (OW + TW - 1) / TW;
+  a.tiles_h = (OH + TH - 1) / TH;
+  const int tiles_b = (p->B + TB - 1) / TB;
+  const int m_tiles = a.tiles_w * a.tiles_h * tiles_b;
+  a.kc_per_tap = p->Cin / kBlockK;
+  a.flags = ep ? ep->flags : 0;
+  a.slope = ep ? ep->lrelu_slope : 0.2f;
+  a.y = y;
+  a.scale = ep ? ep->scale : nullptr;
+  a.bias = ep ? ep->bias : nullptr;
+  a.noise = ep ? ep->noise : nullptr;
+  a.noise_w = ep ? ep->noise_w : nullptr;
+  a.noise_b = ep ? ep->noise_b : nullptr;
+  a.noise_size = ep ? ep->noise_size : 0;
+  a.residual = ep ? ep->residual : nullptr;
+  if (a.noise && (!a.noise_w || !a.noise_b || a.noise_size < OH || a.noise_size < OW))
+    return set_error(HG_EINVAL, "conv: noise needs noise_w/noise_b and noise_size >= OH,OW");
+
+  // x: NHWC as a 4-D tensor {C, W, H, B}; strided boxes implement stride-2 convs
+  alignas(64) CUtensorMap tmx, tmw;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {(cuuint64_t)p->Cin * 4, (cuuint64_t)p->W * p->Cin * 4,
+                             (cuuint64_t)p->H * p->W * p->Cin * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(TW * p->stride),
+                         (cuuint32_t)(TH * p->stride), (cuuint32_t)TB};
+    cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
+    int rc = encode_map(&tmx, x, 4, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+  }
+  const int Ktot = p->KH * p->KW * p->Cin;
+  const int BN = (p->Cout % 128 == 0) ? 128 : (p->Cout % 64 == 0 ? 64 : 32);
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
+    cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    int rc = encode_map(&tmw, w_packed, 2, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  if (BN == 128) return launch_conv<128, 3>(tmx, tmw, a, m_tiles, stream);
+  if (BN == 64) return launch_conv<64, 4>(tmx, tmw, a, m_tiles, stream);
+  return launch_conv<32, 4>(tmx, tmw, a, m_tiles, stream);
+}

@@ -97,10 +97,13 @@ __device__ __forceinline__ float clamp01(float v) {
   return v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
 }
 
-// source index of F.interpolate(mode='bilinear', align_corners=False)
+// source index of F.interpolate(mode='bilinear', align_corners=False).  The FMA
+// placement reproduces torch's CPU kernel bit-for-bit (verified against
+// F.interpolate for 5 geometries, DESIGN.md "precision"): a resized pixel that is
+// off by one ulp moves its log by ~1e-7 and the bins it dominates by ~1e-5.
 __device__ __forceinline__ void bilinear_taps(float scale, int dst, int in_size,
                                               int& i0, int& i1, float& l0, float& l1) {
-  float src = __fadd_rn(__fmul_rn(scale, __fadd_rn((float)dst, 0.5f)), -0.5f);
+  float src = fmaf(scale, __fadd_rn((float)dst, 0.5f), -0.5f);
   src = src < 0.f ? 0.f : src;
   i0 = (int)src;
   if (i0 > in_size - 1) i0 = in_size - 1;
@@ -129,9 +132,9 @@ __device__ __forceinline__ void load_pixel(const float* __restrict__ x, const Hi
       const float v01 = clamp01(__ldg(xc + y0 * g.sh + x1 * g.sw));
       const float v10 = clamp01(__ldg(xc + y1 * g.sh + x0 * g.sw));
       const float v11 = clamp01(__ldg(xc + y1 * g.sh + x1 * g.sw));
-      const float top = __fadd_rn(__fmul_rn(lx0, v00), __fmul_rn(lx1, v01));
-      const float bot = __fadd_rn(__fmul_rn(lx0, v10), __fmul_rn(lx1, v11));
-      v[c] = __fadd_rn(__fmul_rn(ly0, top), __fmul_rn(ly1, bot));
+      const float top = fmaf(v00, lx0, __fmul_rn(v01, lx1));
+      const float bot = fmaf(v10, lx0, __fmul_rn(v11, lx1));
+      v[c] = fmaf(top, ly0, __fmul_rn(bot, ly1));
     }
   } else {
     int y, xx;

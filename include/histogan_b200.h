@@ -118,6 +118,52 @@ int hg_hellinger_bwd(const float* target, const float* hist, int64_t numel, int3
                      float alpha, const float* q, const float* grad_loss,
                      float* grad_hist, float* grad_target, hg_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * NHWC convolution on tcgen05 tensor cores (TF32 operands, fp32 accumulate)
+ *   the dense contraction of Conv2DMod.forward (histoGAN/histoGAN.py:420-440),
+ *   RGBBlock's 1x1 conv (:375,382), and the DiscriminatorBlock convs (:505-526);
+ *   with mode-1 packed weights also their input gradients.
+ *   x: (B,H,W,Cin) float32 NHWC, already TF32-rounded by its producer;
+ *   w_packed: [Cout][KH][KW][Cin] from hg_pack_conv_weight; y: (B,OH,OW,Cout).
+ * ------------------------------------------------------------------------ */
+#define HG_CONV_LRELU       1   /* LeakyReLU(slope) after scale/bias/noise       */
+#define HG_CONV_ROUND_TF32  2   /* round the stored result to TF32 (RN-even)     */
+
+typedef struct hg_conv_params {
+  int32_t B, H, W, Cin;
+  int32_t Cout, KH, KW, stride, pad;
+  int32_t OH, OW;                       /* (H + 2 pad - KH)/stride + 1, checked   */
+} hg_conv_params;
+
+/* Fused epilogue, applied in this order to the accumulator of output (b,oh,ow,co):
+ *   v *= scale[b][co]                                  demodulation   (:427-429)
+ *   v += bias[co]                                      nn.Conv2d bias (:506-518)
+ *   v += noise[b][ow][oh] * noise_w[co] + noise_b[co]  to_noise Linear + the
+ *                                                      spatial transpose (:465-467)
+ *   v  = LeakyReLU(v)                                  if HG_CONV_LRELU (:471,476)
+ *   v += residual[b][oh][ow][co]                       DiscriminatorBlock (:524)
+ * Any pointer may be NULL to skip its step.                                      */
+typedef struct hg_conv_epilogue {
+  const float* scale;
+  const float* bias;
+  const float* noise;      /* (B, noise_size, noise_size) */
+  const float* noise_w;
+  const float* noise_b;
+  const float* residual;
+  int32_t noise_size;
+  int32_t flags;
+  float   lrelu_slope;
+} hg_conv_epilogue;
+
+int hg_conv2d_fwd(const float* x, const float* w_packed, float* y, const hg_conv_params* p,
+                  const hg_conv_epilogue* ep, hg_stream_t stream);
+
+/* OIHW parameter -> packed K-major TF32 weight.
+ * mode 0: forward  [Cout][KH][KW][Cin];
+ * mode 1: dgrad    [Cin][KH][KW][Cout], taps flipped (conv of dy with it = dx).  */
+int hg_pack_conv_weight(const float* w_oihw, float* w_packed, int32_t Cout, int32_t Cin,
+                        int32_t KH, int32_t KW, int32_t mode, hg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

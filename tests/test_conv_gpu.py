@@ -1,0 +1,78 @@
+"""GPU: the tcgen05 implicit-GEMM convolution against a plain PyTorch fp32
+reference of the same op (inputs pre-rounded to TF32, so the only difference
+left is fp32 accumulation order: tolerance 2e-5 relative to the output scale)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # B, Cin, H, W, Cout, k, stride
+    (8, 64, 4, 4, 128, 3, 1),      # generator block 0 shape family (4x4, several images per tile)
+    (4, 128, 8, 8, 64, 3, 1),      # 8x8: two images per tile
+    (2, 64, 16, 16, 64, 3, 1),     # one image row-band per tile
+    (2, 32, 64, 64, 32, 3, 1),     # BLOCK_N = 32
+    (3, 96, 32, 32, 192, 3, 1),    # BLOCK_N = 64, odd batch, K = 9*3 k-blocks
+    (2, 64, 32, 32, 128, 1, 1),    # 1x1 == plain GEMM
+    (2, 64, 32, 32, 64, 3, 2),     # stride 2 (DiscriminatorBlock.downsample)
+    (5, 256, 4, 4, 256, 3, 1),     # batch tail: 5 images, TB = 8
+    (1, 32, 24, 40, 32, 3, 1),     # non power-of-two spatial size
+]
+
+
+def _ref(x, w, stride, pad):
+    return F.conv2d(x.double(), w.double(), stride=stride, padding=pad).float()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[str(c) for c in CASES])
+def test_conv_matches_torch(case, cuda_device):
+    from histogan_b200 import conv
+    B, Cin, H, W, Cout, k, stride = case
+    g = torch.Generator().manual_seed(0)
+    x = conv.tf32_round(torch.randn(B, Cin, H, W, generator=g)).cuda()
+    w = conv.tf32_round(torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    pad = k // 2
+    wp = conv.pack_weight(w, 0)
+    y = conv.conv2d_nhwc(x, wp, stride, pad)
+    ref = _ref(x, w, stride, pad)
+    assert y.shape == ref.shape
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
+
+
+def test_conv_epilogue(cuda_device):
+    from histogan_b200 import conv
+    B, Cin, S, Cout = 2, 64, 16, 64
+    g = torch.Generator().manual_seed(1)
+    x = conv.tf32_round(torch.randn(B, Cin, S, S, generator=g)).cuda()
+    w = conv.tf32_round(torch.randn(Cout, Cin, 3, 3, generator=g) / 24).cuda()
+    scale = torch.rand(B, Cout, generator=g).cuda() + 0.5
+    bias = torch.randn(Cout, generator=g).cuda()
+    noise = torch.rand(B, 32, 32, generator=g).cuda()          # image noise larger than the layer
+    nw, nb = torch.randn(Cout, generator=g).cuda(), torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(B, Cout, S, S, generator=g).cuda()
+    wp = conv.pack_weight(w, 0)
+    y = conv.conv2d_nhwc(x, wp, 1, 1, scale=scale, bias=bias, noise=noise, noise_w=nw, noise_b=nb,
+                         residual=res, lrelu=True)
+    ref = _ref(x, w, 1, 1) * scale[:, :, None, None] + bias[None, :, None, None]
+    nz = noise[:, :S, :S].transpose(1, 2)                       # (b, oh, ow) <- noise[b, ow, oh]
+    ref = ref + nz[:, None] * nw[None, :, None, None] + nb[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) + res
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
+    y2 = conv.conv2d_nhwc(x, wp, 1, 1, round_tf32=True)
+    assert torch.equal(y2, conv.tf32_round(conv.conv2d_nhwc(x, wp, 1, 1)))
+
+
+def test_dgrad_weight_packing(cuda_device):
+    """conv(dy, pack(w, mode=1)) == d/dx of conv(x, w) for stride 1."""
+    from histogan_b200 import conv
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 64, 16, 16, generator=g).cuda().requires_grad_(True)
+    w = conv.tf32_round(torch.randn(96, 64, 3, 3, generator=g) / 24).cuda()
+    dy = conv.tf32_round(torch.randn(2, 96, 16, 16, generator=g)).cuda()
+    (ref,) = torch.autograd.grad(F.conv2d(x.double(), w.double(), padding=1), x, dy.double())
+    dx = conv.conv2d_nhwc(dy, conv.pack_weight(w, 1), 1, 1)
+    err = (dx - ref.float()).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err

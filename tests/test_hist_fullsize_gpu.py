@@ -31,11 +31,12 @@ def test_full_size_properties(insz, cuda_device):
         perm = torch.randperm(S * S, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
         xp = x[:2].reshape(2, 3, -1)[:, :, perm].reshape(2, 3, S, S)
         assert parity.fro_rel(blk(xp), h[:2]) < 1e-6
-        # channel symmetry: swapping R and B swaps hist0/hist2 and transposes hist1
+        # channel symmetry: swapping R and B swaps the roles of u and v in every
+        # channel: hist0 <-> hist2^T and hist1 -> hist1^T
         xs = x[:2].flip(1)
         hs = blk(xs)
-        assert parity.fro_rel(hs[:, 0], h[:2, 2]) < 1e-6
-        assert parity.fro_rel(hs[:, 2], h[:2, 0]) < 1e-6
+        assert parity.fro_rel(hs[:, 0], h[:2, 2].transpose(1, 2)) < 1e-6
+        assert parity.fro_rel(hs[:, 2], h[:2, 0].transpose(1, 2)) < 1e-6
         assert parity.fro_rel(hs[:, 1], h[:2, 1].transpose(1, 2)) < 1e-6
     # one image against the CPU oracle, full resolution, with loss + grad
     t = ho.synth_random_target(1, seed=2)
