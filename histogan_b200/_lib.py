@@ -61,10 +61,19 @@ _SIGNATURES = {
     "hg_debug_logf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "hg_conv2d_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ConvParams),
                                 C.POINTER(ConvEpilogue), C.c_void_p]),
+    "hg_conv2d_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ConvParams),
+                                  C.c_void_p]),
+    "hg_unpack_conv_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "hg_modulate_round": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_void_p]),
+    "hg_channel_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                 C.c_int32, C.c_void_p]),
     "hg_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "hg_hellinger_workspace_bytes": (C.c_size_t, []),
     "hg_hellinger_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
-                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "hg_hellinger_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

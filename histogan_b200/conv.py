@@ -80,3 +80,24 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: i
                                C.byref(ep), _lib.current_stream_ptr(x.device))
     _lib.check(rc, "hg_conv2d_fwd")
     return y
+
+
+def conv2d_wgrad_nhwc(dy: torch.Tensor, x: torch.Tensor, ksize: int, stride: int = 1,
+                      pad: int = 1) -> torch.Tensor:
+    """dW in OIHW layout (Cout,Cin,k,k) from dy (B,Cout,OH,OW) and x (B,Cin,H,W), both
+    channels_last float32 (hg_conv2d_wgrad + hg_unpack_conv_wgrad)."""
+    lib = _lib.load()
+    _lib.require_cuda(x, "conv2d_wgrad_nhwc")
+    dy, x = as_nhwc(dy), as_nhwc(x)
+    B, Cin, H, W = x.shape
+    _, Cout, OH, OW = dy.shape
+    p = _lib.ConvParams(B, H, W, Cin, Cout, ksize, ksize, stride, pad, OH, OW)
+    dwp = torch.empty((Cout, ksize, ksize, Cin), dtype=torch.float32, device=x.device)
+    dw = torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        st = _lib.current_stream_ptr(x.device)
+        _lib.check(lib.hg_conv2d_wgrad(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dwp), C.byref(p), st),
+                   "hg_conv2d_wgrad")
+        _lib.check(lib.hg_unpack_conv_wgrad(_lib.ptr(dwp), _lib.ptr(dw), Cout, Cin, ksize, ksize, 0, st),
+                   "hg_unpack_conv_wgrad")
+    return dw

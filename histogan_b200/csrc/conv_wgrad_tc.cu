@@ -1,0 +1,284 @@
+// conv_wgrad_tc.cu -- weight gradient of the NHWC convolution on tcgen05 (TF32).
+//
+//   dW[co][kh][kw][ci] = sum_{b,oh,ow} dy[b,oh,ow,co] * x[b, oh*s+kh-p, ow*s+kw-p, ci]
+//
+// (what autograd computes for Conv2DMod's F.conv2d, histoGAN/histoGAN.py:436, and
+// for the nn.Conv2d layers of DiscriminatorBlock, :505-526).  Per filter tap this is
+// a GEMM whose reduction dimension is the PIXEL index: M = Cout, N = Cin,
+// K = B*OH*OW.  In NHWC both operands are "MN-major" (channels contiguous, pixels
+// strided), which the UMMA shared-memory descriptors support for TF32, so the
+// same TMA boxes as the forward kernel feed the tensor cores without a transpose:
+//   A chunk: {32 co, PW, PH, PB} of dy        -> 64 pixel rows x 128 B (swizzle 128B,
+//            32B atoms: the layout tcgen05 requires for MN-major 32-bit operands)
+//   B chunk: {32 ci, PW*s, PH*s, PB} of x at the tap's shifted origin (zero-filled
+//            outside the image == padding), element stride s for stride-2 convs.
+// One CTA owns one (tap, 128-co tile, BN-ci tile) accumulator in TMEM and a slice
+// of the pixel range (split-K); partial results are combined with fp32 atomics.
+#include "hg_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hg {
+
+constexpr int kWgM = 128;               // co per CTA
+constexpr int kWgPix = 64;              // pixels per k-block
+constexpr int kWgChunkBytes = kWgPix * 128;   // 8 KB: 64 rows x 32 fp32
+constexpr int kWgThreads = 192;
+
+struct WgradArgs {
+  int B, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW;
+  int PB, PH, PW;
+  int tiles_w, tiles_h, tiles_b;
+  int co_tiles, ci_tiles, splits;
+  int atomic;
+  float* dw;                            // packed [Cout][KH*KW][Cin]
+};
+
+template <int BN, int STAGES>
+struct WgradSmem {
+  static constexpr int kAChunks = kWgM / 32;
+  static constexpr int kBChunks = BN / 32;
+  static constexpr int kStageBytes = (kAChunks + kBChunks) * kWgChunkBytes;
+  static constexpr int kTotal = STAGES * kStageBytes + 1024 + 256;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kWgThreads)
+conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
+                       const __grid_constant__ CUtensorMap tmx, const WgradArgs a) {
+  using SM = WgradSmem<BN, STAGES>;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * SM::kStageBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmdy);
+    ptx::prefetch_tmap(&tmx);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      ptx::mbar_init(tmem_full_bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  int id = blockIdx.x;
+  const int ci_t = id % a.ci_tiles; id /= a.ci_tiles;
+  const int co_t = id % a.co_tiles; id /= a.co_tiles;
+  const int tap = id;
+  const int kh = tap / a.KW, kw = tap - kh * a.KW;
+  const int co0 = co_t * kWgM, ci0 = ci_t * BN;
+  const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
+  const int kb0 = (int)((long long)blockIdx.y * kb_total / a.splits);
+  const int kb1 = (int)((long long)(blockIdx.y + 1) * kb_total / a.splits);
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int tw_i = kb % a.tiles_w;
+        const int th_i = (kb / a.tiles_w) % a.tiles_h;
+        const int tb_i = kb / (a.tiles_w * a.tiles_h);
+        const int ow0 = tw_i * a.PW, oh0 = th_i * a.PH, b0 = tb_i * a.PB;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sA = base + stage * SM::kStageBytes;
+        uint8_t* sB = sA + SM::kAChunks * kWgChunkBytes;
+        ptx::mbar_expect_tx(&full_bar[stage], SM::kStageBytes);
+#pragma unroll
+        for (int c = 0; c < SM::kAChunks; ++c)
+          ptx::tma_load_4d(sA + c * kWgChunkBytes, &tmdy, &full_bar[stage], co0 + 32 * c, ow0, oh0, b0);
+#pragma unroll
+        for (int c = 0; c < SM::kBChunks; ++c)
+          ptx::tma_load_4d(sB + c * kWgChunkBytes, &tmx, &full_bar[stage], ci0 + 32 * c,
+                           ow0 * a.stride + kw - a.pad, oh0 * a.stride + kh - a.pad, b0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kWgM, BN, 1 /*A MN-major*/, 1 /*B MN-major*/);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sA = ptx::smem_u32(base + stage * SM::kStageBytes);
+        const uint32_t sB = sA + SM::kAChunks * kWgChunkBytes;
+        // MN-major tf32: 128B swizzle with 32B atoms (4 pixel rows x 128 B per atom):
+        // LBO = stride between 32-channel chunks, SBO = stride between 4-row groups
+        const uint64_t a_desc = ptx::make_smem_desc(sA, kWgChunkBytes, 512, ptx::kLayoutSW128Base32);
+        const uint64_t b_desc = ptx::make_smem_desc(sB, kWgChunkBytes, 512, ptx::kLayoutSW128Base32);
+#pragma unroll
+        for (int k = 0; k < kWgPix / 8; ++k) {
+          // next 8 pixels = 8 rows x 128 B = two swizzle atoms: +64 in (addr >> 4) units
+          ptx::mma_tf32_ss(tmem_base, a_desc + (uint64_t)(k * 64), b_desc + (uint64_t)(k * 64), idesc,
+                           (uint32_t)((kb > kb0) | (k != 0)));
+        }
+        ptx::tc_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      ptx::tc_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    const int taps = a.KH * a.KW;
+    if (kb1 > kb0) {
+      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+        if (co < a.Cout) {
+          float* o = a.dw + ((long long)co * taps + tap) * a.Cin + ci0 + c0;
+          if (a.atomic) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// packed [Cout][KH][KW][Cin] gradient -> OIHW parameter gradient (optionally +=)
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout,
+                                    int Cin, int KH, int KW, int accumulate) {
+  const long long total = (long long)Cout * Cin * KH * KW;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int kw = (int)(e % KW);
+  long long r = e / KW;
+  const int kh = (int)(r % KH); r /= KH;
+  const int ci = (int)(r % Cin);
+  const int co = (int)(r / Cin);
+  const float v = dwp[(((long long)co * KH + kh) * KW + kw) * Cin + ci];
+  dw[e] = accumulate ? dw[e] + v : v;
+}
+
+typedef CUresult (*PFN_encodeTiledW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_nhwc_map(CUtensorMap* m, const void* ptr, int C, int W, int H, int B, int bw, int bh,
+                           int bb, int s) {
+  static PFN_encodeTiledW fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess)
+      p = nullptr;
+    return reinterpret_cast<PFN_encodeTiledW>(p);
+  }();
+  if (!fn) return set_error(HG_EARCH, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)(bw * s), (cuuint32_t)(bh * s), (cuuint32_t)bb};
+  cuuint32_t estr[4] = {1, (cuuint32_t)s, (cuuint32_t)s, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(HG_EINVAL, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return 0;
+}
+
+template <int BN, int STAGES>
+static int launch_wgrad(const CUtensorMap& tmdy, const CUtensorMap& tmx, const WgradArgs& a,
+                        cudaStream_t stream) {
+  using SM = WgradSmem<BN, STAGES>;
+  HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BN, STAGES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  dim3 grid(a.KH * a.KW * a.co_tiles * a.ci_tiles, a.splits);
+  conv_wgrad_tf32_kernel<BN, STAGES><<<grid, kWgThreads, SM::kTotal, stream>>>(tmdy, tmx, a);
+  HG_LAUNCH_OK("conv_wgrad_tf32_kernel");
+  return 0;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed,
+                               const hg_conv_params* p, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dy || !x || !dw_packed || !p) return set_error(HG_EINVAL, "null pointer");
+  if (p->Cin % 32 != 0 || p->Cout % 32 != 0)
+    return set_error(HG_ENOSUP, "wgrad: Cin=%d and Cout=%d must be multiples of 32", p->Cin, p->Cout);
+  if (p->stride < 1 || p->stride > 2) return set_error(HG_ENOSUP, "wgrad: stride must be 1 or 2");
+  const int OH = (p->H + 2 * p->pad - p->KH) / p->stride + 1;
+  const int OW = (p->W + 2 * p->pad - p->KW) / p->stride + 1;
+  if (OH != p->OH || OW != p->OW) return set_error(HG_EINVAL, "wgrad: inconsistent OH/OW");
+  const size_t out_bytes = sizeof(float) * (size_t)p->Cout * p->KH * p->KW * p->Cin;
+  if (p->B <= 0) { HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream)); return 0; }
+
+  WgradArgs a{};
+  a.B = p->B; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout; a.KH = p->KH; a.KW = p->KW;
+  a.stride = p->stride; a.pad = p->pad; a.OH = OH; a.OW = OW;
+  int PW = 1; while (PW < 16 && PW < OW) PW <<= 1;
+  int PH = 1; while (PW * PH < kWgPix && PH < OH) PH <<= 1;
+  const int PB = kWgPix / (PW * PH);
+  a.PW = PW; a.PH = PH; a.PB = PB;
+  a.tiles_w = (OW + PW - 1) / PW; a.tiles_h = (OH + PH - 1) / PH; a.tiles_b = (p->B + PB - 1) / PB;
+  const int BN = (p->Cin % 128 == 0) ? 128 : (p->Cin % 64 == 0 ? 64 : 32);
+  a.co_tiles = (p->Cout + kWgM - 1) / kWgM;
+  a.ci_tiles = p->Cin / BN;
+  const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
+  const int base_ctas = p->KH * p->KW * a.co_tiles * a.ci_tiles;
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  int splits = (2 * sms + base_ctas - 1) / base_ctas;
+  if (splits > kb_total / 2) splits = kb_total / 2;
+  if (splits < 1) splits = 1;
+  a.splits = splits;
+  a.atomic = splits > 1;
+  a.dw = dw_packed;
+  if (a.atomic) HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream));
+
+  alignas(64) CUtensorMap tmdy, tmx;
+  int rc = encode_nhwc_map(&tmdy, dy, p->Cout, OW, OH, p->B, PW, PH, PB, 1);
+  if (rc) return rc;
+  rc = encode_nhwc_map(&tmx, x, p->Cin, p->W, p->H, p->B, PW, PH, PB, p->stride);
+  if (rc) return rc;
+  if (BN == 128) return launch_wgrad<128, 3>(tmdy, tmx, a, stream);
+  if (BN == 64) return launch_wgrad<64, 4>(tmdy, tmx, a, stream);
+  return launch_wgrad<32, 4>(tmdy, tmx, a, stream);
+}
+
+extern "C" int hg_unpack_conv_wgrad(const float* dw_packed, float* dw_oihw, int32_t Cout, int32_t Cin,
+                                    int32_t KH, int32_t KW, int32_t accumulate, hg_stream_t stream_) {
+  const long long total = (long long)Cout * Cin * KH * KW;
+  if (total <= 0) return 0;
+  unpack_wgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      dw_packed, dw_oihw, Cout, Cin, KH, KW, accumulate);
+  HG_LAUNCH_OK("unpack_wgrad_kernel");
+  return 0;
+}

@@ -1,5 +1,6 @@
 // hist_host.cu -- host-side geometry for the RGB-uv histogram block + misc ABI.
 #include "hg_common.cuh"
+#include "sm100_ptx.cuh"
 
 #include <math.h>
 #include <mutex>
@@ -130,3 +131,79 @@ int64_t hg_hist_num_pixels(const hg_hist_params* p) {
 }
 
 }  // extern "C"
+
+// ----------------------------------------------------- small elementwise ----
+namespace hg {
+
+// out[b,h,w,c] = tf32_round(x[b,h,w,c] * (mod ? mod[b,c] : 1)), NHWC
+__global__ void __launch_bounds__(256)
+modulate_round_kernel(const float4* __restrict__ x, const float* __restrict__ mod,
+                      float4* __restrict__ out, long long n4, int C, long long per_image4,
+                      int do_round) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = x[i];
+  if (mod) {
+    const int b = (int)(i / per_image4);
+    const int c = (int)((i * 4) % C);
+    const float4 m = *reinterpret_cast<const float4*>(mod + (long long)b * C + c);
+    v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+  }
+  if (do_round) { v.x = tf32_round(v.x); v.y = tf32_round(v.y); v.z = tf32_round(v.z); v.w = tf32_round(v.w); }
+  out[i] = v;
+}
+
+// out[b,c] += sum_{h,w} a[b,h,w,c] * g[b,h,w,c]   (NHWC); grid (C/32, B, splits)
+__global__ void __launch_bounds__(256)
+channel_dot_kernel(const float* __restrict__ a, const float* __restrict__ g,
+                   float* __restrict__ out, int HW, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int per = (HW + gridDim.z - 1) / gridDim.z;
+  const int p0 = blockIdx.z * per, p1 = min(HW, p0 + per);
+  float s = 0.f;
+  if (c < C) {
+    const float* ab = a + (long long)b * HW * C + c;
+    const float* gb = g + (long long)b * HW * C + c;
+    for (int p = p0 + r; p < p1; p += 8) s = fmaf(ab[(long long)p * C], gb[(long long)p * C], s);
+  }
+  red[r][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (r == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    atomicAdd(out + (long long)b * C + c, t);
+  }
+}
+
+}  // namespace hg
+
+extern "C" int hg_modulate_round(const float* x, const float* mod, float* out, int32_t B, int32_t HW,
+                                 int32_t C, int32_t do_round, hg_stream_t stream_) {
+  if (!x || !out) return hg::set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4 != 0) return hg::set_error(HG_ENOSUP, "modulate_round: C=%d must be a multiple of 4", C);
+  const long long n4 = (long long)B * HW * C / 4;
+  if (n4 <= 0) return 0;
+  hg::modulate_round_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      reinterpret_cast<const float4*>(x), mod, reinterpret_cast<float4*>(out), n4, C,
+      (long long)HW * C / 4, do_round);
+  HG_LAUNCH_OK("modulate_round_kernel");
+  return 0;
+}
+
+extern "C" int hg_channel_dot(const float* a, const float* g, float* out, int32_t B, int32_t HW,
+                              int32_t C, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!a || !g || !out) return hg::set_error(HG_EINVAL, "null tensor pointer");
+  if (B <= 0 || HW <= 0 || C <= 0) return 0;
+  HG_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)B * C, stream));
+  int splits = (HW + 2047) / 2048;
+  if (splits > 64) splits = 64;
+  dim3 grid((C + 31) / 32, B, splits);
+  hg::channel_dot_kernel<<<grid, 256, 0, stream>>>(a, g, out, HW, C);
+  HG_LAUNCH_OK("channel_dot_kernel");
+  return 0;
+}

@@ -135,6 +135,10 @@ __device__ __forceinline__ void tmem_ld_wait() {
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start>>4  [16,30) LBO>>4  [32,46) SBO>>4  [46,48) version=1  [61,64) layout
 constexpr uint64_t kLayoutSW128 = 2, kLayoutSW64 = 4, kLayoutSW32 = 6, kLayoutNone = 0;
+// 128-byte swizzle with 32-byte atomicity: the only layout tcgen05 accepts for MN-major
+// 32-bit (tf32) operands; TMA side: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  The swizzle
+// atom is 4 rows x 128 B.
+constexpr uint64_t kLayoutSW128Base32 = 1;
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes,
                                                    uint32_t sbo_bytes, uint64_t layout) {

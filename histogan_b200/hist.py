@@ -161,10 +161,12 @@ class _HellingerFn(torch.autograd.Function):
         lib = _lib.load()
         loss = torch.empty((), dtype=torch.float32, device=generated.device)
         q = torch.empty((), dtype=torch.float32, device=generated.device)
+        ws = _workspace(lib.hg_hellinger_workspace_bytes(), generated.device)
         with torch.cuda.device(generated.device):
             rc = lib.hg_hellinger_fwd(_lib.ptr(target), _lib.ptr(generated), generated.numel(),
                                       generated.shape[0], float(alpha), _lib.ptr(loss),
-                                      _lib.ptr(q), _lib.current_stream_ptr(generated.device))
+                                      _lib.ptr(q), _lib.ptr(ws), ws.numel(),
+                                      _lib.current_stream_ptr(generated.device))
         _lib.check(rc, "hg_hellinger_fwd")
         ctx.alpha = float(alpha)
         ctx.save_for_backward(target, generated, q)

@@ -111,8 +111,10 @@ int hg_debug_logf(const float* in, float* out, int64_t n, hg_stream_t stream);
  * ------------------------------------------------------------------------ */
 
 /* loss, q: device scalars (q = the sum under the square root, saved for bwd). */
+size_t hg_hellinger_workspace_bytes(void);
 int hg_hellinger_fwd(const float* target, const float* hist, int64_t numel, int32_t B,
-                     float alpha, float* loss, float* q, hg_stream_t stream);
+                     float alpha, float* loss, float* q, void* ws, size_t ws_bytes,
+                     hg_stream_t stream);
 /* grad_hist / grad_target (either may be NULL) = grad_loss[0] * dloss/d(.)    */
 int hg_hellinger_bwd(const float* target, const float* hist, int64_t numel, int32_t B,
                      float alpha, const float* q, const float* grad_loss,
@@ -163,6 +165,25 @@ int hg_conv2d_fwd(const float* x, const float* w_packed, float* y, const hg_conv
  * mode 1: dgrad    [Cin][KH][KW][Cout], taps flipped (conv of dy with it = dx).  */
 int hg_pack_conv_weight(const float* w_oihw, float* w_packed, int32_t Cout, int32_t Cin,
                         int32_t KH, int32_t KW, int32_t mode, hg_stream_t stream);
+
+/* Weight gradient: dw_packed [Cout][KH][KW][Cin] (fully written) =
+ *   sum over pixels of dy (B,OH,OW,Cout) x shifted x (B,H,W,Cin); both TF32-rounded
+ *   by their producers.  hg_unpack_conv_wgrad converts to the OIHW layout of the
+ *   nn.Parameter (accumulate != 0: dw_oihw += ...).                              */
+int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed, const hg_conv_params* p,
+                    hg_stream_t stream);
+int hg_unpack_conv_wgrad(const float* dw_packed, float* dw_oihw, int32_t Cout, int32_t Cin,
+                         int32_t KH, int32_t KW, int32_t accumulate, hg_stream_t stream);
+
+/* Producer-side helpers of the modulated convolution (NHWC, C % 4 == 0):
+ *   hg_modulate_round: out = tf32_round?(x * mod[b][c])   -- the style modulation
+ *     w2 * (w1 + 1) of Conv2DMod (histoGAN.py:423-425) moved onto the activations;
+ *     mod may be NULL (round only), do_round = 0 gives the plain product (backward).
+ *   hg_channel_dot:    out[b][c] = sum_hw a * g            -- d/d(mod) of the above. */
+int hg_modulate_round(const float* x, const float* mod, float* out, int32_t B, int32_t HW,
+                      int32_t C, int32_t do_round, hg_stream_t stream);
+int hg_channel_dot(const float* a, const float* g, float* out, int32_t B, int32_t HW, int32_t C,
+                   hg_stream_t stream);
 
 #ifdef __cplusplus
 }
