@@ -1,0 +1,268 @@
+"""Generator / discriminator stacks of HistoGAN on the tcgen05 convolution.
+
+Same class names, constructor arguments, ``forward`` / ``forward_`` signatures,
+output shapes and ``state_dict`` keys as ``histoGAN/histoGAN.py`` (reference
+lines cited per class), so checkpoints and the calling scripts carry over.
+What differs is HOW the modulated convolution is evaluated: the reference
+materialises per-sample weights (B, Cout, Cin, k, k) and runs a grouped conv
+(:423-437, 4.8 GB for one layer at batch 32); here the style scales the
+activations, one shared-weight implicit GEMM runs on the tensor cores, and the
+demodulation is a per-(sample, out-channel) factor on its output.
+
+Activations are channels_last (NHWC in memory) float32; logical shapes stay
+(B, C, H, W) as in the reference.
+"""
+from __future__ import annotations
+
+from math import log2
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+EPS = 1e-8          # histoGAN/histoGAN.py:53
+
+
+def leaky_relu(p=0.2):
+    return nn.LeakyReLU(p, inplace=True)
+
+
+class Flatten(nn.Module):
+    def forward(self, x):
+        return x.reshape(x.shape[0], -1)
+
+
+def _upsample2x():
+    return nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False)
+
+
+# --------------------------------------------------------------- operators ---
+
+class Conv2DMod(nn.Module):
+    """Modulated / demodulated convolution (histoGAN/histoGAN.py:404-440).
+
+    forward(x, y): x (B, Cin, H, W), y (B, Cin) style -> (B, Cout, H, W).
+    ``weight`` keeps the reference layout (Cout, Cin, k, k) and init (:413-415)."""
+
+    def __init__(self, in_chan, out_chan, kernel, demod=True, stride=1, dilation=1, **kwargs):
+        super().__init__()
+        self.filters = out_chan
+        self.demod = demod
+        self.kernel = kernel
+        self.stride = stride
+        self.dilation = dilation
+        self.weight = nn.Parameter(torch.randn((out_chan, in_chan, kernel, kernel)))
+        nn.init.kaiming_normal_(self.weight, a=0, mode='fan_in', nonlinearity='leaky_relu')
+
+    def _get_same_padding(self, size, kernel, dilation, stride):
+        return ((size - 1) * (stride - 1) + dilation * (kernel - 1)) // 2
+
+    def forward(self, x, y):
+        if self.stride != 1 or self.dilation != 1:
+            raise NotImplementedError("Conv2DMod on the sm_100a path supports stride=dilation=1 "
+                                      "(all the reference ever instantiates)")
+        h = x.shape[2]
+        mod = y + 1                                                   # :423-425
+        z = ops.conv2d(x * mod[:, :, None, None], self.weight, None, 1,
+                       self._get_same_padding(h, self.kernel, self.dilation, self.stride))
+        if self.demod:                                                # :427-429
+            wsq = self.weight.pow(2).sum(dim=(2, 3))                  # (Cout, Cin)
+            d = torch.rsqrt(mod.pow(2) @ wsq.t() + EPS)               # (B, Cout)
+            z = z * d[:, :, None, None]
+        return z
+
+
+class RGBBlock(nn.Module):
+    """toRGB: 1x1 modulated conv without demodulation + skip + 2x bilinear
+    upsampling (histoGAN/histoGAN.py:368-401)."""
+
+    def __init__(self, latent_dim, input_channel, upsample, rgba=False):
+        super().__init__()
+        self.input_channel = input_channel
+        self.to_style = nn.Linear(latent_dim, input_channel)
+        out_filters = 3 if not rgba else 4
+        self.conv = Conv2DMod(input_channel, out_filters, 1, demod=False)
+        self.upsample = _upsample2x() if upsample else None
+
+    def forward(self, x, prev_rgb, istyle):
+        return self.forward_(x, prev_rgb, self.to_style(istyle))
+
+    def forward_(self, x, prev_rgb, style):
+        x = self.conv(x, style)
+        if prev_rgb is not None:
+            x = x + prev_rgb
+        if self.upsample is not None:
+            x = self.upsample(x)
+        return x
+
+
+class GeneratorBlock(nn.Module):
+    """upsample -> [mod-conv + noise + LeakyReLU] x 2 -> toRGB
+    (histoGAN/histoGAN.py:443-502)."""
+
+    def __init__(self, latent_dim, input_channels, filters, upsample=True, upsample_rgb=True,
+                 rgba=False):
+        super().__init__()
+        self.upsample = _upsample2x() if upsample else None
+        self.to_style1 = nn.Linear(latent_dim, input_channels)
+        self.to_noise1 = nn.Linear(1, filters)
+        self.conv1 = Conv2DMod(input_channels, filters, 3)
+        self.to_style2 = nn.Linear(latent_dim, filters)
+        self.to_noise2 = nn.Linear(1, filters)
+        self.conv2 = Conv2DMod(filters, filters, 3)
+        self.activation = leaky_relu()
+        self.to_rgb = RGBBlock(latent_dim, filters, upsample_rgb, rgba)
+
+    def _noise_maps(self, inoise, x):
+        inoise = inoise[:, :x.shape[2], :x.shape[3], :]
+        # Linear(1 -> C) on the last axis, then (B,H,W,C) -> (B,C,W,H): the noise image is
+        # used spatially TRANSPOSED, exactly as the reference does (:465-467)
+        return (self.to_noise1(inoise).permute((0, 3, 2, 1)),
+                self.to_noise2(inoise).permute((0, 3, 2, 1)))
+
+    def forward(self, x, prev_rgb, istyle, inoise, latent=None):
+        return self.forward_(x, prev_rgb, None, None, None, inoise=inoise, latent=latent,
+                             _istyle=istyle)
+
+    def forward_(self, x, prev_rgb, style1, style2, to_rgb_style, inoise=None, noise1=None,
+                 noise2=None, latent=None, _istyle=None):
+        if self.upsample is not None:
+            x = self.upsample(x)
+        if noise1 is None or noise2 is None:
+            if inoise is None:
+                raise Exception('No noise is given')
+            noise1, noise2 = self._noise_maps(inoise, x)
+        if _istyle is not None:
+            style1 = self.to_style1(_istyle)
+        x = self.conv1(x, style1)
+        x = self.activation(x + noise1)
+        if latent is not None:
+            x = x + latent
+        if _istyle is not None:
+            style2 = self.to_style2(_istyle)
+        x = self.conv2(x, style2)
+        x = self.activation(x + noise2)
+        if _istyle is not None:
+            rgb = self.to_rgb(x, prev_rgb, _istyle)
+        else:
+            rgb = self.to_rgb.forward_(x, prev_rgb, to_rgb_style)
+        return x, rgb
+
+
+class DiscriminatorBlock(nn.Module):
+    """1x1 residual + 2 x [3x3 conv + LeakyReLU], sum, stride-2 3x3
+    (histoGAN/histoGAN.py:505-526).  The nn.Conv2d children only hold the parameters
+    (same state_dict keys); the arithmetic runs on the tcgen05 kernels."""
+
+    def __init__(self, input_channels, filters, downsample=True):
+        super().__init__()
+        self.conv_res = nn.Conv2d(input_channels, filters, 1)
+        self.net = nn.Sequential(
+            nn.Conv2d(input_channels, filters, 3, padding=1), leaky_relu(),
+            nn.Conv2d(filters, filters, 3, padding=1), leaky_relu())
+        self.downsample = nn.Conv2d(filters, filters, 3, padding=1, stride=2) if downsample else None
+
+    @staticmethod
+    def _conv(m: nn.Conv2d, x):
+        return ops.conv2d(x, m.weight, m.bias, m.stride[0], m.padding[0])
+
+    def forward(self, x):
+        res = self._conv(self.conv_res, x)
+        x = F.leaky_relu(self._conv(self.net[0], x), 0.2)
+        x = F.leaky_relu(self._conv(self.net[2], x), 0.2)
+        x = x + res
+        if self.downsample is not None:
+            x = self._conv(self.downsample, x)
+        return x
+
+
+# ---------------------------------------------------------------- networks ---
+
+class HistVectorizer(nn.Module):
+    """histogram -> latent MLP (histoGAN/histoGAN.py:335-351)."""
+
+    def __init__(self, insize, emb, depth):
+        super().__init__()
+        self.flatten = Flatten()
+        dims = [insize * insize * 3, emb * 2] + [emb] * (depth - 1)
+        layers = []
+        for i in range(depth):
+            layers += [nn.Linear(dims[i], dims[i + 1]), leaky_relu()]
+        self.fcs = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.fcs(self.flatten(x))
+
+
+class StyleVectorizer(nn.Module):
+    """z -> w mapping network (histoGAN/histoGAN.py:354-365)."""
+
+    def __init__(self, emb, depth):
+        super().__init__()
+        layers = []
+        for _ in range(depth):
+            layers += [nn.Linear(emb, emb), leaky_relu()]
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class Generator(nn.Module):
+    """histoGAN/histoGAN.py:529-568."""
+
+    def __init__(self, image_size, latent_dim, network_capacity=16, transparent=False):
+        super().__init__()
+        self.image_size = image_size
+        self.latent_dim = latent_dim
+        self.num_layers = int(log2(image_size) - 1)
+        init_channels = 4 * network_capacity
+        self.initial_block = nn.Parameter(torch.randn((init_channels, 4, 4)))
+        filters = [init_channels] + [network_capacity * (2 ** (i + 1))
+                                     for i in range(self.num_layers)][::-1]
+        self.blocks = nn.ModuleList([
+            GeneratorBlock(latent_dim, cin, cout, upsample=i != 0,
+                           upsample_rgb=i != self.num_layers - 1, rgba=transparent)
+            for i, (cin, cout) in enumerate(zip(filters[:-1], filters[1:]))])
+
+    def forward(self, styles, hists, input_noise):
+        batch_size = styles.shape[0]
+        x = self.initial_block.expand(batch_size, -1, -1, -1)
+        # blocks 0..L-3 take the mapped latent, the last two the histogram latent (:561-563)
+        per_block = torch.cat((styles.transpose(0, 1), hists.transpose(0, 1)), dim=0)
+        rgb = None
+        for style, block in zip(per_block, self.blocks):
+            x, rgb = block(x, rgb, style, input_noise)
+        return rgb
+
+
+class Discriminator(nn.Module):
+    """histoGAN/histoGAN.py:572-631 with the default fq_layers = attn_layers = [] (the
+    optional VectorQuantize / linear-attention blocks depend on packages that are not part
+    of the reference tree and are out of scope)."""
+
+    def __init__(self, image_size, network_capacity=16, fq_layers=[], fq_dict_size=256,
+                 attn_layers=[], transparent=False):
+        super().__init__()
+        if len(fq_layers) or len(attn_layers):
+            raise NotImplementedError("fq_layers / attn_layers need vector_quantize_pytorch / "
+                                      "linear_attention_transformer (not vendored by the reference)")
+        num_layers = int(log2(image_size) - 1)
+        filters = [3 if not transparent else 4] + [network_capacity * (2 ** i)
+                                                   for i in range(num_layers + 1)]
+        pairs = list(zip(filters[:-1], filters[1:]))
+        self.blocks = nn.ModuleList([DiscriminatorBlock(cin, cout, downsample=i != len(pairs) - 1)
+                                     for i, (cin, cout) in enumerate(pairs)])
+        self.attn_blocks = nn.ModuleList([None] * len(pairs))
+        self.quantize_blocks = nn.ModuleList([None] * len(pairs))
+        self.flatten = Flatten()
+        self.to_logit = nn.Linear(2 * 2 * filters[-1], 1)
+
+    def forward(self, x):
+        quantize_loss = torch.zeros(1).to(x)
+        for block in self.blocks:
+            x = block(x)
+        x = self.to_logit(self.flatten(x))
+        return x.squeeze(), quantize_loss

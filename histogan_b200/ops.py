@@ -56,17 +56,20 @@ def _round_tf32_nhwc(x: torch.Tensor) -> torch.Tensor:
 
 
 class _PackCache:
-    """packed (K-major, TF32) copies of a weight, reused until the parameter changes."""
+    """Packed (K-major, TF32) copies of a weight, kept ON the weight tensor object and
+    reused until the tensor is modified in place (optimizer step / load_state_dict bump
+    ``_version``).  Nothing is keyed by address, so a freed-and-reallocated tensor can
+    never hit a stale entry."""
 
-    def __init__(self):
-        self._d = {}
+    ATTR = "_hg_packed"
 
     def get(self, w: torch.Tensor, mode: int) -> torch.Tensor:
-        key = (w.data_ptr(), tuple(w.shape), mode)
         ver = w._version
-        hit = self._d.get(key)
-        if hit is not None and hit[0] == ver:
-            return hit[1]
+        store = getattr(w, self.ATTR, None)
+        if store is not None:
+            hit = store.get(mode)
+            if hit is not None and hit[0] == ver:
+                return hit[1]
         co, ci, kh, kw = w.shape
         cop, cip = _round_up(co), _round_up(ci)
         wd = w.detach().float()
@@ -75,9 +78,14 @@ class _PackCache:
             wp[:co, :ci] = wd
             wd = wp
         packed = _conv.pack_weight(wd, mode)
-        if len(self._d) > 512:
-            self._d.clear()
-        self._d[key] = (ver, packed)
+        if w.is_leaf:                       # parameters persist; temporaries are not worth caching
+            if store is None:
+                store = {}
+                try:
+                    setattr(w, self.ATTR, store)
+                except AttributeError:
+                    return packed
+            store[mode] = (ver, packed)
         return packed
 
 

@@ -1,0 +1,539 @@
+"""HistoGAN container + Trainer with the reference's public API
+(``histoGAN/histoGAN.py:634-1139``) on the sm_100a kernels.
+
+``Trainer.train(alpha)`` performs the same optimisation step as the reference
+(D phase: hinge loss + R1-style gradient penalty every 4th step; G phase:
+adversarial + Hellinger histogram loss + path-length regulariser every 32nd step;
+EMA / NaN guard / checkpointing on the same schedule) but
+
+* the histogram block and its loss are the fused CUDA kernels (hist.py),
+* every convolution runs on the tcgen05 kernels (gan.py / ops.py),
+* the generator pass of the D phase runs without building an autograd graph (the
+  reference builds one and throws it away, :904-910),
+* under ``torch.distributed`` (one process per GPU) gradients are averaged with a
+  bucketed NCCL all-reduce before each optimiser step, which is exactly the
+  reference's ``gradient_accumulate_every = world_size`` semantics (:924,977):
+  the Hellinger loss keeps its per-micro-batch global sqrt.
+"""
+from __future__ import annotations
+
+import json
+from math import floor, log2
+from pathlib import Path
+from random import random
+from shutil import rmtree
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+from torch import nn
+
+from .gan import (Discriminator, Generator, HistVectorizer, StyleVectorizer, EPS)
+from .hist import RGBuvHistBlock, hellinger_loss
+from .optim import DiffGrad
+
+SCALE = 1 / np.sqrt(2.0)       # histoGAN/histoGAN.py:54
+
+
+class NanException(Exception):
+    pass
+
+
+class EMA:
+    def __init__(self, beta):
+        self.beta = beta
+
+    def update_average(self, old, new):
+        if old is None:
+            return new
+        return old * self.beta + (1 - self.beta) * new
+
+
+def default(value, d):
+    return d if value is None else value
+
+
+def cast_list(el):
+    return el if isinstance(el, list) else [el]
+
+
+def is_empty(t):
+    if isinstance(t, torch.Tensor):
+        return t.nelement() == 0
+    return t is None
+
+
+def raise_if_nan(t):
+    if torch.isnan(t):
+        raise NanException
+
+
+def set_requires_grad(model, flag):
+    for p in model.parameters():
+        p.requires_grad = flag
+
+
+# latent / noise helpers: random numbers are drawn on the CPU generator and copied, in the
+# same order as the reference (histoGAN/histoGAN.py:166-189), so seeded runs see the same
+# stream; `fast=True` draws on the device instead (no host round trip).
+
+def noise(n, latent_dim, fast=False):
+    if fast:
+        return torch.randn(n, latent_dim, device='cuda')
+    return torch.randn(n, latent_dim).cuda()
+
+
+def noise_list(n, layers, latent_dim, fast=False):
+    return [(noise(n, latent_dim, fast), layers)]
+
+
+def mixed_list(n, layers, latent_dim, fast=False):
+    tt = int(torch.rand(()).numpy() * layers)
+    return noise_list(n, tt, latent_dim, fast) + noise_list(n, layers - tt, latent_dim, fast)
+
+
+def image_noise(n, im_size, fast=False):
+    if fast:
+        return torch.rand(n, im_size, im_size, 1, device='cuda')
+    return torch.FloatTensor(n, im_size, im_size, 1).uniform_(0.0, 1.0).cuda()
+
+
+def latent_to_w(style_vectorizer, latent_descr):
+    return [(style_vectorizer(z), num_layers) for z, num_layers in latent_descr]
+
+
+def styles_def_to_tensor(styles_def):
+    return torch.cat([t[:, None, :].expand(-1, n, -1) for t, n in styles_def], dim=1)
+
+
+def evaluate_in_chunks(max_batch_size, model, *args):
+    chunks = list(zip(*[a.split(max_batch_size, dim=0) for a in args]))
+    outs = [model(*c) for c in chunks]
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=0)
+
+
+def gradient_penalty(images, output, weight=10):
+    """R1-style penalty on d D(x)/d x (histoGAN/histoGAN.py:156-163); needs the
+    second-order gradients the conv ops provide."""
+    (gradients,) = torch.autograd.grad(outputs=output, inputs=images,
+                                       grad_outputs=torch.ones_like(output),
+                                       create_graph=True, retain_graph=True, only_inputs=True)
+    gradients = gradients.reshape(images.shape[0], -1)
+    return weight * ((gradients.norm(2, dim=1) - 1) ** 2).mean()
+
+
+class HistoGAN(nn.Module):
+    """S, H, G, D + EMA twins SE, HE, GE and the two DiffGrad optimisers
+    (histoGAN/histoGAN.py:634-715).  state_dict keys are the reference's."""
+
+    def __init__(self, image_size, latent_dim=512, style_depth=8, network_capacity=16,
+                 transparent=False, fp16=False, steps=1, lr=1e-4, fq_layers=[], fq_dict_size=256,
+                 attn_layers=[], aug=False, hist=64):
+        super().__init__()
+        if fp16:
+            raise NotImplementedError("Apex AMP (fp16=True) is not part of the sm_100a path; the "
+                                      "convolutions already run TF32 operands / fp32 accumulate")
+        self.lr = lr
+        self.aug = aug
+        self.steps = steps
+        self.ema_updater = EMA(0.995)
+        self.S = StyleVectorizer(latent_dim, style_depth)
+        self.H = HistVectorizer(hist, latent_dim, int(style_depth))
+        self.G = Generator(image_size, latent_dim, network_capacity, transparent=transparent)
+        self.D = Discriminator(image_size, network_capacity, fq_layers=fq_layers,
+                               fq_dict_size=fq_dict_size, attn_layers=attn_layers,
+                               transparent=transparent)
+        self.SE = StyleVectorizer(latent_dim, style_depth)
+        self.HE = HistVectorizer(hist, latent_dim, int(style_depth))
+        self.GE = Generator(image_size, latent_dim, network_capacity, transparent=transparent)
+        if self.aug:
+            raise NotImplementedError("DiffAugment (aug_prob > 0) is out of scope (off by default "
+                                      "in the reference, histoGAN.py:254)")
+        self.D_aug = None
+        for m in (self.SE, self.HE, self.GE):
+            set_requires_grad(m, False)
+        g_params = list(self.G.parameters()) + list(self.S.parameters()) + list(self.H.parameters())
+        self.G_opt = DiffGrad(g_params, lr=self.lr, betas=(0.5, 0.9))
+        self.D_opt = DiffGrad(self.D.parameters(), lr=self.lr, betas=(0.5, 0.9))
+        self._init_weights()
+        self.reset_parameter_averaging()
+        self.cuda()
+
+    def _init_weights(self):
+        for m in self.modules():
+            if type(m) in {nn.Conv2d, nn.Linear}:
+                nn.init.kaiming_normal_(m.weight, a=0, mode='fan_in', nonlinearity='leaky_relu')
+        for block in self.G.blocks:
+            for lin in (block.to_noise1, block.to_noise2):
+                nn.init.zeros_(lin.weight)
+                nn.init.zeros_(lin.bias)
+
+    @torch.no_grad()
+    def EMA(self):
+        beta = self.ema_updater.beta
+        for ma, cur in ((self.SE, self.S), (self.HE, self.H), (self.GE, self.G)):
+            ma_p, cur_p = list(ma.parameters()), list(cur.parameters())
+            torch._foreach_mul_(ma_p, beta)
+            torch._foreach_add_(ma_p, cur_p, alpha=1 - beta)
+
+    def reset_parameter_averaging(self):
+        self.SE.load_state_dict(self.S.state_dict())
+        self.HE.load_state_dict(self.H.state_dict())
+        self.GE.load_state_dict(self.G.state_dict())
+
+    def forward(self, x):
+        return x
+
+
+def _allreduce_mean_grads(params, bucket_bytes=128 << 20):
+    """bucketed NCCL all-reduce (mean) of .grad over the default process group."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    world = dist.get_world_size()
+    grads = [p.grad for p in params if p.grad is not None]
+    bucket, size, works = [], 0, []
+
+    def flush():
+        nonlocal bucket, size
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, async_op=True), flat, bucket))
+        bucket, size = [], 0
+
+    for g in grads:
+        bucket.append(g)
+        size += g.numel() * 4
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    for work, flat, tensors in works:
+        work.wait()
+        flat.div_(world)
+        torch._foreach_copy_(tensors, list(flat.split([t.numel() for t in tensors])))
+
+
+class Trainer:
+    """Same constructor / attributes / methods as the reference Trainer
+    (histoGAN/histoGAN.py:718-1139)."""
+
+    def __init__(self, name, results_dir, models_dir, image_size, network_capacity,
+                 transparent=False, batch_size=4, mixed_prob=0.9, gradient_accumulate_every=1,
+                 lr=2e-4, num_workers=None, save_every=1000, trunc_psi=0.6, fp16=False,
+                 fq_layers=[], fq_dict_size=256, attn_layers=[], hist_method='inverse-quadratic',
+                 hist_resizing='sampling', hist_sigma=0.02, hist_bin=64, hist_insz=150,
+                 aug_prob=0.0, dataset_aug_prob=0.0, aug_types=None, *args, **kwargs):
+        if aug_types is None:
+            aug_types = ['translation', 'cutout']
+        self.fast_rng = bool(kwargs.pop('fast_rng', False))
+        self.GAN_params = [args, kwargs]
+        self.GAN = None
+        self.hist_method = hist_method
+        self.hist_resizing = hist_resizing
+        self.hist_sigma = hist_sigma
+        self.hist_bin = hist_bin
+        self.hist_insz = hist_insz
+        self.histBlock = RGBuvHistBlock(insz=self.hist_insz, h=self.hist_bin,
+                                        method=self.hist_method, resizing=self.hist_resizing,
+                                        sigma=self.hist_sigma)
+        self.name = name
+        self.results_dir = Path(results_dir)
+        self.models_dir = Path(models_dir)
+        self.config_path = self.models_dir / name / '.config.json'
+        assert log2(image_size).is_integer(), 'image size must be a power of 2 (64, 128, 256, 512, 1024)'
+        self.image_size = image_size
+        self.network_capacity = network_capacity
+        self.transparent = transparent
+        self.fq_layers = cast_list(fq_layers)
+        self.fq_dict_size = fq_dict_size
+        self.attn_layers = cast_list(attn_layers)
+        self.aug_prob = aug_prob
+        self.aug_types = aug_types
+        self.dataset_aug_prob = dataset_aug_prob
+        self.lr = lr
+        self.batch_size = batch_size
+        self.num_workers = num_workers
+        self.mixed_prob = mixed_prob
+        self.save_every = save_every
+        self.steps = 0
+        self.av = None
+        self.trunc_psi = trunc_psi
+        self.pl_mean = 0
+        self.gradient_accumulate_every = gradient_accumulate_every
+        assert not fp16, 'Apex mixed precision is not available on the sm_100a path'
+        self.fp16 = fp16
+        self.d_loss = 0
+        self.g_loss = 0
+        self.last_gp_loss = 0
+        self.last_cr_loss = 0
+        self.q_loss = 0
+        self.pl_length_ma = EMA(0.99)
+        self.init_folders()
+        self.loader = None
+        self.loader_evaluate = None
+
+    # ------------------------------------------------------------ plumbing --
+    def init_GAN(self):
+        args, kwargs = self.GAN_params
+        self.GAN = HistoGAN(lr=self.lr, image_size=self.image_size,
+                            network_capacity=self.network_capacity, transparent=self.transparent,
+                            fq_layers=self.fq_layers, fq_dict_size=self.fq_dict_size,
+                            attn_layers=self.attn_layers, fp16=self.fp16, hist=self.hist_bin,
+                            aug=self.aug_prob > 0, *args, **kwargs)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            for p in self.GAN.parameters():        # replicas start from rank 0's weights
+                dist.broadcast(p.data, src=0)
+
+    def config(self):
+        return {'image_size': self.image_size, 'network_capacity': self.network_capacity,
+                'transparent': self.transparent, 'fq_layers': self.fq_layers,
+                'fq_dict_size': self.fq_dict_size, 'attn_layers': self.attn_layers}
+
+    def write_config(self):
+        self.config_path.write_text(json.dumps(self.config()))
+
+    def load_config(self):
+        config = self.config() if not self.config_path.exists() else json.loads(
+            self.config_path.read_text())
+        self.image_size = config['image_size']
+        self.network_capacity = config['network_capacity']
+        self.transparent = config['transparent']
+        self.fq_layers = config['fq_layers']
+        self.fq_dict_size = config['fq_dict_size']
+        self.attn_layers = config.pop('attn_layers', [])
+        del self.GAN
+        self.init_GAN()
+
+    def set_data_src(self, folder):
+        from .data import make_loaders
+        self.loader, self.loader_evaluate = make_loaders(self, folder)
+
+    def _is_main(self):
+        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+    # --------------------------------------------------------------- train --
+    def _sample_latents(self, get_latents_fn, batch_size, num_layers, latent_dim, image_size):
+        style = get_latents_fn(batch_size, num_layers - 2, latent_dim, self.fast_rng)
+        return style, image_noise(batch_size, image_size, self.fast_rng)
+
+    def _generate(self, style, hist_batch, inoise):
+        GAN = self.GAN
+        h_w = GAN.H(hist_batch).unsqueeze(1)
+        h_w = torch.cat((h_w, h_w), dim=1)                         # last two blocks (:900-902)
+        w_styles = styles_def_to_tensor(latent_to_w(GAN.S, style))
+        return GAN.G(w_styles, h_w, inoise), w_styles, h_w
+
+    def train(self, alpha=2):
+        assert self.loader is not None, ('You must first initialize the data source with '
+                                         '`. set_data_src(<folder of images>)`')
+        torch.autograd.set_detect_anomaly(False)
+        if self.GAN is None:
+            self.init_GAN()
+        GAN = self.GAN
+        GAN.train()
+        total_disc_loss = torch.tensor(0.0).cuda()
+        total_gen_loss = torch.tensor(0.0).cuda()
+        total_hist_loss = torch.tensor(0.0).cuda()
+        batch_size = self.batch_size
+        image_size, latent_dim, num_layers = GAN.G.image_size, GAN.G.latent_dim, GAN.G.num_layers
+        accum = self.gradient_accumulate_every
+        apply_gradient_penalty = self.steps % 4 == 0
+        apply_path_penalty = self.steps % 32 == 0
+        avg_pl_length = self.pl_mean
+
+        # ---------------------------------------------------- discriminator --
+        GAN.D_opt.zero_grad()
+        for _ in range(accum):
+            get_latents_fn = mixed_list if random() < self.mixed_prob else noise_list
+            style, inoise = self._sample_latents(get_latents_fn, batch_size, num_layers,
+                                                 latent_dim, image_size)
+            batch = next(self.loader)
+            image_batch = batch['images'].cuda(non_blocking=True)
+            image_batch.requires_grad_()
+            hist_batch = batch['histograms'].cuda(non_blocking=True)
+            with torch.no_grad():                                   # graph is never used (:910)
+                generated_images, _, _ = self._generate(style, hist_batch, inoise)
+            fake_output, fake_q_loss = GAN.D(generated_images)
+            real_output, real_q_loss = GAN.D(image_batch)
+            divergence = (F.relu(1 + real_output) + F.relu(1 - fake_output)).mean()
+            quantize_loss = (fake_q_loss + real_q_loss).mean()
+            self.q_loss = float(quantize_loss.detach().item())
+            disc_loss = divergence + quantize_loss
+            if apply_gradient_penalty:
+                gp = gradient_penalty(image_batch, real_output)
+                self.last_gp_loss = gp.clone().detach().item()
+                disc_loss = disc_loss + gp
+            disc_loss = disc_loss / accum
+            disc_loss.register_hook(raise_if_nan)
+            disc_loss.backward()
+            total_disc_loss += divergence.detach().item() / accum
+        self.d_loss = float(total_disc_loss)
+        _allreduce_mean_grads(list(GAN.D.parameters()))
+        GAN.D_opt.step()
+
+        # -------------------------------------------------------- generator --
+        GAN.G_opt.zero_grad()
+        g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        for _ in range(accum):
+            style, inoise = self._sample_latents(get_latents_fn, batch_size, num_layers,
+                                                 latent_dim, image_size)
+            batch = next(self.loader)
+            hist_batch = batch['histograms'].cuda(non_blocking=True)
+            hist_batch.requires_grad_()
+            generated_images, w_styles, h_w = self._generate(style, hist_batch, inoise)
+            fake_output, _ = GAN.D(generated_images)
+            generated_histograms = self.histBlock(F.relu(generated_images))      # :955
+            histogram_loss = hellinger_loss(hist_batch, generated_histograms, alpha)  # :957-960
+            loss = fake_output.mean()
+            gen_loss = loss + histogram_loss
+            if apply_path_penalty:
+                std = 0.1 / (w_styles.std(dim=0, keepdim=True) + EPS)
+                pert = torch.randn(w_styles.shape, device='cuda') if self.fast_rng else \
+                    torch.randn(w_styles.shape).cuda()
+                w_styles_2 = w_styles + pert / (std + EPS)
+                pl_images = GAN.G(w_styles_2, h_w, inoise)
+                pl_lengths = ((pl_images - generated_images) ** 2).mean(dim=(1, 2, 3))
+                avg_pl_length = np.mean(pl_lengths.detach().cpu().numpy())
+                if not is_empty(self.pl_mean):
+                    pl_loss = ((pl_lengths - self.pl_mean) ** 2).mean()
+                    if not torch.isnan(pl_loss):
+                        gen_loss = gen_loss + pl_loss
+            gen_loss = gen_loss / accum
+            gen_loss.register_hook(raise_if_nan)
+            gen_loss.backward()
+            total_gen_loss += loss.detach().item() / accum
+            total_hist_loss += histogram_loss.detach().item() / accum
+        self.g_loss = float(total_gen_loss)
+        self.h_loss = float(total_hist_loss)
+        _allreduce_mean_grads(g_params)
+        GAN.G_opt.step()
+
+        # ------------------------------------------------------ bookkeeping --
+        if apply_path_penalty and not np.isnan(avg_pl_length):
+            self.pl_mean = self.pl_length_ma.update_average(self.pl_mean, avg_pl_length)
+        if self.steps % 10 == 0 and self.steps > 20000:
+            GAN.EMA()
+        if self.steps <= 25000 and self.steps % 1000 == 2:
+            GAN.reset_parameter_averaging()
+
+        checkpoint_num = floor(self.steps / self.save_every)
+        nan_flag = torch.isnan(total_gen_loss) | torch.isnan(total_disc_loss)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            f = nan_flag.float()
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)               # all ranks retry together
+            nan_flag = f > 0
+        if bool(nan_flag):
+            print(f'NaN detected for generator or discriminator. Loading from checkpoint '
+                  f'#{checkpoint_num}')
+            self.load(checkpoint_num)
+            raise NanException
+        if self.steps % self.save_every == 0 and self._is_main():
+            self.save(checkpoint_num)
+        if (self.steps % 1000 == 0 or (self.steps % 100 == 0 and self.steps < 2500)) and self._is_main():
+            self.evaluate(floor(self.steps / 1000))
+        self.steps += 1
+        self.av = None
+
+    # ------------------------------------------------------------ evaluate --
+    @torch.no_grad()
+    def evaluate(self, num=0, hist_batch=None, num_image_tiles=4, latents=None, n=None,
+                 save_noise_latent=False, load_noise_file=None, load_latent_file=None):
+        self.GAN.eval()
+        if hist_batch is None:
+            hist_batch = next(self.loader_evaluate)['histograms'].cuda()
+        ext = 'jpg' if not self.transparent else 'png'
+        num_rows = num_image_tiles
+        if latents is None and n is None:
+            G = self.GAN.G
+            n = torch.tensor(np.load(load_noise_file)).cuda() if load_noise_file is not None else \
+                image_noise(num_rows ** 2, G.image_size)
+            latents = np.load(load_latent_file) if load_latent_file is not None else \
+                noise_list(num_rows ** 2, G.num_layers - 2, G.latent_dim)
+        generated_images = self.generate_truncated(self.GAN.SE, self.GAN.HE, self.GAN.GE,
+                                                   hist_batch, latents, n, trunc_psi=self.trunc_psi)
+        if num is not None:
+            import torchvision
+            torchvision.utils.save_image(generated_images.contiguous(),
+                                         str(self.results_dir / self.name / f'{str(num)}-ema.{ext}'),
+                                         nrow=num_rows)
+        if save_noise_latent:
+            Path(f'temp/{self.name}').mkdir(parents=True, exist_ok=True)
+            np.save(f'temp/{self.name}/{str(num)}-noise.npy', n.clone().cpu().numpy())
+            np.save(f'temp/{self.name}/{str(num)}-latents.npy', latents)
+        return generated_images
+
+    @torch.no_grad()
+    def generate_truncated(self, S, H, G, hist_batch, style, noi, trunc_psi=0.75):
+        latent_dim = G.latent_dim
+        if self.av is None:
+            z = noise(2000, latent_dim)
+            samples = evaluate_in_chunks(self.batch_size, S, z).cpu().numpy()
+            self.av = np.expand_dims(np.mean(samples, axis=0), axis=0)
+        av_torch = torch.from_numpy(self.av).cuda()
+        w_space = [(trunc_psi * (S(t) - av_torch) + av_torch, nl) for t, nl in style]
+        h_w = H(hist_batch).unsqueeze(1)
+        h_w = torch.cat((h_w, h_w), dim=1)
+        for _ in range(int(np.log2(np.sqrt(w_space[0][0].shape[0])))):
+            h_w = torch.cat((h_w, h_w), dim=0)
+        w_styles = styles_def_to_tensor(w_space)
+        generated_images = evaluate_in_chunks(self.batch_size, G, w_styles, h_w, noi)
+        return generated_images.clamp_(0.0, 1.0)
+
+    def print_log(self):
+        h = f' | H: {self.h_loss:.2f}' if hasattr(self, 'h_loss') else ''
+        print(f'\nG: {self.g_loss:.2f}{h} | D: {self.d_loss:.2f} | GP: {self.last_gp_loss:.2f}'
+              f' | PL: {self.pl_mean:.2f} | CR: {self.last_cr_loss:.2f} | Q: {self.q_loss:.2f}')
+
+    # --------------------------------------------------------- checkpoints --
+    def model_name(self, num):
+        return str(self.models_dir / self.name / f'model_{num}.pt')
+
+    def init_folders(self):
+        (self.results_dir / self.name).mkdir(parents=True, exist_ok=True)
+        (self.models_dir / self.name).mkdir(parents=True, exist_ok=True)
+
+    def clear(self):
+        rmtree(f'./models/{self.name}', True)
+        rmtree(f'./results/{self.name}', True)
+        rmtree(str(self.config_path), True)
+        self.init_folders()
+
+    def save(self, num):
+        torch.save(self.GAN.state_dict(), self.model_name(num))
+        self.write_config()
+
+    def load(self, num=-1):
+        self.load_config()
+        name = num
+        if num == -1:
+            saved = sorted(int(p.stem.split('_')[1])
+                           for p in Path(self.models_dir / self.name).glob('model_*.pt'))
+            if len(saved) == 0:
+                return
+            name = saved[-1]
+            print(f'continuing from previous epoch - {name}')
+        self.steps = name * self.save_every
+        self.GAN.load_state_dict(torch.load(self.model_name(name),
+                                            map_location=f'cuda:{torch.cuda.current_device()}'))
+
+
+class SyntheticLoader:
+    """Infinite iterator of {'images', 'histograms'} batches resident on the device
+    (benchmarks / smoke tests; replaces Trainer.set_data_src)."""
+
+    def __init__(self, batch_size, image_size, hist_bin=64, seed=0, device='cuda', eval_batch=None):
+        g = torch.Generator().manual_seed(seed)
+        b = eval_batch or batch_size
+        self.images = torch.rand(b, 3, image_size, image_size, generator=g).to(device)
+        t = torch.rand(b, 3, hist_bin, hist_bin, generator=g)
+        self.hists = (t / t.sum(dim=(1, 2, 3), keepdim=True)).to(device)
+        self.eval_only = eval_batch is not None
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.eval_only:
+            return {'histograms': self.hists}
+        return {'images': self.images, 'histograms': self.hists}

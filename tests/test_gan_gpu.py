@@ -1,0 +1,68 @@
+"""GPU: the tcgen05-backed Generator / Discriminator modules.
+
+Two references:
+ (1) the reference's golden vectors (fp32, made by the reference classes on CPU):
+     activations within 1e-3 relative (north_star);
+ (2) the SAME algorithm evaluated on the CPU with torch stand-ins for the three raw
+     conv primitives and TF32-rounded operands (tests/emulation.py) = the rounding
+     noise floor of the algorithm.  For every activation / gradient / second-order
+     (gradient-penalty) quantity the CUDA path must be no further from the fp32 golden
+     than 2x that floor (+2e-3), and its activations within 1e-3 of the emulation.
+     (They are not bit-close to the emulation: the tensor cores truncate while
+     accumulating -- a -1e-6 .. -2e-5 relative bias per layer, identical to cuDNN's
+     TF32 kernels, scripts/probe_conv_precision.py -- which the cancellation-heavy
+     gradients amplify to the 1e-2 level, the same level as the TF32 floor itself.)"""
+import pytest
+import torch
+
+from oracle import gan_oracle as go
+from tests import gan_checks
+from tests.emulation import emulated_conv
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-3
+VS_EMULATION_ACT_TOL = 1e-3
+
+
+def _within_noise_floor(e_gpu, e_emu):
+    bad = {k: (e_gpu[k], e_emu[k]) for k in e_gpu if e_gpu[k] > 2 * e_emu[k] + 2e-3}
+    assert not bad, bad
+
+
+def test_conv2dmod_matches_oracle(cuda_device):
+    from histogan_b200.gan import Conv2DMod
+    torch.manual_seed(0)
+    for cin, cout, k, demod, s in [(64, 128, 3, True, 8), (128, 3, 1, False, 16), (32, 32, 3, True, 32)]:
+        m = Conv2DMod(cin, cout, k, demod=demod).cuda()
+        x, y = torch.randn(3, cin, s, s), torch.randn(3, cin)
+        ref = go.mod_conv(x, y, m.weight.detach().cpu(), demod)
+        out = m(x.cuda(), y.cuda())
+        assert out.shape == ref.shape
+        assert gan_checks.rel(out, ref) < ACT_TOL, (cin, cout, k)
+
+
+def test_generator(cuda_device):
+    e_gpu, out_gpu = gan_checks.generator_errors("cuda")
+    with emulated_conv(round_operands=True):
+        e_emu, out_emu = gan_checks.generator_errors("cpu")
+    print("generator vs golden (GPU):", {k: f"{v:.2e}" for k, v in e_gpu.items()})
+    print("generator vs golden (CPU TF32 emulation):", {k: f"{v:.2e}" for k, v in e_emu.items()})
+    worst, key = gan_checks.max_rel_between(out_gpu, out_emu)
+    print("generator GPU vs emulation: worst", f"{worst:.2e}", key)
+    assert e_gpu["rgb"] < ACT_TOL and e_gpu["act_last"] < ACT_TOL and e_gpu["act_norms"] < ACT_TOL
+    assert gan_checks.rel(out_gpu["rgb"], out_emu["rgb"]) < VS_EMULATION_ACT_TOL
+    _within_noise_floor(e_gpu, e_emu)
+
+
+def test_discriminator_and_gradient_penalty(cuda_device):
+    e_gpu, out_gpu = gan_checks.discriminator_errors("cuda")
+    with emulated_conv(round_operands=True):
+        e_emu, out_emu = gan_checks.discriminator_errors("cpu")
+    print("discriminator vs golden (GPU):", {k: f"{v:.2e}" for k, v in e_gpu.items()})
+    print("discriminator vs golden (CPU TF32 emulation):", {k: f"{v:.2e}" for k, v in e_emu.items()})
+    worst, key = gan_checks.max_rel_between(out_gpu, out_emu)
+    print("discriminator GPU vs emulation: worst", f"{worst:.2e}", key)
+    assert e_gpu["logits"] < ACT_TOL
+    assert gan_checks.rel(out_gpu["logits"], out_emu["logits"]) < VS_EMULATION_ACT_TOL
+    _within_noise_floor(e_gpu, e_emu)
