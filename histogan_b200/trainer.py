@@ -211,7 +211,8 @@ def _allreduce_mean_grads(params, bucket_bytes=128 << 20):
     for work, flat, tensors in works:
         work.wait()
         flat.div_(world)
-        torch._foreach_copy_(tensors, list(flat.split([t.numel() for t in tensors])))
+        pieces = flat.split([t.numel() for t in tensors])
+        torch._foreach_copy_(tensors, [p.view_as(t) for p, t in zip(pieces, tensors)])
 
 
 class Trainer:

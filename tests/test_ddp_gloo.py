@@ -1,0 +1,75 @@
+"""CPU, world_size 2 over gloo: the data-parallel plumbing of the Trainer --
+bucketed gradient averaging (== the reference's gradient_accumulate_every semantics,
+histoGAN/histoGAN.py:924,977), rank-consistent NaN handling and weight broadcast."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from histogan_b200.trainer import _allreduce_mean_grads
+    torch.manual_seed(0)
+    shapes = [(7, 3), (5,), (64, 32, 3, 3), (1,), (1000, 13)]
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in params:
+        p.grad = torch.randn(p.shape, generator=g)
+    params.append(torch.nn.Parameter(torch.zeros(3)))           # a parameter without grad
+    expected = []
+    for s in shapes:
+        acc = torch.zeros(s)
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            # replay rank r's stream up to this tensor
+            for s2 in shapes:
+                t = torch.randn(s2, generator=gr)
+                if s2 is s:
+                    acc += t
+                    break
+        expected.append(acc / world)
+    _allreduce_mean_grads(params, bucket_bytes=4096)               # several buckets
+    ok = all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(params, expected))
+    ok = ok and params[-1].grad is None
+    # NaN flag agreement (Trainer.train): MAX-reduce of a per-rank flag
+    f = torch.tensor([1.0 if rank == 1 else 0.0])
+    dist.all_reduce(f, op=dist.ReduceOp.MAX)
+    ok = ok and bool(f.item() == 1.0)
+    # replicas start from rank 0's weights (Trainer.init_GAN)
+    w = torch.full((4,), float(rank))
+    dist.broadcast(w, src=0)
+    ok = ok and bool((w == 0).all())
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)], res
+
+
+def test_single_process_is_noop():
+    from histogan_b200.trainer import _allreduce_mean_grads
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    _allreduce_mean_grads([p])
+    assert torch.equal(p.grad, torch.ones(3))
