@@ -69,6 +69,12 @@ _SIGNATURES = {
                                     C.c_int32, C.c_int32, C.c_void_p]),
     "hg_channel_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_int32, C.c_void_p]),
+    "hg_modconv_epilogue_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
+    "hg_modulate_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
+    "hg_torgb_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
+    "hg_torgb_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
+    "hg_diffgrad_step": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_float] * 5 + [C.c_void_p]),
+    "hg_bias_act_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_float, C.c_void_p]),
     "hg_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
     "hg_hellinger_workspace_bytes": (C.c_size_t, []),

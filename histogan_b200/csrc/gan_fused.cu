@@ -1,0 +1,369 @@
+// gan_fused.cu -- memory-bound companions of the tensor-core convolutions: the
+// element-wise / reduction halves of GeneratorBlock (histoGAN/histoGAN.py:461-479)
+// and RGBBlock (:380-390), each fused into ONE pass over the NHWC activation.
+//
+//   modconv_epilogue_bwd   adjoint of the conv epilogue  y = lrelu(d*z + noise)
+//                          -> dz (TF32-rounded, ready for dgrad/wgrad), d/d(d),
+//                             d/d(noise weight), d/d(noise bias)
+//   modulate_bwd           adjoint of xm = x * mod[b,c]: dx (in place) and d/d(mod)
+//   torgb_fwd / torgb_bwd  1x1 modulated conv to 3 channels (+ previous rgb), planar
+//                          NCHW output; backward gives dx and d/d(per-sample weights)
+//
+// Common skeleton: a CTA = 256 threads = 8 channel lanes (one float4 = 4 channels
+// each -> 32 channels) x 32 pixel lanes; it walks a chunk of pixels of one image,
+// keeps per-thread partial sums for its 4 channels, reduces them over the pixel
+// lanes through shared memory and finishes with one atomicAdd per channel.
+#include "hg_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hg {
+
+constexpr int kFusedThreads = 256;
+constexpr int kPixLanes = 32;
+
+// reduce NQ float4 partials per thread over the 32 pixel lanes; returns the sums in
+// the threads with pixel lane 0 (valid for those threads only)
+template <int NQ>
+__device__ __forceinline__ void reduce_pixel_lanes(float4 (&acc)[NQ], float4* smem /*[NQ][32][8]*/,
+                                                   int cl, int pl) {
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) smem[(q * kPixLanes + pl) * 8 + cl] = acc[q];
+  __syncthreads();
+  if (pl == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < kPixLanes; ++k) {
+        const float4 v = smem[(q * kPixLanes + k) * 8 + cl];
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
+      acc[q] = s;
+    }
+  }
+}
+
+__device__ __forceinline__ void atomic_add4(float* p, const float4& v) {
+  atomicAdd(p + 0, v.x); atomicAdd(p + 1, v.y); atomicAdd(p + 2, v.z); atomicAdd(p + 3, v.w);
+}
+
+// ---------------------------------------------------------------------------
+// y = lrelu(d[b,c]*z + nz[b,p]*nw[c] + nb[c])   (conv epilogue, conv_tc.cu)
+// given dy, y:  dpre = dy * (y > 0 ? 1 : slope)
+//   dz  = tf32_round(dpre * d)          gd[b,c] += sum_p dpre * z ,  z = (pre - noise)/d
+//   gnw[c] += sum_{b,p} dpre * nz       gnb[c] += sum_{b,p} dpre
+// grid (C/32, pixel chunks, B)
+__global__ void __launch_bounds__(kFusedThreads)
+modconv_epilogue_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                            const float* __restrict__ d, const float* __restrict__ noise,
+                            const float* __restrict__ nw, const float* __restrict__ nb,
+                            float* __restrict__ dz, float* __restrict__ gd, float* __restrict__ gnw,
+                            float* __restrict__ gnb, int H, int W, int C, int noise_size,
+                            float slope, int pix_per_cta) {
+  __shared__ float4 red[3 * kPixLanes * 8];
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 32 + cl * 4;
+  const int b = blockIdx.z;
+  const int HW = H * W;
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const bool cvalid = c < C;
+  float4 dv = make_float4(1.f, 1.f, 1.f, 1.f), nwv = make_float4(0.f, 0.f, 0.f, 0.f), nbv = nwv;
+  if (cvalid) {
+    if (d) dv = *reinterpret_cast<const float4*>(d + (long long)b * C + c);
+    if (noise) {
+      nwv = *reinterpret_cast<const float4*>(nw + c);
+      nbv = *reinterpret_cast<const float4*>(nb + c);
+    }
+  }
+  const float inv_slope = 1.f / slope;
+  float4 acc[3];
+  acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cvalid) {
+    for (int p = p0 + pl; p < p1; p += kPixLanes) {
+      const long long off = ((long long)b * HW + p) * C + c;
+      const float4 g = *reinterpret_cast<const float4*>(dy + off);
+      const float4 yv = *reinterpret_cast<const float4*>(y + off);
+      float nz = 0.f;
+      if (noise) {
+        const int oh = p / W, ow = p - oh * W;      // transposed noise image (histoGAN.py:466-467)
+        nz = noise[((long long)b * noise_size + ow) * noise_size + oh];
+      }
+      float4 dp, o;
+#define HG_EBWD(F)                                                                   \
+      {                                                                              \
+        const bool pos = yv.F > 0.f;                                                 \
+        dp.F = pos ? g.F : g.F * slope;                                              \
+        const float pre = pos ? yv.F : yv.F * inv_slope;                             \
+        const float z_times_d = pre - fmaf(nz, nwv.F, nbv.F);                        \
+        acc[0].F = fmaf(dp.F, z_times_d, acc[0].F);                                  \
+        acc[1].F = fmaf(dp.F, nz, acc[1].F);                                         \
+        acc[2].F += dp.F;                                                            \
+        o.F = tf32_round(dp.F * dv.F);                                               \
+      }
+      HG_EBWD(x) HG_EBWD(y) HG_EBWD(z) HG_EBWD(w)
+#undef HG_EBWD
+      *reinterpret_cast<float4*>(dz + off) = o;
+    }
+  }
+  reduce_pixel_lanes<3>(acc, red, cl, pl);
+  if (pl == 0 && cvalid) {
+    if (gd) {
+      float4 v = acc[0];
+      v.x /= dv.x; v.y /= dv.y; v.z /= dv.z; v.w /= dv.w;
+      atomic_add4(gd + (long long)b * C + c, v);
+    }
+    if (gnw) { atomic_add4(gnw + c, acc[1]); atomic_add4(gnb + c, acc[2]); }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// xm = x * mod[b,c]  ->  dx = dxm * mod (written over dxm), gmod[b,c] += sum_p dxm * x
+__global__ void __launch_bounds__(kFusedThreads)
+modulate_bwd_kernel(float* __restrict__ dxm, const float* __restrict__ x,
+                    const float* __restrict__ mod, float* __restrict__ gmod, int HW, int C,
+                    int pix_per_cta) {
+  __shared__ float4 red[kPixLanes * 8];
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 32 + cl * 4;
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const bool cvalid = c < C;
+  float4 acc[1];
+  acc[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cvalid) {
+    const float4 m = *reinterpret_cast<const float4*>(mod + (long long)b * C + c);
+    for (int p = p0 + pl; p < p1; p += kPixLanes) {
+      const long long off = ((long long)b * HW + p) * C + c;
+      float4 g = *reinterpret_cast<const float4*>(dxm + off);
+      const float4 xv = *reinterpret_cast<const float4*>(x + off);
+      acc[0].x = fmaf(g.x, xv.x, acc[0].x); acc[0].y = fmaf(g.y, xv.y, acc[0].y);
+      acc[0].z = fmaf(g.z, xv.z, acc[0].z); acc[0].w = fmaf(g.w, xv.w, acc[0].w);
+      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+      *reinterpret_cast<float4*>(dxm + off) = g;
+    }
+  }
+  reduce_pixel_lanes<1>(acc, red, cl, pl);
+  if (pl == 0 && cvalid) atomic_add4(gmod + (long long)b * C + c, acc[0]);
+}
+
+// ---------------------------------------------------------------------------
+// rgb[b,o,p] = sum_c x[b,p,c] * wmod[b,o,c] (+ prev[b,o,p]);  x NHWC, rgb/prev planar NCHW.
+// One warp per pixel group: 8 channel lanes x float4, 4 pixels per warp pass.
+__global__ void __launch_bounds__(kFusedThreads)
+torgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wmod,
+                 const float* __restrict__ prev, float* __restrict__ rgb, int HW, int C,
+                 int pix_per_cta) {
+  extern __shared__ float sw[];                     // [3][C]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 3 * C; i += kFusedThreads) sw[i] = wmod[(long long)b * 3 * C + i];
+  __syncthreads();
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  for (int p = p0 + pl; p < p1; p += kPixLanes) {
+    const float* xp = x + ((long long)b * HW + p) * C;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    for (int c = cl * 4; c < C; c += 32) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + c);
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(sw + C + c);
+      const float4 w2 = *reinterpret_cast<const float4*>(sw + 2 * C + c);
+      a0 += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+      a1 += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+      a2 += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {               // reduce over the 8 channel lanes
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (cl < 3) {
+      const float v = cl == 0 ? a0 : (cl == 1 ? a1 : a2);
+      const long long o = ((long long)b * 3 + cl) * HW + p;
+      rgb[o] = prev ? v + prev[o] : v;
+    }
+  }
+}
+
+// dx[b,p,c] = sum_o drgb[b,o,p] * wmod[b,o,c] ; gw[b,o,c] += sum_p drgb[b,o,p] * x[b,p,c]
+// grid (C/32, pixel chunks, B)
+__global__ void __launch_bounds__(kFusedThreads)
+torgb_bwd_kernel(const float* __restrict__ drgb, const float* __restrict__ x,
+                 const float* __restrict__ wmod, float* __restrict__ dx, float* __restrict__ gw,
+                 int HW, int C, int pix_per_cta, int accumulate_dx) {
+  __shared__ float4 red[3 * kPixLanes * 8];
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 32 + cl * 4;
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const bool cvalid = c < C;
+  float4 acc[3];
+  acc[0] = acc[1] = acc[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cvalid) {
+    const float* wb = wmod + (long long)b * 3 * C + c;
+    const float4 w0 = *reinterpret_cast<const float4*>(wb);
+    const float4 w1 = *reinterpret_cast<const float4*>(wb + C);
+    const float4 w2 = *reinterpret_cast<const float4*>(wb + 2 * C);
+    const float* gb = drgb + (long long)b * 3 * HW;
+    for (int p = p0 + pl; p < p1; p += kPixLanes) {
+      const float g0 = gb[p], g1 = gb[HW + p], g2 = gb[2 * HW + p];
+      const long long off = ((long long)b * HW + p) * C + c;
+      const float4 xv = *reinterpret_cast<const float4*>(x + off);
+      float4 o;
+      o.x = g0 * w0.x + g1 * w1.x + g2 * w2.x; o.y = g0 * w0.y + g1 * w1.y + g2 * w2.y;
+      o.z = g0 * w0.z + g1 * w1.z + g2 * w2.z; o.w = g0 * w0.w + g1 * w1.w + g2 * w2.w;
+      if (accumulate_dx) {
+        const float4 old = *reinterpret_cast<const float4*>(dx + off);
+        o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+      }
+      *reinterpret_cast<float4*>(dx + off) = o;
+      acc[0].x = fmaf(g0, xv.x, acc[0].x); acc[0].y = fmaf(g0, xv.y, acc[0].y);
+      acc[0].z = fmaf(g0, xv.z, acc[0].z); acc[0].w = fmaf(g0, xv.w, acc[0].w);
+      acc[1].x = fmaf(g1, xv.x, acc[1].x); acc[1].y = fmaf(g1, xv.y, acc[1].y);
+      acc[1].z = fmaf(g1, xv.z, acc[1].z); acc[1].w = fmaf(g1, xv.w, acc[1].w);
+      acc[2].x = fmaf(g2, xv.x, acc[2].x); acc[2].y = fmaf(g2, xv.y, acc[2].y);
+      acc[2].z = fmaf(g2, xv.z, acc[2].z); acc[2].w = fmaf(g2, xv.w, acc[2].w);
+    }
+  }
+  reduce_pixel_lanes<3>(acc, red, cl, pl);
+  if (pl == 0 && cvalid) {
+    float* gwb = gw + (long long)b * 3 * C + c;
+    atomic_add4(gwb, acc[0]); atomic_add4(gwb + C, acc[1]); atomic_add4(gwb + 2 * C, acc[2]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// adjoint of y = act(conv + bias): dpre = tf32_round(dy * (y > 0 ? 1 : slope)) (y may be
+// null: no activation) and gb[c] += sum_{b,p} dpre (before rounding).  grid (C/32, chunks, B)
+__global__ void __launch_bounds__(kFusedThreads)
+bias_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                    float* __restrict__ dpre, float* __restrict__ gb, int HW, int C, float slope,
+                    int pix_per_cta) {
+  __shared__ float4 red[kPixLanes * 8];
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 32 + cl * 4;
+  const int b = blockIdx.z;
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const bool cvalid = c < C;
+  float4 acc[1];
+  acc[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cvalid) {
+    for (int p = p0 + pl; p < p1; p += kPixLanes) {
+      const long long off = ((long long)b * HW + p) * C + c;
+      float4 g = *reinterpret_cast<const float4*>(dy + off);
+      if (y) {
+        const float4 yv = *reinterpret_cast<const float4*>(y + off);
+        g.x = yv.x > 0.f ? g.x : g.x * slope; g.y = yv.y > 0.f ? g.y : g.y * slope;
+        g.z = yv.z > 0.f ? g.z : g.z * slope; g.w = yv.w > 0.f ? g.w : g.w * slope;
+      }
+      acc[0].x += g.x; acc[0].y += g.y; acc[0].z += g.z; acc[0].w += g.w;
+      g.x = tf32_round(g.x); g.y = tf32_round(g.y); g.z = tf32_round(g.z); g.w = tf32_round(g.w);
+      *reinterpret_cast<float4*>(dpre + off) = g;
+    }
+  }
+  if (gb) {
+    reduce_pixel_lanes<1>(acc, red, cl, pl);
+    if (pl == 0 && cvalid) atomic_add4(gb + c, acc[0]);
+  }
+}
+
+static int pick_pix_per_cta(int HW, int B, int cblocks) {
+  // aim for ~4 waves of CTAs over 148 SMs, at least 64 pixels (2 per lane) per CTA
+  const long long target = 4LL * 148 * 4;
+  long long chunks = (target + (long long)B * cblocks - 1) / ((long long)B * cblocks);
+  if (chunks < 1) chunks = 1;
+  int per = (int)((HW + chunks - 1) / chunks);
+  if (per < 64) per = 64;
+  per = (per + kPixLanes - 1) / kPixLanes * kPixLanes;
+  return per;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" int hg_modconv_epilogue_bwd(const float* dy, const float* y, const float* d,
+                                       const float* noise, const float* noise_w,
+                                       const float* noise_b, float* dz, float* gd, float* gnw,
+                                       float* gnb, int32_t B, int32_t H, int32_t W, int32_t C,
+                                       int32_t noise_size, float slope, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dy || !y || !dz) return set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
+  if (d && !gd) return set_error(HG_EINVAL, "gd required with d");
+  if (noise && (!noise_w || !noise_b || !gnw || !gnb)) return set_error(HG_EINVAL, "noise grads required");
+  if (B <= 0) return 0;
+  if (gd) HG_CUDA_OK(cudaMemsetAsync(gd, 0, sizeof(float) * (size_t)B * C, stream));
+  if (gnw) {
+    HG_CUDA_OK(cudaMemsetAsync(gnw, 0, sizeof(float) * (size_t)C, stream));
+    HG_CUDA_OK(cudaMemsetAsync(gnb, 0, sizeof(float) * (size_t)C, stream));
+  }
+  const int cblocks = (C + 31) / 32;
+  const int per = pick_pix_per_cta(H * W, B, cblocks);
+  dim3 grid(cblocks, (H * W + per - 1) / per, B);
+  modconv_epilogue_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(
+      dy, y, d, noise, noise_w, noise_b, dz, gd, gnw, gnb, H, W, C, noise_size, slope, per);
+  HG_LAUNCH_OK("modconv_epilogue_bwd_kernel");
+  return 0;
+}
+
+extern "C" int hg_modulate_bwd(float* dxm_inout, const float* x, const float* mod, float* gmod,
+                               int32_t B, int32_t HW, int32_t C, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dxm_inout || !x || !mod || !gmod) return set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
+  if (B <= 0) return 0;
+  HG_CUDA_OK(cudaMemsetAsync(gmod, 0, sizeof(float) * (size_t)B * C, stream));
+  const int cblocks = (C + 31) / 32;
+  const int per = pick_pix_per_cta(HW, B, cblocks);
+  dim3 grid(cblocks, (HW + per - 1) / per, B);
+  modulate_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(dxm_inout, x, mod, gmod, HW, C, per);
+  HG_LAUNCH_OK("modulate_bwd_kernel");
+  return 0;
+}
+
+extern "C" int hg_torgb_fwd(const float* x, const float* wmod, const float* prev, float* rgb,
+                            int32_t B, int32_t HW, int32_t C, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!x || !wmod || !rgb) return set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
+  if (B <= 0) return 0;
+  const size_t smem = sizeof(float) * 3 * (size_t)C;
+  if (smem > 48 * 1024)
+    HG_CUDA_OK(cudaFuncSetAttribute(torgb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int per = pick_pix_per_cta(HW, B, 1);
+  dim3 grid((HW + per - 1) / per, B);
+  torgb_fwd_kernel<<<grid, kFusedThreads, smem, stream>>>(x, wmod, prev, rgb, HW, C, per);
+  HG_LAUNCH_OK("torgb_fwd_kernel");
+  return 0;
+}
+
+extern "C" int hg_torgb_bwd(const float* drgb, const float* x, const float* wmod, float* dx,
+                            float* gw, int32_t B, int32_t HW, int32_t C, int32_t accumulate_dx,
+                            hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!drgb || !x || !wmod || !dx || !gw) return set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
+  if (B <= 0) return 0;
+  HG_CUDA_OK(cudaMemsetAsync(gw, 0, sizeof(float) * (size_t)B * 3 * C, stream));
+  const int cblocks = (C + 31) / 32;
+  const int per = pick_pix_per_cta(HW, B, cblocks);
+  dim3 grid(cblocks, (HW + per - 1) / per, B);
+  torgb_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(drgb, x, wmod, dx, gw, HW, C, per, accumulate_dx);
+  HG_LAUNCH_OK("torgb_bwd_kernel");
+  return 0;
+}
+
+extern "C" int hg_bias_act_bwd(const float* dy, const float* y, float* dpre, float* gb, int32_t B,
+                               int32_t HW, int32_t C, float slope, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dy || !dpre) return set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
+  if (B <= 0) return 0;
+  if (gb) HG_CUDA_OK(cudaMemsetAsync(gb, 0, sizeof(float) * (size_t)C, stream));
+  const int cblocks = (C + 31) / 32;
+  const int per = pick_pix_per_cta(HW, B, cblocks);
+  dim3 grid(cblocks, (HW + per - 1) / per, B);
+  bias_act_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(dy, y, dpre, gb, HW, C, slope, per);
+  HG_LAUNCH_OK("bias_act_bwd_kernel");
+  return 0;
+}

@@ -1,0 +1,146 @@
+"""Fused generator-layer operators: one autograd Function per reference sub-module call
+chain, each a handful of kernel launches.
+
+  mod_conv_layer   x -> LeakyReLU(Conv2DMod(x, style) + noise)      (histoGAN.py:465-476)
+                   = hg_modulate_round -> hg_conv2d_fwd (demod / noise / lrelu epilogue)
+                   backward = hg_modconv_epilogue_bwd -> hg_conv2d_fwd (dgrad) ->
+                              hg_modulate_bwd ; hg_conv2d_wgrad
+  to_rgb           RGBBlock's 1x1 modulated conv + skip              (histoGAN.py:380-386)
+                   = hg_torgb_fwd / hg_torgb_bwd
+
+First-order gradients only (the generator is never differentiated twice: the gradient
+penalty acts on the discriminator, the path-length regulariser is first order).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from . import conv as _conv
+from . import ops
+
+
+def _st(dev):
+    return _lib.current_stream_ptr(dev)
+
+
+def _modulate_round(x, mod):
+    lib = _lib.load()
+    x = x if x.is_contiguous(memory_format=torch.channels_last) else \
+        x.contiguous(memory_format=torch.channels_last)
+    B, Cc, H, W = x.shape
+    out = torch.empty_like(x, memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = lib.hg_modulate_round(_lib.ptr(x), _lib.ptr(mod), _lib.ptr(out), B, H * W, Cc, 1,
+                                   _st(x.device))
+    _lib.check(rc, "hg_modulate_round")
+    return x, out
+
+
+class _ModConvLayer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mod, w, d, inoise, nw, nb, slope):
+        k = w.shape[2]
+        pad = (k - 1) // 2
+        mod = mod.contiguous()
+        x, xm = _modulate_round(x.float(), mod)
+        y = _conv.conv2d_nhwc(xm, ops._packs.get(w, 0), 1, pad, scale=d, noise=inoise, noise_w=nw,
+                              noise_b=nb, lrelu=True, slope=slope)
+        ctx.save_for_backward(x, xm, mod, w, d, inoise, nw, nb, y)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, xm, mod, w, d, inoise, nw, nb, y = ctx.saved_tensors
+        lib = _lib.load()
+        B, Cout, H, W = y.shape
+        Cin, k = w.shape[1], w.shape[2]
+        dev = y.device
+        dy = dy if dy.is_contiguous(memory_format=torch.channels_last) else \
+            dy.contiguous(memory_format=torch.channels_last)
+        dz = torch.empty_like(y, memory_format=torch.channels_last)
+        gd = torch.empty((B, Cout), dtype=torch.float32, device=dev) if d is not None else None
+        gnw = torch.empty((Cout,), dtype=torch.float32, device=dev) if inoise is not None else None
+        gnb = torch.empty((Cout,), dtype=torch.float32, device=dev) if inoise is not None else None
+        with torch.cuda.device(dev):
+            rc = lib.hg_modconv_epilogue_bwd(
+                _lib.ptr(dy), _lib.ptr(y), _lib.ptr(d), _lib.ptr(inoise), _lib.ptr(nw), _lib.ptr(nb),
+                _lib.ptr(dz), _lib.ptr(gd), _lib.ptr(gnw), _lib.ptr(gnb), B, H, W, Cout,
+                int(inoise.shape[1]) if inoise is not None else 0, float(ctx.slope), _st(dev))
+        _lib.check(rc, "hg_modconv_epilogue_bwd")
+        dx = gmod = dw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dx = _conv.conv2d_nhwc(dz, ops._packs.get(w, 1), 1, k - 1 - (k - 1) // 2)
+            gmod = torch.empty((B, Cin), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                rc = lib.hg_modulate_bwd(_lib.ptr(dx), _lib.ptr(x), _lib.ptr(mod), _lib.ptr(gmod), B,
+                                         H * W, Cin, _st(dev))
+            _lib.check(rc, "hg_modulate_bwd")
+        if ctx.needs_input_grad[2]:
+            dw = _conv.conv2d_wgrad_nhwc(dz, xm, k, 1, (k - 1) // 2)
+        return dx, gmod, dw, gd, None, gnw, gnb, None
+
+
+def fusable(x, w):
+    return x.is_cuda and w.shape[0] % 32 == 0 and w.shape[1] % 32 == 0 and x.shape[1] % 32 == 0
+
+
+def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e-8):
+    """LeakyReLU(Conv2DMod(x, style) + to_noise(inoise).permute(0,3,2,1)) in one fused op.
+    style (B,Cin); inoise (B,S,S,1) image noise or None; noise_lin = the nn.Linear(1, Cout)."""
+    mod = style + 1                                                    # histoGAN.py:423-425
+    d = None
+    if demod:                                                          # :427-429
+        wsq = weight.pow(2).sum(dim=(2, 3))
+        d = torch.rsqrt(mod.pow(2) @ wsq.t() + eps)
+    nz = nw = nb = None
+    if inoise is not None:
+        nz = inoise.reshape(inoise.shape[0], inoise.shape[1], inoise.shape[2])
+        nw = noise_lin.weight.reshape(-1)
+        nb = noise_lin.bias
+    return _ModConvLayer.apply(x, mod, weight, d, nz, nw, nb, slope)
+
+
+class _ToRGB(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, wmod, prev):
+        lib = _lib.load()
+        x = x if x.is_contiguous(memory_format=torch.channels_last) else \
+            x.contiguous(memory_format=torch.channels_last)
+        B, Cc, H, W = x.shape
+        wmod = wmod.contiguous()
+        prev_c = prev.contiguous() if prev is not None else None
+        rgb = torch.empty((B, 3, H, W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.hg_torgb_fwd(_lib.ptr(x), _lib.ptr(wmod), _lib.ptr(prev_c), _lib.ptr(rgb), B,
+                                  H * W, Cc, _st(x.device))
+        _lib.check(rc, "hg_torgb_fwd")
+        ctx.save_for_backward(x, wmod)
+        ctx.has_prev = prev is not None
+        return rgb
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, drgb):
+        x, wmod = ctx.saved_tensors
+        lib = _lib.load()
+        B, Cc, H, W = x.shape
+        drgb = drgb.contiguous()
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        gw = torch.empty_like(wmod)
+        with torch.cuda.device(x.device):
+            rc = lib.hg_torgb_bwd(_lib.ptr(drgb), _lib.ptr(x), _lib.ptr(wmod), _lib.ptr(dx),
+                                  _lib.ptr(gw), B, H * W, Cc, 0, _st(x.device))
+        _lib.check(rc, "hg_torgb_bwd")
+        return dx, gw, (drgb if ctx.has_prev else None)
+
+
+def to_rgb(x, style, weight, prev_rgb):
+    """Conv2DMod(C -> 3, k=1, demod=False)(x, style) + prev_rgb, planar NCHW result."""
+    wmod = weight[None, :, :, 0, 0] * (style[:, None, :] + 1)           # (B,3,C)
+    return _ToRGB.apply(x, wmod, prev_rgb)

@@ -20,7 +20,10 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import ops
+from . import fused, ops
+
+# fused generator layers (fused.py); False = compose torch ops around ops.conv2d
+USE_FUSED = True
 
 EPS = 1e-8          # histoGAN/histoGAN.py:53
 
@@ -90,9 +93,12 @@ class RGBBlock(nn.Module):
         return self.forward_(x, prev_rgb, self.to_style(istyle))
 
     def forward_(self, x, prev_rgb, style):
-        x = self.conv(x, style)
-        if prev_rgb is not None:
-            x = x + prev_rgb
+        if USE_FUSED and self.conv.filters == 3 and x.is_cuda and x.shape[1] % 4 == 0:
+            x = fused.to_rgb(x, style, self.conv.weight, prev_rgb)
+        else:
+            x = self.conv(x, style)
+            if prev_rgb is not None:
+                x = x + prev_rgb
         if self.upsample is not None:
             x = self.upsample(x)
         return x
@@ -130,20 +136,32 @@ class GeneratorBlock(nn.Module):
                  noise2=None, latent=None, _istyle=None):
         if self.upsample is not None:
             x = self.upsample(x)
-        if noise1 is None or noise2 is None:
-            if inoise is None:
-                raise Exception('No noise is given')
-            noise1, noise2 = self._noise_maps(inoise, x)
         if _istyle is not None:
-            style1 = self.to_style1(_istyle)
-        x = self.conv1(x, style1)
-        x = self.activation(x + noise1)
-        if latent is not None:
-            x = x + latent
-        if _istyle is not None:
-            style2 = self.to_style2(_istyle)
-        x = self.conv2(x, style2)
-        x = self.activation(x + noise2)
+            style1, style2 = self.to_style1(_istyle), self.to_style2(_istyle)
+        use_fused = (USE_FUSED and noise1 is None and noise2 is None and inoise is not None
+                     and fused.fusable(x, self.conv1.weight) and fused.fusable(x, self.conv2.weight)
+                     and self.conv1.demod and self.conv2.demod)
+        if use_fused:
+            nz = inoise[:, :x.shape[2], :x.shape[3], :]
+            if nz.shape[1] != nz.shape[2]:
+                use_fused = False
+        if use_fused:
+            nz = inoise if inoise.is_contiguous() else inoise.contiguous()
+            x = fused.mod_conv_layer(x, style1, self.conv1.weight, True, nz, self.to_noise1)
+            if latent is not None:
+                x = x + latent
+            x = fused.mod_conv_layer(x, style2, self.conv2.weight, True, nz, self.to_noise2)
+        else:
+            if noise1 is None or noise2 is None:
+                if inoise is None:
+                    raise Exception('No noise is given')
+                noise1, noise2 = self._noise_maps(inoise, x)
+            x = self.conv1(x, style1)
+            x = self.activation(x + noise1)
+            if latent is not None:
+                x = x + latent
+            x = self.conv2(x, style2)
+            x = self.activation(x + noise2)
         if _istyle is not None:
             rgb = self.to_rgb(x, prev_rgb, _istyle)
         else:
@@ -169,6 +187,10 @@ class DiscriminatorBlock(nn.Module):
         return ops.conv2d(x, m.weight, m.bias, m.stride[0], m.padding[0])
 
     def forward(self, x):
+        if USE_FUSED and x.is_cuda:
+            y = self.forward_padded(ops.round_pad(x), round_out=False)
+            c = self.conv_res.out_channels
+            return y if y.shape[1] == c else y[:, :c]
         res = self._conv(self.conv_res, x)
         x = F.leaky_relu(self._conv(self.net[0], x), 0.2)
         x = F.leaky_relu(self._conv(self.net[2], x), 0.2)
@@ -176,6 +198,22 @@ class DiscriminatorBlock(nn.Module):
         if self.downsample is not None:
             x = self._conv(self.downsample, x)
         return x
+
+    def forward_padded(self, x, round_out=True):
+        """fused path on TF32-rounded NHWC tensors whose channel count is padded to a multiple
+        of 32 with zeros (only D's 3- and 16-channel ends are affected): 4 kernels per block,
+        bias / LeakyReLU / residual sum live in the conv epilogues."""
+        c1, c2, cr, dn = self.net[0], self.net[2], self.conv_res, self.downsample
+        t = ops.conv_bias_act(x, c1.weight, c1.bias, None, 1, 1, act=True, x_rounded=True,
+                              round_out=True)
+        t = ops.conv_bias_act(t, c2.weight, c2.bias, None, 1, 1, act=True, x_rounded=True,
+                              round_out=False)
+        y = ops.conv_bias_act(x, cr.weight, cr.bias, t, 1, 0, act=False, x_rounded=True,
+                              round_out=round_out or dn is not None)
+        if dn is not None:
+            y = ops.conv_bias_act(y, dn.weight, dn.bias, None, 2, 1, act=False, x_rounded=True,
+                                  round_out=round_out)
+        return y
 
 
 # ---------------------------------------------------------------- networks ---
@@ -262,7 +300,15 @@ class Discriminator(nn.Module):
 
     def forward(self, x):
         quantize_loss = torch.zeros(1).to(x)
-        for block in self.blocks:
-            x = block(x)
+        if USE_FUSED and x.is_cuda:
+            x = ops.round_pad(x)                            # image: pad 3 -> 32 channels, round once
+            for i, block in enumerate(self.blocks):
+                x = block.forward_padded(x, round_out=i != len(self.blocks) - 1)
+            c = self.blocks[-1].conv_res.out_channels
+            if x.shape[1] != c:
+                x = x[:, :c]
+        else:
+            for block in self.blocks:
+                x = block(x)
         x = self.to_logit(self.flatten(x))
         return x.squeeze(), quantize_loss

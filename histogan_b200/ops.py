@@ -11,11 +11,16 @@ penalty of ``histoGAN/histoGAN.py:156-163`` back-propagates through
                 conv's input gradient is the stride-1 conv of the zero-dilated dy
     grad weight hg_conv2d_wgrad                   (conv_wgrad_tc.cu)
 
+On top of them ``conv_bias_act`` fuses what a DiscriminatorBlock layer does around
+its convolution (bias, LeakyReLU, residual sum, histoGAN/histoGAN.py:520-526) into
+the conv epilogue, with a backward that is itself built from differentiable pieces.
+
 Operands are rounded to TF32 (round-to-nearest-even) right before the MMA and
-accumulated in fp32, which keeps the generator within ~3e-4 of the fp32
-reference (DESIGN.md "precision").  Channel counts that are not multiples of 32
-(the RGB ends of G and D, D's 16-channel block) are zero-padded to 32 for the
-kernel call and sliced back.
+accumulated in fp32, which keeps the networks within ~3e-4 of the fp32 reference
+(DESIGN.md "precision").  Producers that already emit TF32-rounded NHWC tensors
+say so (``*_rounded`` flags) and the extra rounding pass is skipped.  Channel
+counts that are not multiples of 32 (the RGB ends of G and D, D's 16-channel block)
+are zero-padded to 32 for the kernel calls.
 """
 from __future__ import annotations
 
@@ -33,19 +38,26 @@ def _round_up(n, m=_CH):
     return (n + m - 1) // m * m
 
 
-def _round_tf32_nhwc(x: torch.Tensor) -> torch.Tensor:
-    """fp32 channels_last copy of x, channels zero-padded to a multiple of 32, TF32-rounded."""
+def _is_nhwc(x):
+    return x.is_contiguous(memory_format=torch.channels_last)
+
+
+def round_tf32_nhwc(x: torch.Tensor, already_rounded: bool = False) -> torch.Tensor:
+    """fp32 channels_last copy of x, channels zero-padded to a multiple of 32, TF32-rounded
+    (no-op when the producer already delivered exactly that)."""
     lib = _lib.load()
     B, Cc, H, W = x.shape
     Cp = _round_up(Cc)
+    if already_rounded and Cp == Cc and x.dtype == torch.float32 and _is_nhwc(x):
+        return x
     if x.dtype != torch.float32:
         x = x.float()
     if Cp != Cc:
-        src = x.new_zeros((B, Cp, H, W)).contiguous(memory_format=torch.channels_last)
+        src = torch.zeros((B, Cp, H, W), dtype=torch.float32, device=x.device).contiguous(
+            memory_format=torch.channels_last)
         src[:, :Cc] = x
     else:
-        src = x if x.is_contiguous(memory_format=torch.channels_last) else \
-            x.contiguous(memory_format=torch.channels_last)
+        src = x if _is_nhwc(x) else x.contiguous(memory_format=torch.channels_last)
     out = torch.empty_like(src, memory_format=torch.channels_last)
     if src.numel():
         with torch.cuda.device(x.device):
@@ -53,6 +65,24 @@ def _round_tf32_nhwc(x: torch.Tensor) -> torch.Tensor:
                                        _lib.current_stream_ptr(x.device))
         _lib.check(rc, "hg_modulate_round")
     return out
+
+
+class _RoundPad(torch.autograd.Function):
+    """differentiable face of round_tf32_nhwc: the TF32 rounding is treated as identity
+    (as it is inside the conv Functions), the channel padding as a zero-extension."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return round_tf32_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g if g.shape[1] == ctx.c else g[:, :ctx.c]
+
+
+def round_pad(x: torch.Tensor) -> torch.Tensor:
+    return _RoundPad.apply(x)
 
 
 class _PackCache:
@@ -92,18 +122,22 @@ class _PackCache:
 _packs = _PackCache()
 
 
-def _slice_channels(y: torch.Tensor, c: int) -> torch.Tensor:
+def _match_channels(y: torch.Tensor, c: int) -> torch.Tensor:
+    """drop (or keep) the zero padding channels: `c` is what the caller's tensors carry"""
     if y.shape[1] == c:
         return y
     return y[:, :c].contiguous(memory_format=torch.channels_last)
 
 
-def _raw_conv(x, w, stride, pad):
-    y = _conv.conv2d_nhwc(_round_tf32_nhwc(x), _packs.get(w, 0), stride, pad)
-    return _slice_channels(y, w.shape[0])
+# the three raw primitives (tests/emulation.py swaps these for torch stand-ins on CPU) ------
+
+def _raw_conv(x, w, stride, pad, x_rounded=False, padded_io=False):
+    """padded_io: x / y carry round_up(C, 32) channels (zeros in the padding) instead of C"""
+    y = _conv.conv2d_nhwc(round_tf32_nhwc(x, x_rounded), _packs.get(w, 0), stride, pad)
+    return y if padded_io else _match_channels(y, w.shape[0])
 
 
-def _raw_grad_input(dy, w, stride, pad, in_hw):
+def _raw_grad_input(dy, w, stride, pad, in_hw, dy_rounded=False, padded_io=False):
     k = w.shape[2]
     if stride == 1:
         g = dy
@@ -111,71 +145,75 @@ def _raw_grad_input(dy, w, stride, pad, in_hw):
         g = dy.new_zeros((dy.shape[0], dy.shape[1], in_hw[0], in_hw[1])).contiguous(
             memory_format=torch.channels_last)
         g[:, :, ::stride, ::stride][:, :, :dy.shape[2], :dy.shape[3]] = dy
-    dx = _conv.conv2d_nhwc(_round_tf32_nhwc(g), _packs.get(w, 1), 1, k - 1 - pad)
+    dx = _conv.conv2d_nhwc(round_tf32_nhwc(g, dy_rounded), _packs.get(w, 1), 1, k - 1 - pad)
     assert dx.shape[2:] == tuple(in_hw), (dx.shape, in_hw)
-    return _slice_channels(dx, w.shape[1])
+    return dx if padded_io else _match_channels(dx, w.shape[1])
 
 
-def _raw_grad_weight(dy, x, k, stride, pad):
-    dw = _conv.conv2d_wgrad_nhwc(_round_tf32_nhwc(dy), _round_tf32_nhwc(x), k, stride, pad)
-    return dw[:dy.shape[1], :x.shape[1]].contiguous()
+def _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False):
+    k = wshape[2]
+    dw = _conv.conv2d_wgrad_nhwc(round_tf32_nhwc(dy, dy_rounded), round_tf32_nhwc(x, x_rounded), k,
+                                 stride, pad)
+    return dw[:wshape[0], :wshape[1]].contiguous()
 
 
 class _Conv2d(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, stride, pad):
+    def forward(ctx, x, w, stride, pad, x_rounded=False, padded_io=False):
         ctx.save_for_backward(x, w)
-        ctx.cfg = (stride, pad)
-        return _raw_conv(x, w, stride, pad)
+        ctx.cfg = (stride, pad, x_rounded, padded_io)
+        return _raw_conv(x, w, stride, pad, x_rounded, padded_io)
 
     @staticmethod
     def backward(ctx, dy):
         x, w = ctx.saved_tensors
-        stride, pad = ctx.cfg
+        stride, pad, x_rounded, padded_io = ctx.cfg
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx = _Conv2dGradInput.apply(dy, w, stride, pad, tuple(x.shape[2:]))
+            dx = _Conv2dGradInput.apply(dy, w, stride, pad, tuple(x.shape[2:]), False, padded_io)
         if ctx.needs_input_grad[1]:
-            dw = _Conv2dGradWeight.apply(dy, x, w.shape[2], stride, pad)
-        return dx, dw, None, None
+            dw = _Conv2dGradWeight.apply(dy, x, tuple(w.shape), stride, pad, False, x_rounded)
+        return dx, dw, None, None, None, None
 
 
 class _Conv2dGradInput(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dy, w, stride, pad, in_hw):
+    def forward(ctx, dy, w, stride, pad, in_hw, dy_rounded=False, padded_io=False):
         ctx.save_for_backward(dy, w)
-        ctx.cfg = (stride, pad, in_hw)
-        return _raw_grad_input(dy, w, stride, pad, in_hw)
+        ctx.cfg = (stride, pad, in_hw, dy_rounded, padded_io)
+        return _raw_grad_input(dy, w, stride, pad, in_hw, dy_rounded, padded_io)
 
     @staticmethod
     def backward(ctx, ddx):
         dy, w = ctx.saved_tensors
-        stride, pad, in_hw = ctx.cfg
+        stride, pad, in_hw, dy_rounded, padded_io = ctx.cfg
         g_dy = g_w = None
         if ctx.needs_input_grad[0]:
-            g_dy = _Conv2d.apply(ddx, w, stride, pad)
+            g_dy = _Conv2d.apply(ddx, w, stride, pad, False, padded_io)
         if ctx.needs_input_grad[1]:
-            g_w = _Conv2dGradWeight.apply(dy, ddx, w.shape[2], stride, pad)
-        return g_dy, g_w, None, None, None
+            g_w = _Conv2dGradWeight.apply(dy, ddx, tuple(w.shape), stride, pad, dy_rounded, False)
+        return g_dy, g_w, None, None, None, None, None
 
 
 class _Conv2dGradWeight(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dy, x, k, stride, pad):
+    def forward(ctx, dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False):
         ctx.save_for_backward(dy, x)
-        ctx.cfg = (k, stride, pad)
-        return _raw_grad_weight(dy, x, k, stride, pad)
+        ctx.cfg = (wshape, stride, pad, dy_rounded, x_rounded)
+        return _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded, x_rounded)
 
     @staticmethod
     def backward(ctx, ddw):
         dy, x = ctx.saved_tensors
-        k, stride, pad = ctx.cfg
+        wshape, stride, pad, dy_rounded, x_rounded = ctx.cfg
         g_dy = g_x = None
+        padded_io = (dy.shape[1], x.shape[1]) != (wshape[0], wshape[1])
         if ctx.needs_input_grad[0]:
-            g_dy = _Conv2d.apply(x, ddw, stride, pad)
+            g_dy = _Conv2d.apply(x, ddw, stride, pad, x_rounded, padded_io)
         if ctx.needs_input_grad[1]:
-            g_x = _Conv2dGradInput.apply(dy, ddw, stride, pad, tuple(x.shape[2:]))
-        return g_dy, g_x, None, None, None
+            g_x = _Conv2dGradInput.apply(dy, ddw, stride, pad, tuple(x.shape[2:]), dy_rounded,
+                                         padded_io)
+        return g_dy, g_x, None, None, None, None, None
 
 
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias=None, stride: int = 1,
@@ -188,3 +226,89 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias=None, stride: int = 1,
     if bias is not None:
         y = y + bias.view(1, -1, 1, 1)
     return y
+
+
+# ------------------------------------------------- fused conv + bias + act ------
+
+class _BiasActBwd(torch.autograd.Function):
+    """(dy, y) -> dpre = tf32_round(dy * lrelu'(y)), db = sum dpre   (hg_bias_act_bwd).
+    Linear in dy, so its own backward is the same op."""
+
+    @staticmethod
+    def forward(ctx, dy, y, slope, want_db):
+        lib = _lib.load()
+        dy = dy if _is_nhwc(dy) else dy.contiguous(memory_format=torch.channels_last)
+        B, Cc, H, W = dy.shape
+        dpre = torch.empty_like(dy, memory_format=torch.channels_last)
+        db = torch.empty((Cc,), dtype=torch.float32, device=dy.device) if want_db else None
+        with torch.cuda.device(dy.device):
+            rc = lib.hg_bias_act_bwd(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dpre), _lib.ptr(db), B, H * W,
+                                     Cc, float(slope), _lib.current_stream_ptr(dy.device))
+        _lib.check(rc, "hg_bias_act_bwd")
+        ctx.save_for_backward(y)
+        ctx.slope = slope
+        ctx.shape = tuple(dy.shape)
+        return dpre, db
+
+    @staticmethod
+    def backward(ctx, g_dpre, g_db):
+        (y,) = ctx.saved_tensors
+        g = g_dpre
+        if g_db is not None:
+            gb = g_db.view(1, -1, 1, 1)
+            g = gb.expand(ctx.shape) if g is None else g + gb
+        if g is None:
+            return None, None, None, None
+        ddy, _ = _BiasActBwd.apply(g, y, ctx.slope, False)
+        return ddy, None, None, None
+
+
+class _ConvBiasAct(torch.autograd.Function):
+    """y = [LeakyReLU](conv(x, w) + b) [+ residual], optionally stored TF32-rounded --
+    one kernel (hg_conv2d_fwd with fused epilogue).  Works on channel-padded tensors:
+    x and y carry round_up(C, 32) channels, the padding channels stay exactly zero."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, res, stride, pad, act, slope, x_rounded, round_out):
+        cout_p = _round_up(w.shape[0])
+        xr = round_tf32_nhwc(x, x_rounded)
+        bp = None
+        if b is not None:
+            bp = b.detach().float()
+            if cout_p != w.shape[0]:
+                bp = torch.nn.functional.pad(bp, (0, cout_p - w.shape[0]))
+        y = _conv.conv2d_nhwc(xr, _packs.get(w, 0), stride, pad, bias=bp, residual=res, lrelu=act,
+                              slope=slope, round_tf32=round_out)
+        ctx.save_for_backward(xr, w, y if act else None)
+        ctx.cfg = (stride, pad, act, slope, b is not None, res is not None, tuple(x.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xr, w, y = ctx.saved_tensors
+        stride, pad, act, slope, has_b, has_res, xshape = ctx.cfg
+        need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], \
+            has_b and ctx.needs_input_grad[2]
+        dx = dw = db = None
+        if need_x or need_w or need_b:
+            dpre, dbp = _BiasActBwd.apply(dy, y if act else None, slope if act else 1.0, need_b)
+            if need_b:
+                db = dbp[:w.shape[0]]
+            if need_x:
+                dx = _Conv2dGradInput.apply(dpre, w, stride, pad, tuple(xr.shape[2:]), True, True)
+                if dx.shape[1] != xshape[1]:
+                    dx = dx[:, :xshape[1]]
+            if need_w:
+                dw = _Conv2dGradWeight.apply(dpre, xr, tuple(w.shape), stride, pad, True, True)
+        dres = dy if (has_res and ctx.needs_input_grad[3]) else None
+        return dx, dw, db, dres, None, None, None, None, None, None
+
+
+def conv_bias_act(x, weight, bias=None, residual=None, stride=1, padding=0, act=False, slope=0.2,
+                  x_rounded=False, round_out=False):
+    """fused ``[leaky_relu](conv2d(x, weight, bias, stride, padding)) [+ residual]``.
+    Returns a channels_last tensor with round_up(Cout, 32) channels (padding channels are
+    zero); `x` may itself be such a padded tensor."""
+    _lib.require_cuda(x, "conv_bias_act")
+    return _ConvBiasAct.apply(x, weight, bias, residual, int(stride), int(padding), bool(act),
+                              float(slope), bool(x_rounded), bool(round_out))

@@ -185,6 +185,48 @@ int hg_modulate_round(const float* x, const float* mod, float* out, int32_t B, i
 int hg_channel_dot(const float* a, const float* g, float* out, int32_t B, int32_t HW, int32_t C,
                    hg_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * Fused element-wise / reduction halves of GeneratorBlock and RGBBlock (NHWC)
+ * ------------------------------------------------------------------------ */
+
+/* adjoint of the conv epilogue y = lrelu(d[b,c]*z + noise[b,ow,oh]*nw[c] + nb[c])
+ * (histoGAN/histoGAN.py:427-429,465-471): from dy and y
+ *   dz (B,H,W,C) = tf32_round(dpre * d)   (input of dgrad / wgrad)
+ *   gd (B,C)     = d loss / d d ;  gnw (C), gnb (C) = grads of the to_noise Linear
+ * d / noise may be NULL (then gd / gnw,gnb are ignored).                           */
+int hg_modconv_epilogue_bwd(const float* dy, const float* y, const float* d, const float* noise,
+                            const float* noise_w, const float* noise_b, float* dz, float* gd,
+                            float* gnw, float* gnb, int32_t B, int32_t H, int32_t W, int32_t C,
+                            int32_t noise_size, float slope, hg_stream_t stream);
+
+/* adjoint of xm = x * mod[b,c] (the style modulation, :423-425): dxm_inout *= mod in place
+ * (-> dx) and gmod (B,C) = sum_hw dxm * x.                                         */
+int hg_modulate_bwd(float* dxm_inout, const float* x, const float* mod, float* gmod, int32_t B,
+                    int32_t HW, int32_t C, hg_stream_t stream);
+
+/* RGBBlock (:380-386): rgb (B,3,HW) planar = sum_c x[b,p,c] * wmod[b,o,c] (+ prev), with
+ * wmod (B,3,C) = conv.weight * (style + 1); backward: dx (B,HW,C) and gw (B,3,C).  */
+int hg_torgb_fwd(const float* x, const float* wmod, const float* prev, float* rgb, int32_t B,
+                 int32_t HW, int32_t C, hg_stream_t stream);
+int hg_torgb_bwd(const float* drgb, const float* x, const float* wmod, float* dx, float* gw,
+                 int32_t B, int32_t HW, int32_t C, int32_t accumulate_dx, hg_stream_t stream);
+
+/* adjoint of y = LeakyReLU(conv + bias) (DiscriminatorBlock, :507-518): dpre = TF32-rounded
+ * dy * (y > 0 ? 1 : slope) (y NULL: no activation) and gb (C) = sum over batch and pixels
+ * of the unrounded dpre (gb may be NULL).                                          */
+int hg_bias_act_bwd(const float* dy, const float* y, float* dpre, float* gb, int32_t B,
+                    int32_t HW, int32_t C, float slope, hg_stream_t stream);
+
+/* ------------------------------------------------------------------------ *
+ * Fused multi-tensor DiffGrad step (torch_optimizer.DiffGrad as used at
+ * histoGAN/histoGAN.py:670-671,932,989).  HOST arrays of `count` DEVICE pointers;
+ * step_size = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller.
+ * ------------------------------------------------------------------------ */
+int hg_diffgrad_step(int32_t count, float* const* p, const float* const* g, float* const* m,
+                     float* const* v, float* const* prev, const int64_t* numel, float beta1,
+                     float beta2, float eps, float step_size, float weight_decay,
+                     hg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,17 +22,17 @@ def tf32(t):
 def emulated_conv(round_operands: bool):
     r = tf32 if round_operands else (lambda t: t)
 
-    def raw_conv(x, w, stride, pad):
+    def raw_conv(x, w, stride, pad, x_rounded=False, padded_io=False):
         return F.conv2d(r(x.float()), r(w.detach().float()), stride=stride, padding=pad)
 
-    def raw_grad_input(dy, w, stride, pad, in_hw):
+    def raw_grad_input(dy, w, stride, pad, in_hw, dy_rounded=False, padded_io=False):
         k = w.shape[2]
         out_pad = (in_hw[0] + 2 * pad - k) % stride, (in_hw[1] + 2 * pad - k) % stride
         return F.conv_transpose2d(r(dy.float()), r(w.detach().float()), stride=stride, padding=pad,
                                   output_padding=out_pad)
 
-    def raw_grad_weight(dy, x, k, stride, pad):
-        return torch.nn.grad.conv2d_weight(r(x.float()), (dy.shape[1], x.shape[1], k, k), r(dy.float()),
+    def raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False):
+        return torch.nn.grad.conv2d_weight(r(x.float()), tuple(wshape), r(dy.float()),
                                            stride=stride, padding=pad)
 
     saved = (ops._raw_conv, ops._raw_grad_input, ops._raw_grad_weight, _lib.require_cuda)

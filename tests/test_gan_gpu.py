@@ -42,7 +42,12 @@ def test_conv2dmod_matches_oracle(cuda_device):
         assert gan_checks.rel(out, ref) < ACT_TOL, (cin, cout, k)
 
 
-def test_generator(cuda_device):
+@pytest.mark.parametrize("use_fused", [True, False], ids=["fused", "composed"])
+def test_generator(use_fused, cuda_device, monkeypatch):
+    """fused = fused.py layer operators (the default); composed = torch element-wise ops
+    around ops.conv2d -- both must sit at the TF32 noise floor."""
+    from histogan_b200 import gan
+    monkeypatch.setattr(gan, "USE_FUSED", use_fused)
     e_gpu, out_gpu = gan_checks.generator_errors("cuda")
     with emulated_conv(round_operands=True):
         e_emu, out_emu = gan_checks.generator_errors("cpu")
@@ -55,7 +60,10 @@ def test_generator(cuda_device):
     _within_noise_floor(e_gpu, e_emu)
 
 
-def test_discriminator_and_gradient_penalty(cuda_device):
+@pytest.mark.parametrize("use_fused", [True, False], ids=["fused", "composed"])
+def test_discriminator_and_gradient_penalty(use_fused, cuda_device, monkeypatch):
+    from histogan_b200 import gan
+    monkeypatch.setattr(gan, "USE_FUSED", use_fused)
     e_gpu, out_gpu = gan_checks.discriminator_errors("cuda")
     with emulated_conv(round_operands=True):
         e_emu, out_emu = gan_checks.discriminator_errors("cpu")
