@@ -21,7 +21,8 @@
 //   thread ever touches operand data.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA
 // issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> fused
-// scale / bias / noise / LeakyReLU / residual -> NHWC global).
+// scale / bias / noise / LeakyReLU / residual -> NHWC global).  The kernel is
+// persistent (one CTA per SM) with two TMEM accumulator stages.
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -36,6 +37,7 @@ struct ConvArgs {
   int B, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW;
   int TB, TH, TW;                 // pixel tile (TB*TH*TW == 128)
   int tiles_w, tiles_h;           // tiles per image row / column
+  int m_tiles;                    // tiles_w * tiles_h * ceil(B / TB)
   int kc_per_tap;                 // Cin / 32
   int flags;
   float slope;
@@ -56,19 +58,25 @@ struct ConvSmem {
   static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+// Persistent kernel: one CTA per SM walks output tiles (n fastest, so the CTAs running
+// together share A tiles through L2).  Two TMEM accumulator stages let the epilogue of
+// tile t overlap the main loop of tile t+1; the smem ring (STAGES deep) runs straight
+// through tile boundaries.
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kConvThreads)
+__global__ void __launch_bounds__(kConvThreads, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                  const ConvArgs a) {
   using SM = ConvSmem<BLOCK_N, STAGES>;
-  constexpr uint32_t kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * SM::kStageBytes);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -83,7 +91,10 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         ptx::mbar_init(&full_bar[s], 1);
         ptx::mbar_init(&empty_bar[s], 1);
       }
-      ptx::mbar_init(tmem_full_bar, 1);
+      for (int s = 0; s < 2; ++s) {
+        ptx::mbar_init(&tmem_full_bar[s], 1);
+        ptx::mbar_init(&tmem_empty_bar[s], 4);        // one arrival per epilogue warp
+      }
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -95,13 +106,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  // tile coordinates
-  const int mt = blockIdx.x;
-  const int tw_i = mt % a.tiles_w;
-  const int th_i = (mt / a.tiles_w) % a.tiles_h;
-  const int tb_i = mt / (a.tiles_w * a.tiles_h);
-  const int ow0 = tw_i * a.TW, oh0 = th_i * a.TH, b0 = tb_i * a.TB;
-  const int n0 = blockIdx.y * BLOCK_N;
+  const int n_tiles = a.Cout / BLOCK_N;
+  const int total_tiles = a.m_tiles * n_tiles;
   const int taps = a.KH * a.KW;
   const int total_kb = taps * a.kc_per_tap;
 
@@ -109,17 +115,24 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      const int iw0 = ow0 * a.stride - a.pad, ih0 = oh0 * a.stride - a.pad;
-      for (int tap = 0; tap < taps; ++tap) {
-        const int kh = tap / a.KW, kw = tap - kh * a.KW;
-        for (int kc = 0; kc < a.kc_per_tap; ++kc) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sA = base + stage * SM::kStageBytes;
-          uint8_t* sB = sA + kABytes;
-          ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
-          ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
-          ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Cin + kc * kBlockK, n0);
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BLOCK_N;
+        const int tw_i = mt % a.tiles_w;
+        const int th_i = (mt / a.tiles_w) % a.tiles_h;
+        const int tb_i = mt / (a.tiles_w * a.tiles_h);
+        const int iw0 = tw_i * a.TW * a.stride - a.pad, ih0 = th_i * a.TH * a.stride - a.pad;
+        const int b0 = tb_i * a.TB;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int kh = tap / a.KW, kw = tap - kh * a.KW;
+          for (int kc = 0; kc < a.kc_per_tap; ++kc) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sA = base + stage * SM::kStageBytes;
+            uint8_t* sB = sA + kABytes;
+            ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
+            ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
+            ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Cin + kc * kBlockK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -128,61 +141,84 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       constexpr uint32_t idesc = ptx::make_idesc(2 /*tf32*/, kBlockM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < total_kb; ++kb) {
-        ptx::mbar_wait(&full_bar[stage], phase);
+      int t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int acc = t & 1;
+        const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
+        ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // epilogue drained this stage
         ptx::tc_fence_after();
-        const uint32_t sA = ptx::smem_u32(base + stage * SM::kStageBytes);
-        const uint64_t a_desc = ptx::make_smem_desc(sA, 16, 1024, ptx::kLayoutSW128);
-        const uint64_t b_desc = ptx::make_smem_desc(sA + kABytes, 16, 1024, ptx::kLayoutSW128);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t sA = ptx::smem_u32(base + stage * SM::kStageBytes);
+          const uint64_t a_desc = ptx::make_smem_desc(sA, 16, 1024, ptx::kLayoutSW128);
+          const uint64_t b_desc = ptx::make_smem_desc(sA + kABytes, 16, 1024, ptx::kLayoutSW128);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 8; ++k) {
-          // advance 8 tf32 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
-          ptx::mma_tf32_ss(tmem_base, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                           (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < kBlockK / 8; ++k) {
+            // advance 8 tf32 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
+            ptx::mma_tf32_ss(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                             (uint32_t)((kb | k) != 0));
+          }
+          ptx::tc_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
-        ptx::tc_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
-        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        ptx::tc_commit(&tmem_full_bar[acc]);          // accumulator of this tile complete
       }
-      ptx::tc_commit(tmem_full_bar);                // accumulator complete
     }
   } else {
     // ------------------------------------------------------------ epilogue --
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
     const int tw = row % a.TW, th = (row / a.TW) % a.TH, tb = row / (a.TW * a.TH);
-    const int b = b0 + tb, oh = oh0 + th, ow = ow0 + tw;
-    const bool valid = b < a.B && oh < a.OH && ow < a.OW;
-    const long long pix = ((long long)b * a.OH + oh) * a.OW + ow;
-    float nz = 0.f;
-    if (a.noise && valid)                            // spatially transposed (histoGAN.py:466-467)
-      nz = a.noise[((long long)b * a.noise_size + ow) * a.noise_size + oh];
-    ptx::mbar_wait(tmem_full_bar, 0);
-    ptx::tc_fence_after();
+    int t = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int acc = t & 1;
+      const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
+      const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BLOCK_N;
+      const int tw_i = mt % a.tiles_w;
+      const int th_i = (mt / a.tiles_w) % a.tiles_h;
+      const int tb_i = mt / (a.tiles_w * a.tiles_h);
+      const int b = tb_i * a.TB + tb, oh = th_i * a.TH + th, ow = tw_i * a.TW + tw;
+      const bool valid = b < a.B && oh < a.OH && ow < a.OW;
+      const long long pix = ((long long)b * a.OH + oh) * a.OW + ow;
+      float nz = 0.f;
+      if (a.noise && valid)                          // spatially transposed (histoGAN.py:466-467)
+        nz = a.noise[((long long)b * a.noise_size + ow) * a.noise_size + oh];
+      ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+      ptx::tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      ptx::tmem_ld_wait();
-      if (valid) {
-        const int n = n0 + c0;
-        float* yo = a.y + pix * a.Cout + n;
-        const float* ro = a.residual ? a.residual + pix * a.Cout + n : nullptr;
-        const float* sc = a.scale ? a.scale + (long long)b * a.Cout + n : nullptr;
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * kAccCols +
+                                    (uint32_t)c0, v);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= BLOCK_N) {                    // last read of this accumulator stage:
+          ptx::tc_fence_before();                    // hand it back to the MMA warp
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (valid) {
+          const int n = n0 + c0;
+          float* yo = a.y + pix * a.Cout + n;
+          const float* ro = a.residual ? a.residual + pix * a.Cout + n : nullptr;
+          const float* sc = a.scale ? a.scale + (long long)b * a.Cout + n : nullptr;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float o[4];
+          for (int j = 0; j < 32; j += 4) {
+            float o[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float t = __uint_as_float(v[j + e]);
-            if (sc) t *= __ldg(sc + j + e);
-            if (a.bias) t += __ldg(a.bias + n + j + e);
-            if (a.noise) t = fmaf(nz, __ldg(a.noise_w + n + j + e), t + __ldg(a.noise_b + n + j + e));
-            if (a.flags & HG_CONV_LRELU) t = t > 0.f ? t : t * a.slope;
-            if (ro) t += __ldg(ro + j + e);
-            if (a.flags & HG_CONV_ROUND_TF32) t = tf32_round(t);
-            o[e] = t;
+            for (int e = 0; e < 4; ++e) {
+              float tv = __uint_as_float(v[j + e]);
+              if (sc) tv *= __ldg(sc + j + e);
+              if (a.bias) tv += __ldg(a.bias + n + j + e);
+              if (a.noise) tv = fmaf(nz, __ldg(a.noise_w + n + j + e), tv + __ldg(a.noise_b + n + j + e));
+              if (a.flags & HG_CONV_LRELU) tv = tv > 0.f ? tv : tv * a.slope;
+              if (ro) tv += __ldg(ro + j + e);
+              if (a.flags & HG_CONV_ROUND_TF32) tv = tf32_round(tv);
+              o[e] = tv;
+            }
+            *reinterpret_cast<float4*>(yo + j) = make_float4(o[0], o[1], o[2], o[3]);
           }
-          *reinterpret_cast<float4*>(yo + j) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
     }
@@ -249,9 +285,15 @@ template <int BLOCK_N, int STAGES>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
                        int m_tiles, cudaStream_t stream) {
   using SM = ConvSmem<BLOCK_N, STAGES>;
-  HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-  dim3 grid(m_tiles, a.Cout / BLOCK_N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set = true;
+  }
+  const int total = m_tiles * (a.Cout / BLOCK_N);
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  const int grid = total < sms ? total : sms;
   conv_tf32_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
   HG_LAUNCH_OK("conv_tf32_kernel");
   return 0;
@@ -306,6 +348,7 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
   a.tiles_h = (OH + TH - 1) / TH;
   const int tiles_b = (p->B + TB - 1) / TB;
   const int m_tiles = a.tiles_w * a.tiles_h * tiles_b;
+  a.m_tiles = m_tiles;
   a.kc_per_tap = p->Cin / kBlockK;
   a.flags = ep ? ep->flags : 0;
   a.slope = ep ? ep->lrelu_slope : 0.2f;
@@ -342,7 +385,7 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     int rc = encode_map(&tmw, w_packed, 2, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
   }
-  if (BN == 128) return launch_conv<128, 3>(tmx, tmw, a, m_tiles, stream);
-  if (BN == 64) return launch_conv<64, 4>(tmx, tmw, a, m_tiles, stream);
-  return launch_conv<32, 4>(tmx, tmw, a, m_tiles, stream);
+  if (BN == 128) return launch_conv<128, 6>(tmx, tmw, a, m_tiles, stream);
+  if (BN == 64) return launch_conv<64, 8>(tmx, tmw, a, m_tiles, stream);
+  return launch_conv<32, 8>(tmx, tmw, a, m_tiles, stream);
 }

@@ -216,8 +216,12 @@ template <int BN, int STAGES>
 static int launch_wgrad(const CUtensorMap& tmdy, const CUtensorMap& tmx, const WgradArgs& a,
                         cudaStream_t stream) {
   using SM = WgradSmem<BN, STAGES>;
-  HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BN, STAGES>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+  static bool attr_set = false;
+  if (!attr_set) {
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BN, STAGES>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set = true;
+  }
   dim3 grid(a.KH * a.KW * a.co_tiles * a.ci_tiles, a.splits);
   conv_wgrad_tf32_kernel<BN, STAGES><<<grid, kWgThreads, SM::kTotal, stream>>>(tmdy, tmx, a);
   HG_LAUNCH_OK("conv_wgrad_tf32_kernel");
