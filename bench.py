@@ -375,7 +375,8 @@ def run_train(args):
     tr = Trainer("bench", os.path.join(out_dir, "results"), os.path.join(out_dir, "models"),
                  image_size=S, network_capacity=CAPACITY, batch_size=B_PER_GPU,
                  gradient_accumulate_every=1, hist_insz=150, hist_resizing="interpolation",
-                 save_every=10 ** 9, fast_rng=True)
+                 save_every=10 ** 9, fast_rng=True,
+                 cuda_graphs=os.environ.get("HG_CUDA_GRAPHS", "1") != "0")
     tr.loader_evaluate = DeviceLoader(dv.rank, dv.dev, eval_only=True)
     sampler = ClockSampler(dv.local_rank) if dv.rank == 0 else None
 
@@ -385,14 +386,15 @@ def run_train(args):
         for _ in range(warmup):
             tr.train(alpha=ALPHA)
         dv.barrier()
-        n0 = lib.hg_launch_count()
+        n0 = lib.hg_launch_count() + tr.graph_replayed_launches
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(steps):
             tr.train(alpha=ALPHA)
         e.record()
         dv.barrier()
-        return dv.max_over_ranks(s.elapsed_time(e) * 1e-3), lib.hg_launch_count() - n0
+        return (dv.max_over_ranks(s.elapsed_time(e) * 1e-3),
+                lib.hg_launch_count() + tr.graph_replayed_launches - n0)
 
     # allocator / one-time kernel-attribute warm-up beyond the requested W (not timed)
     timed(DeviceLoader(dv.rank, dv.dev), 2, 2)
@@ -401,6 +403,7 @@ def run_train(args):
     t_e2e, _ = timed(host, args.steps, 1)
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
     losses = {"d": tr.d_loss, "g": tr.g_loss, "h": tr.h_loss, "gp": tr.last_gp_loss}
+    tr_graphs = tr.cuda_graphs
     del tr
     torch.cuda.empty_cache()
     hist_info, _, _, _ = hist_section(dv, 5, 3)
@@ -428,6 +431,7 @@ def run_train(args):
                        "l2_flush": "not needed: the step's working set (GBs of activations) >> 126 MB L2",
                        "timed_steps": f"trainer.steps {FIRST_STEP}..{FIRST_STEP + args.steps - 1}",
                        "rng": "device-side latent / noise generation (fast_rng=True)",
+                       "cuda_graphs": bool(tr_graphs),
                        "peak_mem_gib": round(mem_gb, 2), "final_losses": losses},
             "e2e": {"value": round(n_imgs / t_e2e, 2), "unit": "images/s",
                     "h2d_bytes_per_step": host.x.numel() * 4 + 2 * host.t.numel() * 4,

@@ -71,6 +71,8 @@ _SIGNATURES = {
                                  C.c_int32, C.c_void_p]),
     "hg_modconv_epilogue_bwd": (C.c_int, [C.c_void_p] * 10 + [C.c_int32] * 5 + [C.c_float, C.c_void_p]),
     "hg_modulate_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
+    "hg_upsample_modulate_round": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 4 + [C.c_void_p]),
+    "hg_upsample_modulate_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
     "hg_torgb_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
     "hg_torgb_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
     "hg_diffgrad_step": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_float] * 5 + [C.c_void_p]),

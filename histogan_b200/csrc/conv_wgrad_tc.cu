@@ -94,6 +94,7 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      const int a_chunks = min(SM::kAChunks, (a.Cout - co0 + 31) / 32);
       for (int kb = kb0; kb < kb1; ++kb) {
         const int tw_i = kb % a.tiles_w;
         const int th_i = (kb / a.tiles_w) % a.tiles_h;
@@ -102,10 +103,13 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
         uint8_t* sA = base + stage * SM::kStageBytes;
         uint8_t* sB = sA + SM::kAChunks * kWgChunkBytes;
-        ptx::mbar_expect_tx(&full_bar[stage], SM::kStageBytes);
+        // only the 32-channel chunks of dy that exist are fetched; the MMA still runs M = 128 and
+        // the accumulator rows of the missing channels hold garbage that the epilogue never reads
+        ptx::mbar_expect_tx(&full_bar[stage], (a_chunks + SM::kBChunks) * kWgChunkBytes);
 #pragma unroll
         for (int c = 0; c < SM::kAChunks; ++c)
-          ptx::tma_load_4d(sA + c * kWgChunkBytes, &tmdy, &full_bar[stage], co0 + 32 * c, ow0, oh0, b0);
+          if (c < a_chunks)
+            ptx::tma_load_4d(sA + c * kWgChunkBytes, &tmdy, &full_bar[stage], co0 + 32 * c, ow0, oh0, b0);
 #pragma unroll
         for (int c = 0; c < SM::kBChunks; ++c)
           ptx::tma_load_4d(sB + c * kWgChunkBytes, &tmx, &full_bar[stage], ci0 + 32 * c,

@@ -266,6 +266,111 @@ bias_act_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y,
   }
 }
 
+// ---------------------------------------------------------------------------
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (histoGAN.py:446-447,
+// 462-463) fused with the style modulation of the conv that consumes it:
+//   xm[b, oh, ow, c] = tf32_round( bilerp2x(x)[b, oh, ow, c] * mod[b, c] )
+// taps/weights as torch: src = (o + 0.5)/2 - 0.5 clamped at 0, i1 = min(i0 + 1, n - 1).
+__device__ __forceinline__ void up2_taps(int o, int n, int& i0, int& i1, float& l0, float& l1) {
+  float src = fmaf(0.5f, (float)o + 0.5f, -0.5f);
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  i1 = i0 + (i0 < n - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+__device__ __forceinline__ float4 f4_axpy(float a, const float4& x, const float4& y) {
+  return make_float4(fmaf(a, x.x, y.x), fmaf(a, x.y, y.y), fmaf(a, x.z, y.z), fmaf(a, x.w, y.w));
+}
+
+__device__ __forceinline__ float4 up2_sample(const float* __restrict__ xb, int H, int W, int C, int c,
+                                             int oh, int ow) {
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  up2_taps(oh, H, y0, y1, ly0, ly1);
+  up2_taps(ow, W, x0, x1, lx0, lx1);
+  const float4 v00 = *reinterpret_cast<const float4*>(xb + ((long long)y0 * W + x0) * C + c);
+  const float4 v01 = *reinterpret_cast<const float4*>(xb + ((long long)y0 * W + x1) * C + c);
+  const float4 v10 = *reinterpret_cast<const float4*>(xb + ((long long)y1 * W + x0) * C + c);
+  const float4 v11 = *reinterpret_cast<const float4*>(xb + ((long long)y1 * W + x1) * C + c);
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 r = f4_axpy(ly0 * lx0, v00, z);
+  r = f4_axpy(ly0 * lx1, v01, r);
+  r = f4_axpy(ly1 * lx0, v10, r);
+  r = f4_axpy(ly1 * lx1, v11, r);
+  return r;
+}
+
+// one thread = one output pixel x 4 channels
+__global__ void __launch_bounds__(256)
+upsample_modulate_round_kernel(const float* __restrict__ x, const float* __restrict__ mod,
+                               float* __restrict__ xm, int B, int H, int W, int C) {
+  const long long n4 = (long long)B * 4 * H * W * (C / 4);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)(i % (C / 4)) * 4;
+  long long p = i / (C / 4);
+  const int ow = (int)(p % (2 * W)); p /= 2 * W;
+  const int oh = (int)(p % (2 * H));
+  const int b = (int)(p / (2 * H));
+  float4 v = up2_sample(x + (long long)b * H * W * C, H, W, C, c, oh, ow);
+  const float4 m = *reinterpret_cast<const float4*>(mod + (long long)b * C + c);
+  v.x = tf32_round(v.x * m.x); v.y = tf32_round(v.y * m.y);
+  v.z = tf32_round(v.z * m.z); v.w = tf32_round(v.w * m.w);
+  *reinterpret_cast<float4*>(xm + (((long long)b * 2 * H + oh) * 2 * W + ow) * C + c) = v;
+}
+
+// adjoint: dx[b,h,w,c] = sum over the <=4x4 output pixels that tap (h,w) of weight * dxm * mod,
+//          gmod[b,c]  += sum over this thread's 2x2 output pixels of dxm * bilerp2x(x)
+// grid (C/32, low-res pixel chunks, B); same CTA skeleton as the other kernels
+__global__ void __launch_bounds__(kFusedThreads)
+upsample_modulate_bwd_kernel(const float* __restrict__ dxm, const float* __restrict__ x,
+                             const float* __restrict__ mod, float* __restrict__ dx,
+                             float* __restrict__ gmod, int H, int W, int C, int pix_per_cta) {
+  __shared__ float4 red[kPixLanes * 8];
+  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 32 + cl * 4;
+  const int b = blockIdx.z;
+  const int HW = H * W;
+  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+  const bool cvalid = c < C;
+  float4 acc[1];
+  acc[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (cvalid) {
+    const float4 m = *reinterpret_cast<const float4*>(mod + (long long)b * C + c);
+    const float* xb = x + (long long)b * HW * C;
+    const float* gb = dxm + (long long)b * 4 * HW * C;
+    for (int p = p0 + pl; p < p1; p += kPixLanes) {
+      const int h = p / W, w = p - h * W;
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int oh = max(0, 2 * h - 1); oh <= min(2 * H - 1, 2 * h + 2); ++oh) {
+        int y0, y1; float ly0, ly1;
+        up2_taps(oh, H, y0, y1, ly0, ly1);
+        const float wy = (y0 == h ? ly0 : 0.f) + (y1 == h ? ly1 : 0.f);
+        if (wy == 0.f) continue;
+        for (int ow = max(0, 2 * w - 1); ow <= min(2 * W - 1, 2 * w + 2); ++ow) {
+          int x0, x1; float lx0, lx1;
+          up2_taps(ow, W, x0, x1, lx0, lx1);
+          const float wx = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
+          if (wx == 0.f) continue;
+          const float4 gv = *reinterpret_cast<const float4*>(gb + ((long long)oh * 2 * W + ow) * C + c);
+          g = f4_axpy(wy * wx, gv, g);
+          if ((oh >> 1) == h && (ow >> 1) == w) {          // this thread owns output (oh, ow)
+            const float4 xu = up2_sample(xb, H, W, C, c, oh, ow);
+            acc[0].x = fmaf(gv.x, xu.x, acc[0].x); acc[0].y = fmaf(gv.y, xu.y, acc[0].y);
+            acc[0].z = fmaf(gv.z, xu.z, acc[0].z); acc[0].w = fmaf(gv.w, xu.w, acc[0].w);
+          }
+        }
+      }
+      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+      *reinterpret_cast<float4*>(dx + ((long long)b * HW + p) * C + c) = g;
+    }
+  }
+  reduce_pixel_lanes<1>(acc, red, cl, pl);
+  if (pl == 0 && cvalid) atomic_add4(gmod + (long long)b * C + c, acc[0]);
+}
+
 static int pick_pix_per_cta(int HW, int B, int cblocks) {
   // aim for ~4 waves of CTAs over 148 SMs, at least 64 pixels (2 per lane) per CTA
   const long long target = 4LL * 148 * 4;
@@ -365,5 +470,33 @@ extern "C" int hg_bias_act_bwd(const float* dy, const float* y, float* dpre, flo
   dim3 grid(cblocks, (HW + per - 1) / per, B);
   bias_act_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(dy, y, dpre, gb, HW, C, slope, per);
   HG_LAUNCH_OK("bias_act_bwd_kernel");
+  return 0;
+}
+
+extern "C" int hg_upsample_modulate_round(const float* x, const float* mod, float* xm, int32_t B,
+                                          int32_t H, int32_t W, int32_t C, hg_stream_t stream_) {
+  if (!x || !mod || !xm) return set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
+  const long long n4 = (long long)B * 4 * H * W * (C / 4);
+  if (n4 <= 0) return 0;
+  upsample_modulate_round_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
+      x, mod, xm, B, H, W, C);
+  HG_LAUNCH_OK("upsample_modulate_round_kernel");
+  return 0;
+}
+
+extern "C" int hg_upsample_modulate_bwd(const float* dxm, const float* x, const float* mod, float* dx,
+                                        float* gmod, int32_t B, int32_t H, int32_t W, int32_t C,
+                                        hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!dxm || !x || !mod || !dx || !gmod) return set_error(HG_EINVAL, "null tensor pointer");
+  if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
+  if (B <= 0) return 0;
+  HG_CUDA_OK(cudaMemsetAsync(gmod, 0, sizeof(float) * (size_t)B * C, stream));
+  const int cblocks = (C + 31) / 32;
+  const int per = pick_pix_per_cta(H * W, B, cblocks);
+  dim3 grid(cblocks, (H * W + per - 1) / per, B);
+  upsample_modulate_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(dxm, x, mod, dx, gmod, H, W, C, per);
+  HG_LAUNCH_OK("upsample_modulate_bwd_kernel");
   return 0;
 }

@@ -40,13 +40,28 @@ def _modulate_round(x, mod):
     return x, out
 
 
+def _upsample_modulate_round(x, mod):
+    lib = _lib.load()
+    x = x if x.is_contiguous(memory_format=torch.channels_last) else \
+        x.contiguous(memory_format=torch.channels_last)
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, 2 * H, 2 * W), dtype=torch.float32, device=x.device,
+                      memory_format=torch.channels_last)
+    with torch.cuda.device(x.device):
+        rc = lib.hg_upsample_modulate_round(_lib.ptr(x), _lib.ptr(mod), _lib.ptr(out), B, H, W, Cc,
+                                            _st(x.device))
+    _lib.check(rc, "hg_upsample_modulate_round")
+    return x, out
+
+
 class _ModConvLayer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, mod, w, d, inoise, nw, nb, slope):
+    def forward(ctx, x, mod, w, d, inoise, nw, nb, slope, upsample):
         k = w.shape[2]
         pad = (k - 1) // 2
         mod = mod.contiguous()
-        x, xm = _modulate_round(x.float(), mod)
+        x, xm = (_upsample_modulate_round if upsample else _modulate_round)(x.float(), mod)
+        ctx.upsample = upsample
         y = _conv.conv2d_nhwc(xm, ops._packs.get(w, 0), 1, pad, scale=d, noise=inoise, noise_w=nw,
                               noise_b=nb, lrelu=True, slope=slope)
         ctx.save_for_backward(x, xm, mod, w, d, inoise, nw, nb, y)
@@ -77,22 +92,32 @@ class _ModConvLayer(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             dx = _conv.conv2d_nhwc(dz, ops._packs.get(w, 1), 1, k - 1 - (k - 1) // 2)
             gmod = torch.empty((B, Cin), dtype=torch.float32, device=dev)
-            with torch.cuda.device(dev):
-                rc = lib.hg_modulate_bwd(_lib.ptr(dx), _lib.ptr(x), _lib.ptr(mod), _lib.ptr(gmod), B,
-                                         H * W, Cin, _st(dev))
-            _lib.check(rc, "hg_modulate_bwd")
+            if ctx.upsample:
+                dxm = dx
+                dx = torch.empty_like(x, memory_format=torch.channels_last)
+                with torch.cuda.device(dev):
+                    rc = lib.hg_upsample_modulate_bwd(_lib.ptr(dxm), _lib.ptr(x), _lib.ptr(mod),
+                                                      _lib.ptr(dx), _lib.ptr(gmod), B, H // 2, W // 2,
+                                                      Cin, _st(dev))
+                _lib.check(rc, "hg_upsample_modulate_bwd")
+            else:
+                with torch.cuda.device(dev):
+                    rc = lib.hg_modulate_bwd(_lib.ptr(dx), _lib.ptr(x), _lib.ptr(mod), _lib.ptr(gmod),
+                                             B, H * W, Cin, _st(dev))
+                _lib.check(rc, "hg_modulate_bwd")
         if ctx.needs_input_grad[2]:
             dw = _conv.conv2d_wgrad_nhwc(dz, xm, k, 1, (k - 1) // 2)
-        return dx, gmod, dw, gd, None, gnw, gnb, None
+        return dx, gmod, dw, gd, None, gnw, gnb, None, None
 
 
 def fusable(x, w):
     return x.is_cuda and w.shape[0] % 32 == 0 and w.shape[1] % 32 == 0 and x.shape[1] % 32 == 0
 
 
-def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e-8):
-    """LeakyReLU(Conv2DMod(x, style) + to_noise(inoise).permute(0,3,2,1)) in one fused op.
-    style (B,Cin); inoise (B,S,S,1) image noise or None; noise_lin = the nn.Linear(1, Cout)."""
+def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e-8, upsample=False):
+    """LeakyReLU(Conv2DMod(up(x), style) + to_noise(inoise).permute(0,3,2,1)) in one fused op.
+    style (B,Cin); inoise (B,S,S,1) image noise or None; noise_lin = the nn.Linear(1, Cout);
+    upsample=True folds the block's 2x bilinear nn.Upsample of x into the op."""
     mod = style + 1                                                    # histoGAN.py:423-425
     d = None
     if demod:                                                          # :427-429
@@ -103,7 +128,7 @@ def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e
         nz = inoise.reshape(inoise.shape[0], inoise.shape[1], inoise.shape[2])
         nw = noise_lin.weight.reshape(-1)
         nb = noise_lin.bias
-    return _ModConvLayer.apply(x, mod, weight, d, nz, nw, nb, slope)
+    return _ModConvLayer.apply(x, mod, weight, d, nz, nw, nb, slope, bool(upsample))
 
 
 class _ToRGB(torch.autograd.Function):

@@ -134,24 +134,25 @@ class GeneratorBlock(nn.Module):
 
     def forward_(self, x, prev_rgb, style1, style2, to_rgb_style, inoise=None, noise1=None,
                  noise2=None, latent=None, _istyle=None):
-        if self.upsample is not None:
-            x = self.upsample(x)
         if _istyle is not None:
             style1, style2 = self.to_style1(_istyle), self.to_style2(_istyle)
+        up = self.upsample is not None
         use_fused = (USE_FUSED and noise1 is None and noise2 is None and inoise is not None
                      and fused.fusable(x, self.conv1.weight) and fused.fusable(x, self.conv2.weight)
-                     and self.conv1.demod and self.conv2.demod)
-        if use_fused:
-            nz = inoise[:, :x.shape[2], :x.shape[3], :]
-            if nz.shape[1] != nz.shape[2]:
-                use_fused = False
+                     and self.conv1.demod and self.conv2.demod
+                     and x.shape[2] == x.shape[3]
+                     and inoise.shape[1] >= x.shape[2] * (2 if up else 1)
+                     and inoise.shape[2] >= x.shape[3] * (2 if up else 1))
         if use_fused:
             nz = inoise if inoise.is_contiguous() else inoise.contiguous()
-            x = fused.mod_conv_layer(x, style1, self.conv1.weight, True, nz, self.to_noise1)
+            # the block's nn.Upsample is folded into conv1's producer kernel
+            x = fused.mod_conv_layer(x, style1, self.conv1.weight, True, nz, self.to_noise1, upsample=up)
             if latent is not None:
                 x = x + latent
             x = fused.mod_conv_layer(x, style2, self.conv2.weight, True, nz, self.to_noise2)
         else:
+            if up:
+                x = self.upsample(x)
             if noise1 is None or noise2 is None:
                 if inoise is None:
                     raise Exception('No noise is given')
@@ -299,7 +300,7 @@ class Discriminator(nn.Module):
         self.to_logit = nn.Linear(2 * 2 * filters[-1], 1)
 
     def forward(self, x):
-        quantize_loss = torch.zeros(1).to(x)
+        quantize_loss = torch.zeros(1, device=x.device, dtype=x.dtype)
         if USE_FUSED and x.is_cuda:
             x = ops.round_pad(x)                            # image: pad 3 -> 32 channels, round once
             for i, block in enumerate(self.blocks):

@@ -93,8 +93,15 @@ class _PackCache:
 
     ATTR = "_hg_packed"
 
+    def __init__(self):
+        self.generation = 0
+
+    def new_generation(self):
+        """forget every cached pack (CUDA-graph capture must contain its own pack kernels)"""
+        self.generation += 1
+
     def get(self, w: torch.Tensor, mode: int) -> torch.Tensor:
-        ver = w._version
+        ver = (w._version, self.generation)
         store = getattr(w, self.ATTR, None)
         if store is not None:
             hit = store.get(mode)

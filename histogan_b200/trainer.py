@@ -228,6 +228,12 @@ class Trainer:
         if aug_types is None:
             aug_types = ['translation', 'cutout']
         self.fast_rng = bool(kwargs.pop('fast_rng', False))
+        # cuda_graphs=True: replay each phase (forward + backward) of a regular step as one
+        # CUDA graph (see _train_graphed); steps with the path-length regulariser stay eager
+        self.cuda_graphs = bool(kwargs.pop('cuda_graphs', False))
+        self._graphs = {}
+        self._static = None
+        self.graph_replayed_launches = 0      # library kernels launched through graph replays
         self.GAN_params = [args, kwargs]
         self.GAN = None
         self.hist_method = hist_method
@@ -342,6 +348,11 @@ class Trainer:
         apply_gradient_penalty = self.steps % 4 == 0
         apply_path_penalty = self.steps % 32 == 0
         avg_pl_length = self.pl_mean
+        if self.cuda_graphs and accum == 1 and not apply_path_penalty:
+            total_disc_loss, total_gen_loss, total_hist_loss = self._train_graphed(
+                alpha, apply_gradient_penalty)
+            return self._finish_step(total_disc_loss, total_gen_loss, total_hist_loss,
+                                     apply_path_penalty, avg_pl_length)
 
         # ---------------------------------------------------- discriminator --
         GAN.D_opt.zero_grad()
@@ -410,6 +421,12 @@ class Trainer:
         _allreduce_mean_grads(g_params)
         GAN.G_opt.step()
 
+        return self._finish_step(total_disc_loss, total_gen_loss, total_hist_loss,
+                                 apply_path_penalty, avg_pl_length)
+
+    def _finish_step(self, total_disc_loss, total_gen_loss, total_hist_loss, apply_path_penalty,
+                     avg_pl_length):
+        GAN = self.GAN
         # ------------------------------------------------------ bookkeeping --
         if apply_path_penalty and not np.isnan(avg_pl_length):
             self.pl_mean = self.pl_length_ma.update_average(self.pl_mean, avg_pl_length)
@@ -435,6 +452,115 @@ class Trainer:
             self.evaluate(floor(self.steps / 1000))
         self.steps += 1
         self.av = None
+
+    # ------------------------------------------------------- CUDA-graph path --
+    def _mixed_styles(self, z1, z2, mask):
+        """w_styles of mixed_list / noise_list (histoGAN.py:170-176,215-217) with the split
+        point as a device-side 0/1 mask over the layers, so the graph topology is fixed."""
+        S = self.GAN.S
+        w1, w2 = S(z1)[:, None, :], S(z2)[:, None, :]
+        m = mask[None, :, None]
+        return w1 * m + w2 * (1 - m)
+
+    def _phase_d(self, apply_gp):
+        GAN, st = self.GAN, self._static
+        B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
+        GAN.D_opt.zero_grad(set_to_none=True)
+        z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
+        z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
+        inoise = torch.rand(B, S_, S_, 1, device='cuda')
+        with torch.no_grad():
+            h_w = GAN.H(st['hists']).unsqueeze(1)
+            fake = GAN.G(self._mixed_styles(z1, z2, st['mask']), torch.cat((h_w, h_w), dim=1), inoise)
+        images = st['images_gp'] if apply_gp else st['images']
+        fake_out, _ = GAN.D(fake)
+        real_out, _ = GAN.D(images)
+        divergence = (F.relu(1 + real_out) + F.relu(1 - fake_out)).mean()
+        loss, gp = divergence, None
+        if apply_gp:
+            gp = gradient_penalty(images, real_out)
+            loss = loss + gp
+        loss.backward()
+        return divergence.detach(), (gp.detach() if gp is not None else None)
+
+    def _phase_g(self, alpha):
+        GAN, st = self.GAN, self._static
+        B, S_ = self.batch_size, GAN.G.image_size
+        GAN.G_opt.zero_grad(set_to_none=True)
+        z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
+        z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
+        inoise = torch.rand(B, S_, S_, 1, device='cuda')
+        h_w = GAN.H(st['hists']).unsqueeze(1)
+        fake = GAN.G(self._mixed_styles(z1, z2, st['mask']), torch.cat((h_w, h_w), dim=1), inoise)
+        fake_out, _ = GAN.D(fake)
+        hist_loss = hellinger_loss(st['hists'], self.histBlock(F.relu(fake)), alpha)
+        loss = fake_out.mean()
+        (loss + hist_loss).backward()
+        return loss.detach(), hist_loss.detach()
+
+    def _graphed(self, key, fn):
+        """capture `fn` (one phase: zero_grad + forward + backward) once, then replay"""
+        from . import ops, _lib
+        lib = _lib.load()
+        entry = self._graphs.get(key)
+        if entry is None:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):           # eager warm-up on a side stream
+                fn()
+            torch.cuda.current_stream().wait_stream(side)
+            ops._packs.new_generation()             # the graph must contain its own weight packing
+            g = torch.cuda.CUDAGraph()
+            n0 = lib.hg_launch_count()
+            with torch.cuda.graph(g, pool=self._graphs.get('pool')):
+                outs = fn()
+            self._graphs.setdefault('pool', g.pool())
+            # library kernels recorded in this graph (each replay launches them again)
+            entry = self._graphs[key] = (g, outs, int(lib.hg_launch_count() - n0))
+        entry[0].replay()
+        self.graph_replayed_launches += entry[2]
+        return entry[1]
+
+    def _train_graphed(self, alpha, apply_gp):
+        GAN = self.GAN
+        B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
+        if self._static is None:
+            self._static = {
+                'images': torch.zeros(B, 3, S_, S_, device='cuda'),
+                'images_gp': torch.zeros(B, 3, S_, S_, device='cuda', requires_grad=True),
+                'hists': torch.zeros(B, 3, self.hist_bin, self.hist_bin, device='cuda'),
+                'mask': torch.ones(L, device='cuda'),
+                'mask_host': torch.ones(L).pin_memory(),
+            }
+        st = self._static
+
+        def stage(batch, with_images):
+            get_mixed = random() < self.mixed_prob           # same draws as the eager path
+            tt = int(torch.rand(()).numpy() * L) if get_mixed else L
+            st['mask_host'].copy_((torch.arange(L) < tt).float())
+            st['mask'].copy_(st['mask_host'], non_blocking=True)
+            st['hists'].copy_(batch['histograms'], non_blocking=True)
+            if with_images:
+                dst = st['images_gp'] if apply_gp else st['images']
+                with torch.no_grad():
+                    dst.copy_(batch['images'], non_blocking=True)
+
+        stage(next(self.loader), True)
+        divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp))
+        _allreduce_mean_grads(list(GAN.D.parameters()))
+        GAN.D_opt.step()
+        stage(next(self.loader), False)
+        g_loss, h_loss = self._graphed(('G', float(alpha)), lambda: self._phase_g(alpha))
+        _allreduce_mean_grads([p for grp in GAN.G_opt.param_groups for p in grp['params']])
+        GAN.G_opt.step()
+        # host reads once, after everything has been queued
+        self.q_loss = 0.0
+        if gp is not None:
+            self.last_gp_loss = gp.item()
+        self.d_loss = float(divergence.item())
+        self.g_loss = float(g_loss.item())
+        self.h_loss = float(h_loss.item())
+        return divergence.clone(), g_loss.clone(), h_loss.clone()
 
     # ------------------------------------------------------------ evaluate --
     @torch.no_grad()

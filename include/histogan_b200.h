@@ -204,6 +204,16 @@ int hg_modconv_epilogue_bwd(const float* dy, const float* y, const float* d, con
 int hg_modulate_bwd(float* dxm_inout, const float* x, const float* mod, float* gmod, int32_t B,
                     int32_t HW, int32_t C, hg_stream_t stream);
 
+/* the same two with the generator's 2x bilinear up-sampling (nn.Upsample(scale_factor=2,
+ * mode='bilinear', align_corners=False), :446-447,462-463) folded in: x is the LOW-resolution
+ * (B,H,W,C) activation, xm / dxm the (B,2H,2W,C) conv input / its gradient; the up-sampled
+ * activation is never materialised.                                                 */
+int hg_upsample_modulate_round(const float* x, const float* mod, float* xm, int32_t B, int32_t H,
+                               int32_t W, int32_t C, hg_stream_t stream);
+int hg_upsample_modulate_bwd(const float* dxm, const float* x, const float* mod, float* dx,
+                             float* gmod, int32_t B, int32_t H, int32_t W, int32_t C,
+                             hg_stream_t stream);
+
 /* RGBBlock (:380-386): rgb (B,3,HW) planar = sum_c x[b,p,c] * wmod[b,o,c] (+ prev), with
  * wmod (B,3,C) = conv.weight * (style + 1); backward: dx (B,HW,C) and gw (B,3,C).  */
 int hg_torgb_fwd(const float* x, const float* wmod, const float* prev, float* rgb, int32_t B,

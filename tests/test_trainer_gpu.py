@@ -101,3 +101,29 @@ def test_fused_diffgrad_matches_foreach(cuda_device):
         oa.step(); ob.step()
     for a, b in zip(pa, pb):
         assert torch.allclose(a.detach().cpu(), b.detach(), rtol=1e-5, atol=1e-7)
+
+
+def test_cuda_graph_training_path(tmp_path, cuda_device):
+    """cuda_graphs=True: D phase (with / without gradient penalty) and G phase replayed as
+    CUDA graphs; PL steps stay eager.  Must train like the eager path: finite losses,
+    moving weights, and the same loss scale as an eager trainer fed the same data."""
+    torch.manual_seed(0)
+    tg = _trainer(tmp_path / "g", cuda_graphs=True, fast_rng=True)
+    te = _trainer(tmp_path / "e", fast_rng=True)
+    for t in (tg, te):
+        t.init_GAN()
+    te.GAN.load_state_dict(tg.GAN.state_dict())
+    for t in (tg, te):
+        t.steps = 2501
+        for _ in range(9):                 # 2501..2509: graphs incl. two GP steps
+            t.train(alpha=2)
+    assert set(tg._graphs) >= {('D', False), ('D', True), ('G', 2.0)}
+    for name in ("d_loss", "g_loss", "h_loss", "last_gp_loss"):
+        a, b = getattr(tg, name), getattr(te, name)
+        assert a == a and abs(a) < 1e7, (name, a)
+        print(name, "graphed", a, "eager", b)
+    assert abs(tg.h_loss - te.h_loss) < 0.25 * abs(te.h_loss) + 0.05
+    moved = sum(not torch.equal(p, q) for p, q in zip(tg.GAN.G.parameters(), te.GAN.G.parameters()))
+    assert moved > 10          # different random latents -> different but comparable trajectories
+    tg.steps = 2528                        # a path-length step runs eagerly inside a graphed trainer
+    tg.train(alpha=2)
