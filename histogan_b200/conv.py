@@ -29,14 +29,19 @@ def as_nhwc(x: torch.Tensor) -> torch.Tensor:
     return x.contiguous(memory_format=torch.channels_last)
 
 
+def _up32(n):
+    return (n + 31) // 32 * 32
+
+
 def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
-    """hg_pack_conv_weight: OIHW -> [N][KH][KW][K] K-major TF32.  mode 1 = dgrad."""
+    """hg_pack_conv_weight: OIHW -> [Np][KH][KW][Kp] K-major TF32, N/K zero-padded to
+    multiples of 32.  mode 1 = dgrad (N = Cin, K = Cout, taps flipped)."""
     lib = _lib.load()
     _lib.require_cuda(w_oihw, "pack_weight")
     w = w_oihw.detach().contiguous().float()
     co, ci, kh, kw = w.shape
     n, k = (ci, co) if mode else (co, ci)
-    out = torch.empty((n, kh, kw, k), dtype=torch.float32, device=w.device)
+    out = torch.empty((_up32(n), kh, kw, _up32(k)), dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
         rc = lib.hg_pack_conv_weight(_lib.ptr(w), _lib.ptr(out), co, ci, kh, kw, int(mode),
                                      _lib.current_stream_ptr(w.device))
@@ -45,18 +50,22 @@ def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
 
 
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: int = 1, *,
-                scale=None, bias=None, noise=None, noise_w=None, noise_b=None, residual=None,
-                lrelu: bool = False, slope: float = 0.2, round_tf32: bool = False) -> torch.Tensor:
-    """y = epilogue(conv(x, w)); x (B,Cin,H,W) channels_last, w_packed [Cout][KH][KW][Cin].
-    Returns (B,Cout,OH,OW) channels_last."""
+                cout=None, scale=None, bias=None, noise=None, noise_w=None, noise_b=None,
+                residual=None, lrelu: bool = False, slope: float = 0.2,
+                round_tf32: bool = False) -> torch.Tensor:
+    """y = epilogue(conv(x, w)); x (B,Cin,H,W) channels_last (Cin % 4 == 0), w_packed
+    [Cout_p][KH][KW][Cin_p] from pack_weight; `cout` = true number of output channels
+    (% 4 == 0, default Cout_p).  Returns (B,cout,OH,OW) channels_last."""
     lib = _lib.load()
     _lib.require_cuda(x, "conv2d_nhwc")
     assert x.dtype == torch.float32 and x.dim() == 4
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     B, Cin, H, W = x.shape
-    Cout, KH, KW, Cin2 = w_packed.shape
-    assert Cin2 == Cin, (Cin2, Cin)
+    Cout_p, KH, KW, Cin_p = w_packed.shape
+    assert Cin_p == _up32(Cin), (Cin_p, Cin)
+    Cout = Cout_p if cout is None else int(cout)
+    assert Cout <= Cout_p and _up32(Cout) == Cout_p, (Cout, Cout_p)
     OH = (H + 2 * pad - KH) // stride + 1
     OW = (W + 2 * pad - KW) // stride + 1
     y = torch.empty((B, Cout, OH, OW), dtype=torch.float32, device=x.device,
@@ -92,7 +101,7 @@ def conv2d_wgrad_nhwc(dy: torch.Tensor, x: torch.Tensor, ksize: int, stride: int
     B, Cin, H, W = x.shape
     _, Cout, OH, OW = dy.shape
     p = _lib.ConvParams(B, H, W, Cin, Cout, ksize, ksize, stride, pad, OH, OW)
-    dwp = torch.empty((Cout, ksize, ksize, Cin), dtype=torch.float32, device=x.device)
+    dwp = torch.empty((Cout, ksize, ksize, _up32(Cin)), dtype=torch.float32, device=x.device)
     dw = torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         st = _lib.current_stream_ptr(x.device)

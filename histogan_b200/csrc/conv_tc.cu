@@ -38,7 +38,9 @@ struct ConvArgs {
   int TB, TH, TW;                 // pixel tile (TB*TH*TW == 128)
   int tiles_w, tiles_h;           // tiles per image row / column
   int m_tiles;                    // tiles_w * tiles_h * ceil(B / TB)
-  int kc_per_tap;                 // Cin / 32
+  int kc_per_tap;                 // Kp / 32
+  int Kp;                         // Cin rounded up to 32: K extent of one tap in the packed weight
+  int n_tiles;                    // round_up(Cout, 32) / BLOCK_N
   int flags;
   float slope;
   float* y;
@@ -106,7 +108,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int n_tiles = a.Cout / BLOCK_N;
+  const int n_tiles = a.n_tiles;
   const int total_tiles = a.m_tiles * n_tiles;
   const int taps = a.KH * a.KW;
   const int total_kb = taps * a.kc_per_tap;
@@ -130,7 +132,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             uint8_t* sB = sA + kABytes;
             ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
             ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
-            ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Cin + kc * kBlockK, n0);
+            ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Kp + kc * kBlockK, n0);
             if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
@@ -198,27 +200,47 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (valid) {
+        if (valid && n0 + c0 < a.Cout) {
           const int n = n0 + c0;
+          const int ncols = min(32, a.Cout - n);       // Cout % 4 == 0
           float* yo = a.y + pix * a.Cout + n;
           const float* ro = a.residual ? a.residual + pix * a.Cout + n : nullptr;
           const float* sc = a.scale ? a.scale + (long long)b * a.Cout + n : nullptr;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float o[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float tv = __uint_as_float(v[j + e]);
-              if (sc) tv *= __ldg(sc + j + e);
-              if (a.bias) tv += __ldg(a.bias + n + j + e);
-              if (a.noise) tv = fmaf(nz, __ldg(a.noise_w + n + j + e), tv + __ldg(a.noise_b + n + j + e));
-              if (a.flags & HG_CONV_LRELU) tv = tv > 0.f ? tv : tv * a.slope;
-              if (ro) tv += __ldg(ro + j + e);
-              if (a.flags & HG_CONV_ROUND_TF32) tv = tf32_round(tv);
-              o[e] = tv;
-            }
-            *reinterpret_cast<float4*>(yo + j) = make_float4(o[0], o[1], o[2], o[3]);
+#define HG_EPILOGUE_4(J)                                                                      \
+          {                                                                                   \
+            float o[4];                                                                       \
+            _Pragma("unroll") for (int e = 0; e < 4; ++e) {                                   \
+              float tv = __uint_as_float(v[(J) + e]);                                         \
+              if (sc) tv *= __ldg(sc + (J) + e);                                              \
+              if (a.bias) tv += __ldg(a.bias + n + (J) + e);                                  \
+              if (a.noise)                                                                    \
+                tv = fmaf(nz, __ldg(a.noise_w + n + (J) + e), tv + __ldg(a.noise_b + n + (J) + e)); \
+              if (a.flags & HG_CONV_LRELU) tv = tv > 0.f ? tv : tv * a.slope;                 \
+              if (ro) tv += __ldg(ro + (J) + e);                                              \
+              if (a.flags & HG_CONV_ROUND_TF32) tv = tf32_round(tv);                          \
+              o[e] = tv;                                                                      \
+            }                                                                                 \
+            *reinterpret_cast<float4*>(yo + (J)) = make_float4(o[0], o[1], o[2], o[3]);       \
           }
+          if (ncols == 32) {            // common case: fully unrolled, loads batched by the compiler
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) HG_EPILOGUE_4(j)
+          } else {                      // channel tail (Cout not a multiple of 32)
+#pragma unroll 1
+            for (int j = 0; j < ncols; j += 4) {
+              switch (j) {              // keep v[] in registers: constant indices only
+                case 0: HG_EPILOGUE_4(0) break;
+                case 4: HG_EPILOGUE_4(4) break;
+                case 8: HG_EPILOGUE_4(8) break;
+                case 12: HG_EPILOGUE_4(12) break;
+                case 16: HG_EPILOGUE_4(16) break;
+                case 20: HG_EPILOGUE_4(20) break;
+                case 24: HG_EPILOGUE_4(24) break;
+                default: HG_EPILOGUE_4(28) break;
+              }
+            }
+          }
+#undef HG_EPILOGUE_4
         }
       }
     }
@@ -231,24 +253,27 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
 
 // ------------------------------------------------- weight packing kernel ----
 // OIHW parameter (state_dict layout of Conv2DMod.weight / nn.Conv2d.weight)
-//   -> [N][KH][KW][K] K-major, TF32-rounded.
+//   -> [Np][KH][KW][Kp] K-major, TF32-rounded, Np = round_up(N, 32), Kp = round_up(K, 32),
+//      zero padded (the kernels always move 32-channel boxes; tensors with fewer channels are
+//      completed by TMA's out-of-bounds zero fill, the weights by these explicit zeros).
 // mode 0 (forward):  N = Cout, K = Cin : out[co][kh][kw][ci] = w[co][ci][kh][kw]
 // mode 1 (dgrad):    N = Cin, K = Cout : out[ci][kh][kw][co] = w[co][ci][KH-1-kh][KW-1-kw]
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout,
-                                   int Cin, int KH, int KW, int mode) {
-  const long long total = (long long)Cout * Cin * KH * KW;
+                                   int Cin, int KH, int KW, int mode, int Np, int Kp) {
+  const long long total = (long long)Np * KH * KW * Kp;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
   const int N = mode ? Cin : Cout, K = mode ? Cout : Cin;
-  const int k = (int)(e % K);
-  long long r = e / K;
+  const int k = (int)(e % Kp);
+  long long r = e / Kp;
   const int kw = (int)(r % KW); r /= KW;
   const int kh = (int)(r % KH); r /= KH;
   const int n = (int)r;
-  (void)N;
-  float v;
-  if (mode == 0) v = w[(((long long)n * Cin + k) * KH + kh) * KW + kw];
-  else v = w[(((long long)k * Cin + n) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)];
+  float v = 0.f;                                   // zero padding of both the N and the K extent
+  if (n < N && k < K) {
+    if (mode == 0) v = w[(((long long)n * Cin + k) * KH + kh) * KW + kw];
+    else v = w[(((long long)k * Cin + n) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)];
+  }
   out[e] = tf32_round(v);
 }
 
@@ -291,7 +316,7 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set = true;
   }
-  const int total = m_tiles * (a.Cout / BLOCK_N);
+  const int total = m_tiles * a.n_tiles;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int grid = total < sms ? total : sms;
   conv_tf32_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
@@ -306,10 +331,12 @@ using namespace hg;
 extern "C" int hg_pack_conv_weight(const float* w_oihw, float* w_packed, int32_t Cout, int32_t Cin,
                                    int32_t KH, int32_t KW, int32_t mode, hg_stream_t stream_) {
   if (!w_oihw || !w_packed) return set_error(HG_EINVAL, "null tensor pointer");
-  const long long total = (long long)Cout * Cin * KH * KW;
-  if (total <= 0) return set_error(HG_EINVAL, "empty weight");
+  if ((long long)Cout * Cin * KH * KW <= 0) return set_error(HG_EINVAL, "empty weight");
+  const int N = mode ? Cin : Cout, K = mode ? Cout : Cin;
+  const int Np = (N + 31) / 32 * 32, Kp = (K + 31) / 32 * 32;
+  const long long total = (long long)Np * KH * KW * Kp;
   pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
-      w_oihw, w_packed, Cout, Cin, KH, KW, mode);
+      w_oihw, w_packed, Cout, Cin, KH, KW, mode, Np, Kp);
   HG_LAUNCH_OK("pack_weight_kernel");
   return 0;
 }
@@ -320,12 +347,9 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!x || !w_packed || !y || !p) return set_error(HG_EINVAL, "null pointer");
   if (p->B <= 0) return 0;
-  if (p->Cin % kBlockK != 0)
-    return set_error(HG_ENOSUP, "conv: Cin=%d must be a multiple of %d for the tensor-core path",
-                     p->Cin, kBlockK);
-  if (p->Cout % 32 != 0)
-    return set_error(HG_ENOSUP, "conv: Cout=%d must be a multiple of 32 for the tensor-core path",
-                     p->Cout);
+  if (p->Cin % 4 != 0 || p->Cout % 4 != 0)
+    return set_error(HG_ENOSUP, "conv: Cin=%d and Cout=%d must be multiples of 4 (16-byte TMA rows)",
+                     p->Cin, p->Cout);
   if (p->stride < 1 || p->stride > 2) return set_error(HG_ENOSUP, "conv: stride must be 1 or 2");
   const int OH = (p->H + 2 * p->pad - p->KH) / p->stride + 1;
   const int OW = (p->W + 2 * p->pad - p->KW) / p->stride + 1;
@@ -349,7 +373,9 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
   const int tiles_b = (p->B + TB - 1) / TB;
   const int m_tiles = a.tiles_w * a.tiles_h * tiles_b;
   a.m_tiles = m_tiles;
-  a.kc_per_tap = p->Cin / kBlockK;
+  const int Kp = (p->Cin + 31) / 32 * 32, Np = (p->Cout + 31) / 32 * 32;
+  a.Kp = Kp;
+  a.kc_per_tap = Kp / kBlockK;
   a.flags = ep ? ep->flags : 0;
   a.slope = ep ? ep->lrelu_slope : 0.2f;
   a.y = y;
@@ -375,10 +401,11 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     int rc = encode_map(&tmx, x, 4, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
   }
-  const int Ktot = p->KH * p->KW * p->Cin;
-  const int BN = (p->Cout % 128 == 0) ? 128 : (p->Cout % 64 == 0 ? 64 : 32);
+  const int Ktot = p->KH * p->KW * Kp;
+  const int BN = (Np % 128 == 0) ? 128 : (Np % 64 == 0 ? 64 : 32);
+  a.n_tiles = Np / BN;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->Cout};
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Np};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};
     cuuint32_t box[2] = {(cuuint32_t)kBlockK, (cuuint32_t)BN};
     cuuint32_t estr[2] = {1, 1};

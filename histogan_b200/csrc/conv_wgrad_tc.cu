@@ -30,7 +30,8 @@ struct WgradArgs {
   int tiles_w, tiles_h, tiles_b;
   int co_tiles, ci_tiles, splits;
   int atomic;
-  float* dw;                            // packed [Cout][KH*KW][Cin]
+  float* dw;                            // packed [Cout][KH*KW][Kp], Kp = round_up(Cin, 32)
+  int Kp;
 };
 
 template <int BN, int STAGES>
@@ -155,7 +156,7 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
         ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
         ptx::tmem_ld_wait();
         if (co < a.Cout) {
-          float* o = a.dw + ((long long)co * taps + tap) * a.Cin + ci0 + c0;
+          float* o = a.dw + ((long long)co * taps + tap) * a.Kp + ci0 + c0;
           if (a.atomic) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
@@ -186,7 +187,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __rest
   const int kh = (int)(r % KH); r /= KH;
   const int ci = (int)(r % Cin);
   const int co = (int)(r / Cin);
-  const float v = dwp[(((long long)co * KH + kh) * KW + kw) * Cin + ci];
+  const int Kp = (Cin + 31) / 32 * 32;
+  const float v = dwp[(((long long)co * KH + kh) * KW + kw) * Kp + ci];
   dw[e] = accumulate ? dw[e] + v : v;
 }
 
@@ -240,13 +242,14 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
                                const hg_conv_params* p, hg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!dy || !x || !dw_packed || !p) return set_error(HG_EINVAL, "null pointer");
-  if (p->Cin % 32 != 0 || p->Cout % 32 != 0)
-    return set_error(HG_ENOSUP, "wgrad: Cin=%d and Cout=%d must be multiples of 32", p->Cin, p->Cout);
+  if (p->Cin % 4 != 0 || p->Cout % 4 != 0)
+    return set_error(HG_ENOSUP, "wgrad: Cin=%d and Cout=%d must be multiples of 4", p->Cin, p->Cout);
   if (p->stride < 1 || p->stride > 2) return set_error(HG_ENOSUP, "wgrad: stride must be 1 or 2");
   const int OH = (p->H + 2 * p->pad - p->KH) / p->stride + 1;
   const int OW = (p->W + 2 * p->pad - p->KW) / p->stride + 1;
   if (OH != p->OH || OW != p->OW) return set_error(HG_EINVAL, "wgrad: inconsistent OH/OW");
-  const size_t out_bytes = sizeof(float) * (size_t)p->Cout * p->KH * p->KW * p->Cin;
+  const int Kp = (p->Cin + 31) / 32 * 32;
+  const size_t out_bytes = sizeof(float) * (size_t)p->Cout * p->KH * p->KW * Kp;
   if (p->B <= 0) { HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream)); return 0; }
 
   WgradArgs a{};
@@ -257,9 +260,10 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
   const int PB = kWgPix / (PW * PH);
   a.PW = PW; a.PH = PH; a.PB = PB;
   a.tiles_w = (OW + PW - 1) / PW; a.tiles_h = (OH + PH - 1) / PH; a.tiles_b = (p->B + PB - 1) / PB;
-  const int BN = (p->Cin % 128 == 0) ? 128 : (p->Cin % 64 == 0 ? 64 : 32);
+  const int BN = (Kp % 128 == 0) ? 128 : (Kp % 64 == 0 ? 64 : 32);
   a.co_tiles = (p->Cout + kWgM - 1) / kWgM;
-  a.ci_tiles = p->Cin / BN;
+  a.ci_tiles = Kp / BN;
+  a.Kp = Kp;
   const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
   const int base_ctas = p->KH * p->KW * a.co_tiles * a.ci_tiles;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;

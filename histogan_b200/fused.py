@@ -62,8 +62,8 @@ class _ModConvLayer(torch.autograd.Function):
         mod = mod.contiguous()
         x, xm = (_upsample_modulate_round if upsample else _modulate_round)(x.float(), mod)
         ctx.upsample = upsample
-        y = _conv.conv2d_nhwc(xm, ops._packs.get(w, 0), 1, pad, scale=d, noise=inoise, noise_w=nw,
-                              noise_b=nb, lrelu=True, slope=slope)
+        y = _conv.conv2d_nhwc(xm, ops._packs.get(w, 0), 1, pad, cout=w.shape[0], scale=d,
+                              noise=inoise, noise_w=nw, noise_b=nb, lrelu=True, slope=slope)
         ctx.save_for_backward(x, xm, mod, w, d, inoise, nw, nb, y)
         ctx.slope = slope
         return y
@@ -90,7 +90,7 @@ class _ModConvLayer(torch.autograd.Function):
         _lib.check(rc, "hg_modconv_epilogue_bwd")
         dx = gmod = dw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            dx = _conv.conv2d_nhwc(dz, ops._packs.get(w, 1), 1, k - 1 - (k - 1) // 2)
+            dx = _conv.conv2d_nhwc(dz, ops._packs.get(w, 1), 1, k - 1 - (k - 1) // 2, cout=Cin)
             gmod = torch.empty((B, Cin), dtype=torch.float32, device=dev)
             if ctx.upsample:
                 dxm = dx
@@ -111,7 +111,8 @@ class _ModConvLayer(torch.autograd.Function):
 
 
 def fusable(x, w):
-    return x.is_cuda and w.shape[0] % 32 == 0 and w.shape[1] % 32 == 0 and x.shape[1] % 32 == 0
+    """can conv `w` (OIHW) run as a fused layer on activation x?  (channels multiples of 4)"""
+    return x.is_cuda and w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0
 
 
 def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e-8, upsample=False):

@@ -139,6 +139,7 @@ class GeneratorBlock(nn.Module):
         up = self.upsample is not None
         use_fused = (USE_FUSED and noise1 is None and noise2 is None and inoise is not None
                      and fused.fusable(x, self.conv1.weight) and fused.fusable(x, self.conv2.weight)
+                     and x.shape[1] == self.conv1.weight.shape[1]
                      and self.conv1.demod and self.conv2.demod
                      and x.shape[2] == x.shape[3]
                      and inoise.shape[1] >= x.shape[2] * (2 if up else 1)
@@ -202,8 +203,8 @@ class DiscriminatorBlock(nn.Module):
 
     def forward_padded(self, x, round_out=True):
         """fused path on TF32-rounded NHWC tensors whose channel count is padded to a multiple
-        of 32 with zeros (only D's 3- and 16-channel ends are affected): 4 kernels per block,
-        bias / LeakyReLU / residual sum live in the conv epilogues."""
+        of 32 with zeros (only D's 3- and 16-channel ends are affected): 4 kernels per block, bias /
+        LeakyReLU / residual sum live in the conv epilogues."""
         c1, c2, cr, dn = self.net[0], self.net[2], self.conv_res, self.downsample
         t = ops.conv_bias_act(x, c1.weight, c1.bias, None, 1, 1, act=True, x_rounded=True,
                               round_out=True)

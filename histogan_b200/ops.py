@@ -18,9 +18,10 @@ the conv epilogue, with a backward that is itself built from differentiable piec
 Operands are rounded to TF32 (round-to-nearest-even) right before the MMA and
 accumulated in fp32, which keeps the networks within ~3e-4 of the fp32 reference
 (DESIGN.md "precision").  Producers that already emit TF32-rounded NHWC tensors
-say so (``*_rounded`` flags) and the extra rounding pass is skipped.  Channel
-counts that are not multiples of 32 (the RGB ends of G and D, D's 16-channel block)
-are zero-padded to 32 for the kernel calls.
+say so (``*_rounded`` flags) and the extra rounding pass is skipped.  The kernels take
+channel counts that are multiples of 4 (their 32-channel boxes are completed by TMA's
+out-of-bounds zero fill and zero-padded packed weights); this module pads activations
+to multiples of 32 (see ``_CH``), which only affects D's 3- and 16-channel tensors.
 """
 from __future__ import annotations
 
@@ -31,6 +32,11 @@ import torch
 from . import _lib
 from . import conv as _conv
 
+# Activation channel padding.  The kernels accept any multiple of 4 (16-byte TMA rows; their
+# 32-channel boxes are completed by TMA's out-of-bounds zero fill), but measured on B200 a
+# 16-channel 256^2 conv takes exactly as long as the 32-channel one (the kernel is bound by the
+# number of TMA boxes / MMAs per tile, not by bytes) and the 4-channel image path is slower, so
+# D's 3/16-channel tensors are carried zero-padded to 32 channels.
 _CH = 32
 
 
@@ -43,7 +49,7 @@ def _is_nhwc(x):
 
 
 def round_tf32_nhwc(x: torch.Tensor, already_rounded: bool = False) -> torch.Tensor:
-    """fp32 channels_last copy of x, channels zero-padded to a multiple of 32, TF32-rounded
+    """fp32 channels_last copy of x, channels zero-padded to a multiple of _CH, TF32-rounded
     (no-op when the producer already delivered exactly that)."""
     lib = _lib.load()
     B, Cc, H, W = x.shape
@@ -107,14 +113,7 @@ class _PackCache:
             hit = store.get(mode)
             if hit is not None and hit[0] == ver:
                 return hit[1]
-        co, ci, kh, kw = w.shape
-        cop, cip = _round_up(co), _round_up(ci)
-        wd = w.detach().float()
-        if (cop, cip) != (co, ci):
-            wp = wd.new_zeros((cop, cip, kh, kw))
-            wp[:co, :ci] = wd
-            wd = wp
-        packed = _conv.pack_weight(wd, mode)
+        packed = _conv.pack_weight(w, mode)        # zero-pads both extents to multiples of 32
         if w.is_leaf:                       # parameters persist; temporaries are not worth caching
             if store is None:
                 store = {}
@@ -140,7 +139,8 @@ def _match_channels(y: torch.Tensor, c: int) -> torch.Tensor:
 
 def _raw_conv(x, w, stride, pad, x_rounded=False, padded_io=False):
     """padded_io: x / y carry round_up(C, 32) channels (zeros in the padding) instead of C"""
-    y = _conv.conv2d_nhwc(round_tf32_nhwc(x, x_rounded), _packs.get(w, 0), stride, pad)
+    y = _conv.conv2d_nhwc(round_tf32_nhwc(x, x_rounded), _packs.get(w, 0), stride, pad,
+                          cout=_round_up(w.shape[0]))
     return y if padded_io else _match_channels(y, w.shape[0])
 
 
@@ -152,7 +152,8 @@ def _raw_grad_input(dy, w, stride, pad, in_hw, dy_rounded=False, padded_io=False
         g = dy.new_zeros((dy.shape[0], dy.shape[1], in_hw[0], in_hw[1])).contiguous(
             memory_format=torch.channels_last)
         g[:, :, ::stride, ::stride][:, :, :dy.shape[2], :dy.shape[3]] = dy
-    dx = _conv.conv2d_nhwc(round_tf32_nhwc(g, dy_rounded), _packs.get(w, 1), 1, k - 1 - pad)
+    dx = _conv.conv2d_nhwc(round_tf32_nhwc(g, dy_rounded), _packs.get(w, 1), 1, k - 1 - pad,
+                           cout=_round_up(w.shape[1]))
     assert dx.shape[2:] == tuple(in_hw), (dx.shape, in_hw)
     return dx if padded_io else _match_channels(dx, w.shape[1])
 
@@ -273,7 +274,7 @@ class _BiasActBwd(torch.autograd.Function):
 class _ConvBiasAct(torch.autograd.Function):
     """y = [LeakyReLU](conv(x, w) + b) [+ residual], optionally stored TF32-rounded --
     one kernel (hg_conv2d_fwd with fused epilogue).  Works on channel-padded tensors:
-    x and y carry round_up(C, 32) channels, the padding channels stay exactly zero."""
+    x and y carry round_up(C, _CH) channels, the padding channels stay exactly zero."""
 
     @staticmethod
     def forward(ctx, x, w, b, res, stride, pad, act, slope, x_rounded, round_out):
@@ -284,8 +285,8 @@ class _ConvBiasAct(torch.autograd.Function):
             bp = b.detach().float()
             if cout_p != w.shape[0]:
                 bp = torch.nn.functional.pad(bp, (0, cout_p - w.shape[0]))
-        y = _conv.conv2d_nhwc(xr, _packs.get(w, 0), stride, pad, bias=bp, residual=res, lrelu=act,
-                              slope=slope, round_tf32=round_out)
+        y = _conv.conv2d_nhwc(xr, _packs.get(w, 0), stride, pad, cout=cout_p, bias=bp, residual=res,
+                              lrelu=act, slope=slope, round_tf32=round_out)
         ctx.save_for_backward(xr, w, y if act else None)
         ctx.cfg = (stride, pad, act, slope, b is not None, res is not None, tuple(x.shape))
         return y
@@ -314,7 +315,7 @@ class _ConvBiasAct(torch.autograd.Function):
 def conv_bias_act(x, weight, bias=None, residual=None, stride=1, padding=0, act=False, slope=0.2,
                   x_rounded=False, round_out=False):
     """fused ``[leaky_relu](conv2d(x, weight, bias, stride, padding)) [+ residual]``.
-    Returns a channels_last tensor with round_up(Cout, 32) channels (padding channels are
+    Returns a channels_last tensor with round_up(Cout, _CH) channels (padding channels are
     zero); `x` may itself be such a padded tensor."""
     _lib.require_cuda(x, "conv_bias_act")
     return _ConvBiasAct.apply(x, weight, bias, residual, int(stride), int(padding), bool(act),

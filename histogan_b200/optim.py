@@ -104,3 +104,6 @@ class DiffGrad(Optimizer):
                                       beta1, beta2, eps, step_size, weight_decay,
                                       _lib.current_stream_ptr(dev))
         _lib.check(rc, "hg_diffgrad_step")
+        # the kernel wrote through raw pointers: tell autograd the parameters changed in place
+        # (saved-tensor checks, and the packed-weight caches of ops.py key on ``_version``)
+        torch.autograd.graph.increment_version(ps)

@@ -465,14 +465,17 @@ class Trainer:
     def _phase_d(self, apply_gp):
         GAN, st = self.GAN, self._static
         B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
-        GAN.D_opt.zero_grad(set_to_none=True)
+        # gradients live in PERSISTENT buffers shared by every graph (see _static_grads): zero
+        # them in place (captured as fill kernels) instead of dropping them
+        GAN.D_opt.zero_grad(set_to_none=False)
         z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         inoise = torch.rand(B, S_, S_, 1, device='cuda')
         with torch.no_grad():
             h_w = GAN.H(st['hists']).unsqueeze(1)
             fake = GAN.G(self._mixed_styles(z1, z2, st['mask']), torch.cat((h_w, h_w), dim=1), inoise)
-        images = st['images_gp'] if apply_gp else st['images']
+        # a fresh leaf over the static buffer: its .grad is a graph-local temporary
+        images = st['images'].detach().requires_grad_(True) if apply_gp else st['images']
         fake_out, _ = GAN.D(fake)
         real_out, _ = GAN.D(images)
         divergence = (F.relu(1 + real_out) + F.relu(1 - fake_out)).mean()
@@ -486,7 +489,7 @@ class Trainer:
     def _phase_g(self, alpha):
         GAN, st = self.GAN, self._static
         B, S_ = self.batch_size, GAN.G.image_size
-        GAN.G_opt.zero_grad(set_to_none=True)
+        GAN.G_opt.zero_grad(set_to_none=False)
         z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         inoise = torch.rand(B, S_, S_, 1, device='cuda')
@@ -498,12 +501,26 @@ class Trainer:
         (loss + hist_loss).backward()
         return loss.detach(), hist_loss.detach()
 
+    def _static_grads(self):
+        """Every captured graph must write the gradients where the optimiser reads them.  A
+        graph that allocates its own .grad tensors (zero_grad(set_to_none=True) inside the
+        capture) leaves `p.grad` pointing at the LAST captured graph's buffers, so replaying an
+        older graph would update memory nobody reads.  Hence: one persistent .grad per
+        parameter, allocated outside any graph pool, zeroed/accumulated in place."""
+        for opt in (self.GAN.D_opt, self.GAN.G_opt):
+            for grp in opt.param_groups:
+                for p in grp['params']:
+                    if p.requires_grad and (p.grad is None or getattr(p, '_hg_static_grad', None) is not p.grad):
+                        p.grad = torch.zeros_like(p)
+                        p._hg_static_grad = p.grad
+
     def _graphed(self, key, fn):
         """capture `fn` (one phase: zero_grad + forward + backward) once, then replay"""
         from . import ops, _lib
         lib = _lib.load()
         entry = self._graphs.get(key)
         if entry is None:
+            self._static_grads()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):           # eager warm-up on a side stream
@@ -527,7 +544,6 @@ class Trainer:
         if self._static is None:
             self._static = {
                 'images': torch.zeros(B, 3, S_, S_, device='cuda'),
-                'images_gp': torch.zeros(B, 3, S_, S_, device='cuda', requires_grad=True),
                 'hists': torch.zeros(B, 3, self.hist_bin, self.hist_bin, device='cuda'),
                 'mask': torch.ones(L, device='cuda'),
                 'mask_host': torch.ones(L).pin_memory(),
@@ -541,9 +557,7 @@ class Trainer:
             st['mask'].copy_(st['mask_host'], non_blocking=True)
             st['hists'].copy_(batch['histograms'], non_blocking=True)
             if with_images:
-                dst = st['images_gp'] if apply_gp else st['images']
-                with torch.no_grad():
-                    dst.copy_(batch['images'], non_blocking=True)
+                st['images'].copy_(batch['images'], non_blocking=True)
 
         stage(next(self.loader), True)
         divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp))

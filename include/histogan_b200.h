@@ -125,8 +125,10 @@ int hg_hellinger_bwd(const float* target, const float* hist, int64_t numel, int3
  *   the dense contraction of Conv2DMod.forward (histoGAN/histoGAN.py:420-440),
  *   RGBBlock's 1x1 conv (:375,382), and the DiscriminatorBlock convs (:505-526);
  *   with mode-1 packed weights also their input gradients.
- *   x: (B,H,W,Cin) float32 NHWC, already TF32-rounded by its producer;
- *   w_packed: [Cout][KH][KW][Cin] from hg_pack_conv_weight; y: (B,OH,OW,Cout).
+ *   x: (B,H,W,Cin) float32 NHWC, already TF32-rounded by its producer; y: (B,OH,OW,Cout);
+ *   Cin and Cout multiples of 4.  w_packed: [round_up(Cout,32)][KH][KW][round_up(Cin,32)]
+ *   from hg_pack_conv_weight (zero padded; tensors with fewer than 32 channels are completed
+ *   by TMA's out-of-bounds zero fill).
  * ------------------------------------------------------------------------ */
 #define HG_CONV_LRELU       1   /* LeakyReLU(slope) after scale/bias/noise       */
 #define HG_CONV_ROUND_TF32  2   /* round the stored result to TF32 (RN-even)     */
@@ -160,13 +162,13 @@ typedef struct hg_conv_epilogue {
 int hg_conv2d_fwd(const float* x, const float* w_packed, float* y, const hg_conv_params* p,
                   const hg_conv_epilogue* ep, hg_stream_t stream);
 
-/* OIHW parameter -> packed K-major TF32 weight.
- * mode 0: forward  [Cout][KH][KW][Cin];
- * mode 1: dgrad    [Cin][KH][KW][Cout], taps flipped (conv of dy with it = dx).  */
+/* OIHW parameter -> packed K-major TF32 weight, N and K extents zero-padded to multiples of 32.
+ * mode 0: forward  [Cout_p][KH][KW][Cin_p];
+ * mode 1: dgrad    [Cin_p][KH][KW][Cout_p], taps flipped (conv of dy with it = dx).  */
 int hg_pack_conv_weight(const float* w_oihw, float* w_packed, int32_t Cout, int32_t Cin,
                         int32_t KH, int32_t KW, int32_t mode, hg_stream_t stream);
 
-/* Weight gradient: dw_packed [Cout][KH][KW][Cin] (fully written) =
+/* Weight gradient: dw_packed [Cout][KH][KW][round_up(Cin,32)] (fully written) =
  *   sum over pixels of dy (B,OH,OW,Cout) x shifted x (B,H,W,Cin); both TF32-rounded
  *   by their producers.  hg_unpack_conv_wgrad converts to the OIHW layout of the
  *   nn.Parameter (accumulate != 0: dw_oihw += ...).                              */

@@ -11,7 +11,7 @@ from histogan_b200.trainer import Trainer
 dev = torch.device("cuda", 0)
 out = os.path.join(bench.ROOT, "gpurun_out", "ncu_train")
 tr = Trainer("p", out + "/results", out + "/models", image_size=256, network_capacity=16, batch_size=32,
-             hist_insz=150, hist_resizing="interpolation", save_every=10 ** 9, fast_rng=True)
+             hist_insz=150, hist_resizing="interpolation", save_every=10 ** 9, fast_rng=True)   # eager (no graphs): ncu sees every kernel
 tr.loader = bench.DeviceLoader(0, dev); tr.loader_evaluate = bench.DeviceLoader(0, dev, eval_only=True)
 tr.steps = 2501
 for _ in range(int(sys.argv[1])):

@@ -18,6 +18,11 @@ CASES = [
     (2, 64, 32, 32, 64, 3, 2),     # stride 2 (DiscriminatorBlock.downsample)
     (5, 256, 4, 4, 256, 3, 1),     # batch tail: 5 images, TB = 8
     (1, 32, 24, 40, 32, 3, 1),     # non power-of-two spatial size
+    (2, 16, 32, 32, 16, 3, 1),     # 16-channel D block: 32-wide boxes completed by TMA zero fill
+    (2, 4, 32, 32, 16, 3, 1),      # image padded 3 -> 4 channels
+    (2, 16, 32, 32, 32, 1, 1),
+    (2, 32, 32, 32, 16, 3, 2),
+    (2, 48, 16, 16, 80, 3, 1),     # channel tails inside a k-block / an n-tile
 ]
 
 
@@ -34,7 +39,7 @@ def test_conv_matches_torch(case, cuda_device):
     w = conv.tf32_round(torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
     pad = k // 2
     wp = conv.pack_weight(w, 0)
-    y = conv.conv2d_nhwc(x, wp, stride, pad)
+    y = conv.conv2d_nhwc(x, wp, stride, pad, cout=Cout)
     ref = _ref(x, w, stride, pad)
     assert y.shape == ref.shape
     err = (y - ref).abs().max().item() / ref.abs().max().item()
@@ -73,7 +78,7 @@ def test_dgrad_weight_packing(cuda_device):
     w = conv.tf32_round(torch.randn(96, 64, 3, 3, generator=g) / 24).cuda()
     dy = conv.tf32_round(torch.randn(2, 96, 16, 16, generator=g)).cuda()
     (ref,) = torch.autograd.grad(F.conv2d(x.double(), w.double(), padding=1), x, dy.double())
-    dx = conv.conv2d_nhwc(dy, conv.pack_weight(w, 1), 1, 1)
+    dx = conv.conv2d_nhwc(dy, conv.pack_weight(w, 1), 1, 1, cout=64)
     err = (dx - ref.float()).abs().max().item() / ref.abs().max().item()
     assert err < 2e-5, err
 
@@ -88,6 +93,10 @@ WG_CASES = [
     (2, 64, 32, 32, 128, 1, 1),
     (2, 64, 32, 32, 64, 3, 2),
     (1, 32, 24, 40, 32, 3, 1),
+    (2, 16, 32, 32, 16, 3, 1),
+    (2, 4, 32, 32, 16, 3, 1),
+    (2, 16, 32, 32, 32, 3, 2),
+    (2, 48, 16, 16, 80, 3, 1),
 ]
 
 

@@ -48,7 +48,13 @@ def test_generator(use_fused, cuda_device, monkeypatch):
     around ops.conv2d -- both must sit at the TF32 noise floor."""
     from histogan_b200 import gan
     monkeypatch.setattr(gan, "USE_FUSED", use_fused)
+    from histogan_b200 import _lib, fused
+    calls = {"n": 0}
+    real = fused._ModConvLayer.apply
+    monkeypatch.setattr(fused._ModConvLayer, "apply",
+                        staticmethod(lambda *a, **k: (calls.__setitem__("n", calls["n"] + 1), real(*a, **k))[1]))
     e_gpu, out_gpu = gan_checks.generator_errors("cuda")
+    assert (calls["n"] > 0) == use_fused, "the fused generator layers must actually be the ones running"
     with emulated_conv(round_operands=True):
         e_emu, out_emu = gan_checks.generator_errors("cpu")
     print("generator vs golden (GPU):", {k: f"{v:.2e}" for k, v in e_gpu.items()})
