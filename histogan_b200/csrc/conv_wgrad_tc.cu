@@ -34,20 +34,26 @@ struct WgradArgs {
   int Kp;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int TAPS = 1>
 struct WgradSmem {
   static constexpr int kAChunks = kWgM / 32;
-  static constexpr int kBChunks = BN / 32;
+  static constexpr int kBChunks = (BN / 32) * TAPS;
   static constexpr int kStageBytes = (kAChunks + kBChunks) * kWgChunkBytes;
   static constexpr int kTotal = STAGES * kStageBytes + 1024 + 256;
 };
 
-template <int BN, int STAGES>
+// TAPS == 1: one CTA per (filter tap, co tile, ci tile).
+// TAPS == 9 (3x3 filters with <= 32 input channels -- the 256^2 / 128^2 layers, where the
+//   pixel reduction is longest): one CTA keeps all nine tap accumulators (9 x 32 TMEM columns),
+//   so a dy chunk is fetched once per pixel block instead of once per tap and each pixel block
+//   feeds 72 MMAs instead of 8.
+template <int BN, int STAGES, int TAPS = 1>
 __global__ void __launch_bounds__(kWgThreads)
 conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
                        const __grid_constant__ CUtensorMap tmx, const WgradArgs a) {
-  using SM = WgradSmem<BN, STAGES>;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  using SM = WgradSmem<BN, STAGES, TAPS>;
+  static_assert(TAPS == 1 || (TAPS == 9 && BN == 32), "all-taps variant: 3x3, BN = 32");
+  constexpr uint32_t kTmemCols = TAPS == 9 ? 512 : (BN < 32 ? 32 : BN);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -84,7 +90,7 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
   int id = blockIdx.x;
   const int ci_t = id % a.ci_tiles; id /= a.ci_tiles;
   const int co_t = id % a.co_tiles; id /= a.co_tiles;
-  const int tap = id;
+  const int tap = id;                        // 0 when TAPS == 9
   const int kh = tap / a.KW, kw = tap - kh * a.KW;
   const int co0 = co_t * kWgM, ci0 = ci_t * BN;
   const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
@@ -111,10 +117,17 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
         for (int c = 0; c < SM::kAChunks; ++c)
           if (c < a_chunks)
             ptx::tma_load_4d(sA + c * kWgChunkBytes, &tmdy, &full_bar[stage], co0 + 32 * c, ow0, oh0, b0);
+        if (TAPS == 1) {
 #pragma unroll
-        for (int c = 0; c < SM::kBChunks; ++c)
-          ptx::tma_load_4d(sB + c * kWgChunkBytes, &tmx, &full_bar[stage], ci0 + 32 * c,
-                           ow0 * a.stride + kw - a.pad, oh0 * a.stride + kh - a.pad, b0);
+          for (int c = 0; c < SM::kBChunks; ++c)
+            ptx::tma_load_4d(sB + c * kWgChunkBytes, &tmx, &full_bar[stage], ci0 + 32 * c,
+                             ow0 * a.stride + kw - a.pad, oh0 * a.stride + kh - a.pad, b0);
+        } else {
+#pragma unroll
+          for (int t = 0; t < TAPS; ++t)       // chunk t = the x tile shifted by tap t
+            ptx::tma_load_4d(sB + t * kWgChunkBytes, &tmx, &full_bar[stage], ci0,
+                             ow0 * a.stride + (t % 3) - a.pad, oh0 * a.stride + (t / 3) - a.pad, b0);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
     }
@@ -131,12 +144,16 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
         // MN-major tf32: 128B swizzle with 32B atoms (4 pixel rows x 128 B per atom):
         // LBO = stride between 32-channel chunks, SBO = stride between 4-row groups
         const uint64_t a_desc = ptx::make_smem_desc(sA, kWgChunkBytes, 512, ptx::kLayoutSW128Base32);
-        const uint64_t b_desc = ptx::make_smem_desc(sB, kWgChunkBytes, 512, ptx::kLayoutSW128Base32);
 #pragma unroll
-        for (int k = 0; k < kWgPix / 8; ++k) {
-          // next 8 pixels = 8 rows x 128 B = two swizzle atoms: +64 in (addr >> 4) units
-          ptx::mma_tf32_ss(tmem_base, a_desc + (uint64_t)(k * 64), b_desc + (uint64_t)(k * 64), idesc,
-                           (uint32_t)((kb > kb0) | (k != 0)));
+        for (int t = 0; t < TAPS; ++t) {
+          const uint64_t b_desc = ptx::make_smem_desc(sB + (TAPS == 1 ? 0 : t * kWgChunkBytes),
+                                                      kWgChunkBytes, 512, ptx::kLayoutSW128Base32);
+#pragma unroll
+          for (int k = 0; k < kWgPix / 8; ++k) {
+            // next 8 pixels = 8 rows x 128 B = two swizzle atoms: +64 in (addr >> 4) units
+            ptx::mma_tf32_ss(tmem_base + (uint32_t)(t * BN), a_desc + (uint64_t)(k * 64),
+                             b_desc + (uint64_t)(k * 64), idesc, (uint32_t)((kb > kb0) | (k != 0)));
+          }
         }
         ptx::tc_commit(&empty_bar[stage]);
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -151,12 +168,14 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
       ptx::mbar_wait(tmem_full_bar, 0);
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cc = 0; cc < BN * TAPS; cc += 32) {
         uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
         ptx::tmem_ld_wait();
+        const int c0 = TAPS == 1 ? cc : 0;
+        const int tap_o = TAPS == 1 ? tap : cc / 32;
         if (co < a.Cout) {
-          float* o = a.dw + ((long long)co * taps + tap) * a.Kp + ci0 + c0;
+          float* o = a.dw + ((long long)co * taps + tap_o) * a.Kp + ci0 + c0;
           if (a.atomic) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
@@ -218,18 +237,18 @@ static int encode_nhwc_map(CUtensorMap* m, const void* ptr, int C, int W, int H,
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int TAPS = 1>
 static int launch_wgrad(const CUtensorMap& tmdy, const CUtensorMap& tmx, const WgradArgs& a,
                         cudaStream_t stream) {
-  using SM = WgradSmem<BN, STAGES>;
+  using SM = WgradSmem<BN, STAGES, TAPS>;
   static bool attr_set = false;
   if (!attr_set) {
-    HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BN, STAGES>,
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BN, STAGES, TAPS>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set = true;
   }
-  dim3 grid(a.KH * a.KW * a.co_tiles * a.ci_tiles, a.splits);
-  conv_wgrad_tf32_kernel<BN, STAGES><<<grid, kWgThreads, SM::kTotal, stream>>>(tmdy, tmx, a);
+  dim3 grid((a.KH * a.KW / TAPS) * a.co_tiles * a.ci_tiles, a.splits);
+  conv_wgrad_tf32_kernel<BN, STAGES, TAPS><<<grid, kWgThreads, SM::kTotal, stream>>>(tmdy, tmx, a);
   HG_LAUNCH_OK("conv_wgrad_tf32_kernel");
   return 0;
 }
@@ -265,7 +284,8 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
   a.ci_tiles = Kp / BN;
   a.Kp = Kp;
   const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
-  const int base_ctas = p->KH * p->KW * a.co_tiles * a.ci_tiles;
+  const bool all_taps = p->KH == 3 && p->KW == 3 && Kp == 32 && kb_total >= 64;
+  const int base_ctas = (all_taps ? 1 : p->KH * p->KW) * a.co_tiles * a.ci_tiles;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   int splits = (2 * sms + base_ctas - 1) / base_ctas;
   if (splits > kb_total / 2) splits = kb_total / 2;
@@ -280,6 +300,7 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
   if (rc) return rc;
   rc = encode_nhwc_map(&tmx, x, p->Cin, p->W, p->H, p->B, PW, PH, PB, p->stride);
   if (rc) return rc;
+  if (all_taps) return launch_wgrad<32, 2, 9>(tmdy, tmx, a, stream);
   if (BN == 128) return launch_wgrad<128, 3>(tmdy, tmx, a, stream);
   if (BN == 64) return launch_wgrad<64, 4>(tmdy, tmx, a, stream);
   return launch_wgrad<32, 4>(tmdy, tmx, a, stream);

@@ -97,6 +97,9 @@ WG_CASES = [
     (2, 4, 32, 32, 16, 3, 1),
     (2, 16, 32, 32, 32, 3, 2),
     (2, 48, 16, 16, 80, 3, 1),
+    (2, 16, 64, 64, 16, 3, 1),     # all-taps variant (<= 32 input channels, long pixel reduction)
+    (4, 32, 64, 64, 64, 3, 2),     # all-taps, stride 2
+    (2, 32, 64, 64, 160, 3, 1),    # all-taps, two co tiles with a tail
 ]
 
 
