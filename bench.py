@@ -287,7 +287,7 @@ def run_hist(args):
         }
         if dv.world == 1:
             out["cpu_baseline"] = cpu_baseline_hist()
-        print(json.dumps(out), flush=True)
+        emit(out)
     dv.close()
 
 
@@ -451,7 +451,7 @@ def run_train(args):
         }
         if dv.world == 1:
             out["cpu_baseline"] = cpu_baseline_hist()
-        print(json.dumps(out), flush=True)
+        emit(out)
     dv.close()
 
 
@@ -570,7 +570,28 @@ def run_reference(args):
                                                    f"32-image batch), {steps} step(s)"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries (NCCL's version banner, torchrun children) write to fd 1; the contract is ONE
+    JSON line on stdout.  Route fd 1 to stderr for the run and keep the real stdout aside."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = json.dumps(obj)
+    if _REAL_STDOUT is not None:
+        _REAL_STDOUT.write(line + "\n")
+        _REAL_STDOUT.flush()
+    else:
+        print(line, flush=True)
 
 
 def main():
@@ -581,6 +602,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="train", choices=["train", "hist"])
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -53,10 +53,19 @@ struct ConvArgs {
   int noise_size;
 };
 
-template <int BLOCK_N, int STAGES>
+// HALO variant (3x3, stride 1, 16x8-pixel tiles inside one image): one A box with a one-row
+// halo above and below -- {32 ch, 16, 8+2, 1} = 160 pixel rows = 20 KB -- serves the three
+// vertical taps of a filter column: tap kh starts kh*16 rows = kh*2048 B into the box, a
+// multiple of the 1024 B swizzle atom, so the same canonical UMMA descriptor applies.  The
+// activation is then fetched 3x instead of 9x from L2, which is what bounds the 256^2/128^2
+// layers.
+constexpr int kHaloABytes = (8 + 2) * 16 * kBlockK * 4;   // 20 KB
+
+template <int BLOCK_N, int STAGES, bool HALO = false>
 struct ConvSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAStage = HALO ? kHaloABytes : kABytes;
+  static constexpr int kStageBytes = kAStage + (HALO ? 3 : 1) * kBBytes;
   static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -64,11 +73,11 @@ struct ConvSmem {
 // together share A tiles through L2).  Two TMEM accumulator stages let the epilogue of
 // tile t overlap the main loop of tile t+1; the smem ring (STAGES deep) runs straight
 // through tile boundaries.
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool HALO = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                  const ConvArgs a) {
-  using SM = ConvSmem<BLOCK_N, STAGES>;
+  using SM = ConvSmem<BLOCK_N, STAGES, HALO>;
   constexpr uint32_t kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
@@ -124,16 +133,33 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         const int tb_i = mt / (a.tiles_w * a.tiles_h);
         const int iw0 = tw_i * a.TW * a.stride - a.pad, ih0 = th_i * a.TH * a.stride - a.pad;
         const int b0 = tb_i * a.TB;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int kh = tap / a.KW, kw = tap - kh * a.KW;
-          for (int kc = 0; kc < a.kc_per_tap; ++kc) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-            uint8_t* sA = base + stage * SM::kStageBytes;
-            uint8_t* sB = sA + kABytes;
-            ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
-            ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
-            ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Kp + kc * kBlockK, n0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (HALO) {
+          for (int kw = 0; kw < 3; ++kw) {
+            for (int kc = 0; kc < a.kc_per_tap; ++kc) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+              uint8_t* sA = base + stage * SM::kStageBytes;
+              uint8_t* sB = sA + SM::kAStage;
+              ptx::mbar_expect_tx(&full_bar[stage], SM::kStageBytes);
+              ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0, b0);
+#pragma unroll
+              for (int kh = 0; kh < 3; ++kh)
+                ptx::tma_load_2d(sB + kh * SM::kBBytes, &tmw, &full_bar[stage],
+                                 (kh * 3 + kw) * a.Kp + kc * kBlockK, n0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+          }
+        } else {
+          for (int tap = 0; tap < taps; ++tap) {
+            const int kh = tap / a.KW, kw = tap - kh * a.KW;
+            for (int kc = 0; kc < a.kc_per_tap; ++kc) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+              uint8_t* sA = base + stage * SM::kStageBytes;
+              uint8_t* sB = sA + kABytes;
+              ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
+              ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
+              ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Kp + kc * kBlockK, n0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
           }
         }
       }
@@ -150,17 +176,24 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // epilogue drained this stage
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
-        for (int kb = 0; kb < total_kb; ++kb) {
+        const int iters = HALO ? 3 * a.kc_per_tap : total_kb;
+        for (int kb = 0; kb < iters; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sA = ptx::smem_u32(base + stage * SM::kStageBytes);
-          const uint64_t a_desc = ptx::make_smem_desc(sA, 16, 1024, ptx::kLayoutSW128);
-          const uint64_t b_desc = ptx::make_smem_desc(sA + kABytes, 16, 1024, ptx::kLayoutSW128);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 8; ++k) {
-            // advance 8 tf32 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
-            ptx::mma_tf32_ss(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
-                             (uint32_t)((kb | k) != 0));
+          for (int kh = 0; kh < (HALO ? 3 : 1); ++kh) {
+            // HALO: vertical tap kh = the same box 16 pixel rows (2 swizzle atoms) further down
+            const uint64_t a_desc = ptx::make_smem_desc(sA + (uint32_t)(kh * 2048), 16, 1024,
+                                                        ptx::kLayoutSW128);
+            const uint64_t b_desc = ptx::make_smem_desc(sA + SM::kAStage + (uint32_t)(kh * SM::kBBytes),
+                                                        16, 1024, ptx::kLayoutSW128);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 8; ++k) {
+              // advance 8 tf32 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
+              ptx::mma_tf32_ss(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                               (uint32_t)((kb | kh | k) != 0));
+            }
           }
           ptx::tc_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -306,20 +339,20 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
   return 0;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool HALO = false>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
                        int m_tiles, cudaStream_t stream) {
-  using SM = ConvSmem<BLOCK_N, STAGES>;
+  using SM = ConvSmem<BLOCK_N, STAGES, HALO>;
   static bool attr_set = false;
   if (!attr_set) {
-    HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES>,
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES, HALO>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set = true;
   }
   const int total = m_tiles * a.n_tiles;
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int grid = total < sms ? total : sms;
-  conv_tf32_kernel<BLOCK_N, STAGES><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
+  conv_tf32_kernel<BLOCK_N, STAGES, HALO><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
   HG_LAUNCH_OK("conv_tf32_kernel");
   return 0;
 }
@@ -389,6 +422,10 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
   if (a.noise && (!a.noise_w || !a.noise_b || a.noise_size < OH || a.noise_size < OW))
     return set_error(HG_EINVAL, "conv: noise needs noise_w/noise_b and noise_size >= OH,OW");
 
+  // 3x3 / stride 1 / 16x8 tiles within one image: fetch each activation box once per filter
+  // COLUMN (with a one-row halo) instead of once per tap
+  const bool halo = p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1 && TW == 16 &&
+                    TH == 8 && TB == 1;
   // x: NHWC as a 4-D tensor {C, W, H, B}; strided boxes implement stride-2 convs
   alignas(64) CUtensorMap tmx, tmw;
   {
@@ -396,7 +433,7 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     cuuint64_t strides[3] = {(cuuint64_t)p->Cin * 4, (cuuint64_t)p->W * p->Cin * 4,
                              (cuuint64_t)p->H * p->W * p->Cin * 4};
     cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(TW * p->stride),
-                         (cuuint32_t)(TH * p->stride), (cuuint32_t)TB};
+                         (cuuint32_t)(halo ? TH + 2 : TH * p->stride), (cuuint32_t)TB};
     cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
     int rc = encode_map(&tmx, x, 4, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
@@ -411,6 +448,11 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     cuuint32_t estr[2] = {1, 1};
     int rc = encode_map(&tmw, w_packed, 2, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
+  }
+  if (halo) {
+    if (BN == 128) return launch_conv<128, 3, true>(tmx, tmw, a, m_tiles, stream);
+    if (BN == 64) return launch_conv<64, 4, true>(tmx, tmw, a, m_tiles, stream);
+    return launch_conv<32, 6, true>(tmx, tmw, a, m_tiles, stream);
   }
   if (BN == 128) return launch_conv<128, 6>(tmx, tmw, a, m_tiles, stream);
   if (BN == 64) return launch_conv<64, 8>(tmx, tmw, a, m_tiles, stream);
