@@ -450,7 +450,7 @@ def run_train(args):
             "hist_block": hist_info,
         }
         if dv.world == 1:
-            out["cpu_baseline"] = cpu_baseline_hist()
+            out["cpu_baseline"] = cpu_baseline_train()
         emit(out)
     dv.close()
 
@@ -523,6 +523,37 @@ def cpu_train_step(sd_g, sd_d, sd_s, sd_h, B):
     torch.autograd.grad(g_loss, list(sd_g.values()) + list(sd_s.values()) + list(sd_h.values()))
 
 
+def make_cpu_train_step():
+    """closure running one CPU train step at B=1 with seeded weights (oracle arithmetic)"""
+    from histogan_b200.gan import Discriminator, Generator, HistVectorizer, StyleVectorizer
+    from oracle import gan_oracle as go
+
+    def sd_of(m, seed):
+        shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+        return {k: v.requires_grad_(True) for k, v in go.seeded_state_dict(shapes, seed).items()}
+
+    with torch.device("meta"):
+        mods = (Generator(S, 512, CAPACITY), Discriminator(S, CAPACITY), StyleVectorizer(512, 8),
+                HistVectorizer(H_BINS, 512, 8))
+    sds = [sd_of(m, i + 1) for i, m in enumerate(mods)]
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(min(avail, 32))
+    return lambda: cpu_train_step(*sds, 1)
+
+
+def cpu_baseline_train():
+    """the reference's train-step algorithm (torch-CPU restatement, per-sample grouped convs)
+    on a bounded sample: ONE image instead of the 32-image batch, one step."""
+    step = make_cpu_train_step()
+    t0 = time.perf_counter()
+    step()
+    dt = time.perf_counter() - t0
+    return {"value": round(1.0 / dt, 4), "unit": "images/s", "cores": torch.get_num_threads(),
+            "kind": "port",
+            "what": "HistoGAN train step (D + G phase with histogram loss; no GP/PL/optimiser update)",
+            "sample": "1 image (of the 32-image batch) for 1 step, 256x256, capacity 16"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -534,20 +565,7 @@ def run_reference(args):
             "RGBuvHistBlock fwd + Hellinger loss + bwd, 256x256, h=64, insz=256"
         warm = 1
     else:
-        from histogan_b200.gan import Discriminator, Generator, HistVectorizer, StyleVectorizer
-        from oracle import gan_oracle as go
-
-        def sd_of(m, seed):
-            shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
-            return {k: v.requires_grad_(True) for k, v in go.seeded_state_dict(shapes, seed).items()}
-
-        with torch.device("meta"):
-            mods = (Generator(S, 512, CAPACITY), Discriminator(S, CAPACITY), StyleVectorizer(512, 8),
-                    HistVectorizer(H_BINS, 512, 8))
-        sds = [sd_of(m, i + 1) for i, m in enumerate(mods)]
-        avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        torch.set_num_threads(min(avail, 32))
-        step, sample, what = (lambda: cpu_train_step(*sds, 1)), 1, \
+        step, sample, what = make_cpu_train_step(), 1, \
             ("HistoGAN train step (D + G phase with histogram loss; no GP/PL/optimiser), 256x256, "
              "capacity 16; CPU restatement with per-sample grouped convs as the reference")
         warm = 0
