@@ -14,7 +14,7 @@ import torch
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libhistogan_b200.so"
 
-HG_ABI_VERSION = 1
+HG_ABI_VERSION = 2
 
 RESIZE_IDS = {"interpolation": 0, "sampling": 1}
 METHOD_IDS = {"thresholding": 0, "RBF": 1, "inverse-quadratic": 2}
@@ -27,7 +27,7 @@ class HistParams(C.Structure):
         ("sb", C.c_int64), ("sc", C.c_int64), ("sh", C.c_int64), ("sw", C.c_int64),
         ("h", C.c_int32), ("insz", C.c_int32), ("resizing", C.c_int32), ("method", C.c_int32),
         ("sigma", C.c_double), ("lo", C.c_double), ("hi", C.c_double),
-        ("intensity_scale", C.c_int32), ("green_only", C.c_int32),
+        ("intensity_scale", C.c_int32), ("green_only", C.c_int32), ("projection", C.c_int32),
     ]
 
 

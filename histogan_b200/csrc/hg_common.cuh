@@ -64,6 +64,7 @@ struct HistGeom {
   int OH, OW, N;            // pixel grid entering the histogram
   float scale_h, scale_w;   // bilinear: in/out (area_pixel_compute_scale)
   int method, intensity, green_only;
+  int projection;           // HG_PROJ_*
   float inv_sigma2;         // float(1/sigma^2)
   double sigma2;            // sigma**2 as the reference computes it (float64)
   double thr_half;          // thresholding: eps/2 (RGBuvHistBlock.py:70-71,126)

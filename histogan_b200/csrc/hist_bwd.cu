@@ -256,13 +256,16 @@ hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
   const bool valid = p < g.N;
   for (int i = tid; i < kMaxBins; i += kGBThreads) sC[i] = t.c[i];
 
-  float r = 0.f, gg = 0.f, bb = 0.f, lr = 0.f, lg = 0.f, lb = 0.f, w = 0.f;
+  const bool chroma = g.projection == HG_PROJ_RG_CHROMA;
+  float r = 0.f, gg = 0.f, bb = 0.f, lr = 0.f, lg = 0.f, lb = 0.f, w = 0.f, ssum = 1.f;
   if (valid) {
     load_pixel(x, g, t, b, p, r, gg, bb);
     const PixelProj q = project_pixel(r, gg, bb, g.intensity != 0);
     w = q.iy;
     lr = log_f32(__fadd_rn(r, kEps)); lg = log_f32(__fadd_rn(gg, kEps)); lb = log_f32(__fadd_rn(bb, kEps));
+    ssum = __fadd_rn(__fadd_rn(__fadd_rn(r, gg), bb), kEps);
   }
+  float du_c = 0.f, dv_c = 0.f;               // rg-chroma: d/du, d/dv of the single channel
   float dl[3] = {0.f, 0.f, 0.f};
   float d_iy = 0.f;
 
@@ -273,7 +276,8 @@ hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
     for (int e = tid; e < h * h; e += kGBThreads) sG[e] = Gc[e];
     __syncthreads();
     float u, v;
-    if (ch == 0) { u = __fadd_rn(lr, -lg); v = __fadd_rn(lr, -lb); }
+    if (chroma) { u = __fdiv_rn(r, ssum); v = __fdiv_rn(gg, ssum); }
+    else if (ch == 0) { u = __fadd_rn(lr, -lg); v = __fadd_rn(lr, -lb); }
     else if (ch == 1) { u = __fadd_rn(lg, -lr); v = __fadd_rn(lg, -lb); }
     else { u = __fadd_rn(lb, -lr); v = __fadd_rn(lb, -lg); }
     for (int j = 0; j < h; ++j) {
@@ -298,14 +302,24 @@ hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
       dv = fmaf(sS[j * kGBThreads + tid],
                 (float)kernel_grad_f64(v, sC[j], g.method, g.sigma2,
                                        (double)sKv[j * kGBThreads + tid]), dv);
-    const int ia = ch == 0 ? 1 : 0;            // u-partner
-    const int ib = ch == 2 ? 1 : 2;            // v-partner
-    dl[ch] += du + dv;
-    dl[ia] -= du;
-    dl[ib] -= dv;
+    if (chroma) {
+      du_c = du; dv_c = dv;
+    } else {
+      const int ia = ch == 0 ? 1 : 0;            // u-partner
+      const int ib = ch == 2 ? 1 : 2;            // v-partner
+      dl[ch] += du + dv;
+      dl[ia] -= du;
+      dl[ib] -= dv;
+    }
   }
   if (valid) {
-    float dr = dl[0] / (r + kEps), dg = dl[1] / (gg + kEps), db = dl[2] / (bb + kEps);
+    float dr, dg, db;
+    if (chroma) {   // u = R/S, v = G/S, S = R+G+B+eps
+      const float inv = 1.f / ssum, common = -(du_c * r + dv_c * gg) * inv * inv;
+      dr = fmaf(du_c, inv, common); dg = fmaf(dv_c, inv, common); db = common;
+    } else {
+      dr = dl[0] / (r + kEps); dg = dl[1] / (gg + kEps); db = dl[2] / (bb + kEps);
+    }
     if (g.intensity) {
       const float q = d_iy / w;
       dr = fmaf(q, r, dr); dg = fmaf(q, gg, dg); db = fmaf(q, bb, db);

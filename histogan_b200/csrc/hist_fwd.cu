@@ -194,11 +194,19 @@ hist_fwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
       if (p < g.N) {
         float r, gg, bb;
         load_pixel(x, g, t, b, p, r, gg, bb);
-        const PixelProj q = project_pixel(r, gg, bb, g.intensity != 0);
-        const float lr = log_f32(__fadd_rn(r, kEps)), lg = log_f32(__fadd_rn(gg, kEps)),
-                    lb = log_f32(__fadd_rn(bb, kEps));
-        channel_uv(ch, lr, lg, lb, u, v);
-        w = q.iy;
+        if (g.projection == HG_PROJ_RG_CHROMA) {   // rgChromaHistBlock.py:104-112
+          const float ssum = __fadd_rn(__fadd_rn(__fadd_rn(r, gg), bb), kEps);
+          u = __fdiv_rn(r, ssum);
+          v = __fdiv_rn(gg, ssum);
+          w = g.intensity ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, r), __fmul_rn(gg, gg)),
+                                                           __fmul_rn(bb, bb)), kEps)) : 1.f;
+        } else {
+          const PixelProj q = project_pixel(r, gg, bb, g.intensity != 0);
+          const float lr = log_f32(__fadd_rn(r, kEps)), lg = log_f32(__fadd_rn(gg, kEps)),
+                      lb = log_f32(__fadd_rn(bb, kEps));
+          channel_uv(ch, lr, lg, lb, u, v);
+          w = q.iy;
+        }
       }
       sU[tid] = u; sV[tid] = v; sW[tid] = w;
     }
@@ -301,7 +309,7 @@ __global__ void debug_logf_kernel(const float* __restrict__ in, float* __restric
 
 // ============================================================ host side =====
 bool hist_fast_path(const HistGeom& g, const hg_hist_params* p) {
-  return g.h == 64 && !g.green_only && p->lo == -p->hi &&
+  return g.h == 64 && !g.green_only && g.projection == HG_PROJ_RGB_UV && p->lo == -p->hi &&
          (g.method == HG_METHOD_RBF || g.method == HG_METHOD_INVERSE_QUADRATIC);
 }
 

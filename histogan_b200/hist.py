@@ -21,12 +21,12 @@ EPS = 1e-6
 
 
 def _make_params(x: torch.Tensor, h, insz, resizing_id, method_id, sigma, lo, hi,
-                 intensity_scale, green_only) -> _lib.HistParams:
+                 intensity_scale, green_only, projection=0) -> _lib.HistParams:
     B, Cc, H, W = x.shape
     sb, sc, sh, sw = x.stride()
     return _lib.HistParams(B, Cc, H, W, sb, sc, sh, sw, int(h), int(insz), resizing_id,
                            method_id, float(sigma), float(lo), float(hi),
-                           int(bool(intensity_scale)), int(bool(green_only)))
+                           int(bool(intensity_scale)), int(bool(green_only)), int(projection))
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
@@ -40,7 +40,7 @@ class _RGBuvHistFn(torch.autograd.Function):
     def forward(ctx, x, cfg):
         lib = _lib.load()
         params = _make_params(x, *cfg)
-        nc = 1 if cfg[-1] else 3
+        nc = 1 if (cfg[8] or (len(cfg) > 9 and cfg[9])) else 3     # green_only or rg-chroma
         h = int(cfg[0])
         hist = torch.empty((x.shape[0], nc, h, h), dtype=torch.float32, device=x.device)
         hist_sum = torch.empty((x.shape[0],), dtype=torch.float32, device=x.device)
@@ -149,8 +149,26 @@ class RGBuvHistBlock(nn.Module):
         cfg = (self.h, self.insz, _lib.RESIZE_IDS.get(self.resizing, 0),
                _lib.METHOD_IDS[self.method], getattr(self, 'sigma', 1.0),
                self.hist_boundary[0], self.hist_boundary[1], self.intensity_scale,
-               self.green_only)
+               self.green_only, getattr(self, 'PROJECTION', 0))
         return _RGBuvHistFn.apply(x, cfg)
+
+
+class rgChromaHistBlock(RGBuvHistBlock):
+    """Drop-in for ``histogram_classes.rgChromaHistBlock.rgChromaHistBlock``:
+    one-channel soft histogram of the rg chromaticity u = R/(R+G+B+eps), v = G/(R+G+B+eps)
+    (rgChromaHistBlock.py:53-127); default boundary [0, 1], intensity_scale False.  Shares the
+    generic CUDA kernels of the RGB-uv block (float64 soft-binning like the reference).
+    forward(x): (B, C>=3, H, W) -> (B, 1, h, h)."""
+
+    PROJECTION = 1
+
+    def __init__(self, h=64, insz=150, resizing='interpolation', method='inverse-quadratic',
+                 sigma=0.02, intensity_scale=False, hist_boundary=None, device='cuda'):
+        if hist_boundary is None:
+            hist_boundary = [0, 1]
+        super().__init__(h=h, insz=insz, resizing=resizing, method=method, sigma=sigma,
+                         intensity_scale=intensity_scale, hist_boundary=hist_boundary,
+                         green_only=False, device=device)
 
 
 class _HellingerFn(torch.autograd.Function):

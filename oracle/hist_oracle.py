@@ -130,6 +130,30 @@ def rgb_uv_hist(x: torch.Tensor, **kw) -> torch.Tensor:
     return raw / (raw.sum(dim=1).sum(dim=1).sum(dim=1).view(-1, 1, 1, 1) + EPS)
 
 
+def rg_chroma_hist(x: torch.Tensor, h: int = 64, insz: int = 150, resizing: str = "interpolation",
+                   method: str = "inverse-quadratic", sigma: float = 0.02,
+                   intensity_scale: bool = False, hist_boundary=None) -> torch.Tensor:
+    """Restatement of ``histogram_classes/rgChromaHistBlock.py:75-131``: one-channel soft
+    histogram of (R, G) / (R+G+B+EPS); same float64 soft-binning / float32 matmul structure."""
+    if hist_boundary is None:
+        hist_boundary = [0, 1]
+    lo, hi = sorted(hist_boundary)
+    thr = (abs(lo) + abs(hi)) / h
+    centres = torch.tensor(bin_centres(lo, hi, h))
+    xs = preprocess(x, h, insz, resizing)
+    out = []
+    for img in torch.unbind(xs, dim=0):
+        I = torch.t(img.reshape(3, -1))                      # (N,3)
+        II = torch.pow(I, 2)
+        Iy = torch.sqrt(II[:, 0] + II[:, 1] + II[:, 2] + EPS).unsqueeze(1) if intensity_scale else 1
+        ssum = torch.sum(I, dim=-1) + EPS
+        Ku = _soft_assign(I[:, 0] / ssum, centres, method, sigma, thr)
+        Kv = _soft_assign(I[:, 1] / ssum, centres, method, sigma, thr)
+        out.append(torch.mm(torch.t(Iy * Ku), Kv).unsqueeze(0))
+    raw = torch.stack(out, dim=0)
+    return raw / (raw.sum(dim=1).sum(dim=1).sum(dim=1).view(-1, 1, 1, 1) + EPS)
+
+
 SCALE = 1 / np.sqrt(2.0)  # histoGAN/histoGAN.py:54
 
 

@@ -75,11 +75,37 @@ def make_hist_goldens():
         print(f"{name}: hist {tuple(hist.shape)} loss {loss.item():.7f}")
 
 
+CHROMA_CASES = [
+    ("chroma_default_2x48", ho.synth_generator_like, 2, 48, 3, dict()),
+    ("chroma_interp_intensity_2x160", ho.synth_signed, 2, 160, 4, dict(insz=100, intensity_scale=True, h=32)),
+    ("chroma_rbf_sampling_2x160", ho.synth_uniform, 2, 160, 3, dict(insz=100, resizing="sampling", method="RBF", sigma=0.05)),
+]
+
+
+def make_chroma_goldens():
+    """histogram_classes/rgChromaHistBlock.py run unmodified on CPU."""
+    import importlib
+    ref_shim._ensure_path()
+    mod = importlib.import_module("histogram_classes.rgChromaHistBlock")
+    for name, maker, B, S, Cc, kwargs in CHROMA_CASES:
+        x = maker(B, S, seed=0, C=Cc)
+        h = kwargs.get("h", 64)
+        w = ho.synth_random_target(B, h=h, seed=1, nc=1)
+        xr = x.clone().requires_grad_(True)
+        hist = mod.rgChromaHistBlock(device="cpu", **kwargs)(xr)
+        (grad,) = torch.autograd.grad((hist * w).sum(), xr)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), x=x.numpy(), target=w.numpy(),
+                            hist=hist.detach().numpy(), grad_x_lin=grad.numpy(),
+                            loss=np.float32(0), alpha=np.float32(0), kwargs=json.dumps(kwargs))
+        print(f"{name}: hist {tuple(hist.shape)}")
+
+
 def main():
     assert ref_shim.available(), "reference not mounted; goldens can only be made in the build container"
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     make_hist_goldens()
+    make_chroma_goldens()
     try:
         from . import make_golden_gan
         make_golden_gan.main()

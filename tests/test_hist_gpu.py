@@ -158,3 +158,18 @@ def test_clamp_and_relu_masks(cuda_device):
     assert got[0, 0, 0, 0] == 0 and got[0, 0, 0, 4] == 0
     assert got[0, 0, 0, 1] != 0 and got[0, 0, 0, 3] != 0
     parity.assert_grad(got, ref, "clamp mask")
+
+
+@pytest.mark.parametrize("name", parity.golden_names("chroma_"))
+def test_rg_chroma_block_against_reference_golden(name, cuda_device):
+    """rgChromaHistBlock on the generic CUDA kernels vs the unmodified reference."""
+    from histogan_b200 import rgChromaHistBlock
+    g = parity.load_golden(name)
+    kw = {k: (list(v) if isinstance(v, list) else v) for k, v in g["kwargs"].items()}
+    x = g["x"].cuda().requires_grad_(True)
+    hist = rgChromaHistBlock(device="cuda", **kw)(x)
+    assert hist.shape == g["hist"].shape
+    atol = 1e-6 if kw.get("method") == "RBF" else 1e-9
+    print(name, parity.assert_hist_e2e(hist, g["hist"], name, atol_frac=atol))
+    (hist * g["target"].cuda()).sum().backward()
+    parity.assert_grad(x.grad, g["grad_x_lin"], name)
