@@ -7,7 +7,7 @@ path behind the reference's own Python class API.
 The arithmetic lives in ``lib/libhistogan_b200.so`` (C ABI: include/histogan_b200.h),
 built from ``csrc/*.cu`` by ``python -m histogan_b200.build``.
 """
-from .hist import (RGBuvHistBlock, rgChromaHistBlock, hellinger_loss, hist_preprocess,  # noqa: F401
+from .hist import (RGBuvHistBlock, rgChromaHistBlock, LabHistBlock, hellinger_loss, hist_preprocess,  # noqa: F401
                    device_logf)
 
-__all__ = ["RGBuvHistBlock", "rgChromaHistBlock", "hellinger_loss"]
+__all__ = ["RGBuvHistBlock", "rgChromaHistBlock", "LabHistBlock", "hellinger_loss"]

@@ -257,11 +257,12 @@ hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
   for (int i = tid; i < kMaxBins; i += kGBThreads) sC[i] = t.c[i];
 
   const bool chroma = g.projection == HG_PROJ_RG_CHROMA;
+  const bool lab = g.projection == HG_PROJ_LAB;
   float r = 0.f, gg = 0.f, bb = 0.f, lr = 0.f, lg = 0.f, lb = 0.f, w = 0.f, ssum = 1.f;
   if (valid) {
     load_pixel(x, g, t, b, p, r, gg, bb);
     const PixelProj q = project_pixel(r, gg, bb, g.intensity != 0);
-    w = q.iy;
+    w = lab ? (g.intensity ? r : 1.f) : q.iy;
     lr = log_f32(__fadd_rn(r, kEps)); lg = log_f32(__fadd_rn(gg, kEps)); lb = log_f32(__fadd_rn(bb, kEps));
     ssum = __fadd_rn(__fadd_rn(__fadd_rn(r, gg), bb), kEps);
   }
@@ -277,6 +278,7 @@ hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
     __syncthreads();
     float u, v;
     if (chroma) { u = __fdiv_rn(r, ssum); v = __fdiv_rn(gg, ssum); }
+    else if (lab) { u = gg; v = bb; }
     else if (ch == 0) { u = __fadd_rn(lr, -lg); v = __fadd_rn(lr, -lb); }
     else if (ch == 1) { u = __fadd_rn(lg, -lr); v = __fadd_rn(lg, -lb); }
     else { u = __fadd_rn(lb, -lr); v = __fadd_rn(lb, -lg); }
@@ -302,7 +304,7 @@ hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
       dv = fmaf(sS[j * kGBThreads + tid],
                 (float)kernel_grad_f64(v, sC[j], g.method, g.sigma2,
                                        (double)sKv[j * kGBThreads + tid]), dv);
-    if (chroma) {
+    if (chroma || lab) {
       du_c = du; dv_c = dv;
     } else {
       const int ia = ch == 0 ? 1 : 0;            // u-partner
@@ -314,13 +316,15 @@ hist_bwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
   }
   if (valid) {
     float dr, dg, db;
-    if (chroma) {   // u = R/S, v = G/S, S = R+G+B+eps
+    if (lab) {      // u = a, v = b, weight = L (LabHistBlock.py:104-111)
+      dr = g.intensity ? d_iy : 0.f; dg = du_c; db = dv_c;
+    } else if (chroma) {   // u = R/S, v = G/S, S = R+G+B+eps
       const float inv = 1.f / ssum, common = -(du_c * r + dv_c * gg) * inv * inv;
       dr = fmaf(du_c, inv, common); dg = fmaf(dv_c, inv, common); db = common;
     } else {
       dr = dl[0] / (r + kEps); dg = dl[1] / (gg + kEps); db = dl[2] / (bb + kEps);
     }
-    if (g.intensity) {
+    if (g.intensity && !lab) {
       const float q = d_iy / w;
       dr = fmaf(q, r, dr); dg = fmaf(q, gg, dg); db = fmaf(q, bb, db);
     }

@@ -200,6 +200,8 @@ hist_fwd_generic_kernel(const float* __restrict__ x, const HistGeom g, const His
           v = __fdiv_rn(gg, ssum);
           w = g.intensity ? __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r, r), __fmul_rn(gg, gg)),
                                                            __fmul_rn(bb, bb)), kEps)) : 1.f;
+        } else if (g.projection == HG_PROJ_LAB) {    // LabHistBlock.py:104-111 (input is Lab in [0,1])
+          u = gg; v = bb; w = g.intensity ? r : 1.f;
         } else {
           const PixelProj q = project_pixel(r, gg, bb, g.intensity != 0);
           const float lr = log_f32(__fadd_rn(r, kEps)), lg = log_f32(__fadd_rn(gg, kEps)),

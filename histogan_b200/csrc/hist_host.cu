@@ -54,11 +54,11 @@ int make_hist_geom(const hg_hist_params* p, HistGeom* g, HistTables* t) {
   g->B = p->B; g->C = p->C; g->H = p->H; g->W = p->W;
   g->sb = p->sb; g->sc = p->sc; g->sh = p->sh; g->sw = p->sw;
   g->h = p->h;
-  if (p->projection != HG_PROJ_RGB_UV && p->projection != HG_PROJ_RG_CHROMA)
+  if (p->projection < HG_PROJ_RGB_UV || p->projection > HG_PROJ_LAB)
     return set_error(HG_EINVAL, "unknown projection id %d", p->projection);
   g->projection = p->projection;
   g->green_only = (p->green_only && p->projection == HG_PROJ_RGB_UV) ? 1 : 0;
-  g->nc = (g->green_only || p->projection == HG_PROJ_RG_CHROMA) ? 1 : 3;
+  g->nc = (g->green_only || p->projection != HG_PROJ_RGB_UV) ? 1 : 3;
   g->method = p->method;
   g->intensity = p->intensity_scale ? 1 : 0;
   g->sigma2 = p->sigma * p->sigma;

@@ -171,6 +171,14 @@ class rgChromaHistBlock(RGBuvHistBlock):
                          green_only=False, device=device)
 
 
+class LabHistBlock(rgChromaHistBlock):
+    """Drop-in for ``histogram_classes.LabHistBlock.LabHistBlock``: one-channel soft
+    histogram over the (a, b) planes of an image already in Lab scaled to [0, 1], weighted by L
+    when ``intensity_scale`` (LabHistBlock.py:73-145).  forward(x) -> (B, 1, h, h)."""
+
+    PROJECTION = 2
+
+
 class _HellingerFn(torch.autograd.Function):
     """hg_hellinger_fwd / hg_hellinger_bwd."""
 

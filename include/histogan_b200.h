@@ -57,8 +57,10 @@ enum { HG_RESIZE_INTERPOLATION = 0, HG_RESIZE_SAMPLING = 1 };
 enum { HG_METHOD_THRESHOLDING = 0, HG_METHOD_RBF = 1, HG_METHOD_INVERSE_QUADRATIC = 2 };
 /* colour projection: RGB-uv log-chroma, 3 (or green-only 1) channels
  * (histogram_classes/RGBuvHistBlock.py:112-115,150-153,190-193) or rg-chromaticity,
- * 1 channel: u = R/(R+G+B+eps), v = G/(R+G+B+eps) (histogram_classes/rgChromaHistBlock.py:111-112) */
-enum { HG_PROJ_RGB_UV = 0, HG_PROJ_RG_CHROMA = 1 };
+ * 1 channel: u = R/(R+G+B+eps), v = G/(R+G+B+eps) (histogram_classes/rgChromaHistBlock.py:111-112),
+ * or Lab, 1 channel: u = a, v = b, weight L (histogram_classes/LabHistBlock.py:104-111; the input
+ * is already Lab scaled to [0,1]) */
+enum { HG_PROJ_RGB_UV = 0, HG_PROJ_RG_CHROMA = 1, HG_PROJ_LAB = 2 };
 
 typedef struct hg_hist_params {
   /* input image batch x: (B, C>=3, H, W) float32, element strides sb/sc/sh/sw */
@@ -73,7 +75,7 @@ typedef struct hg_hist_params {
   double  lo, hi;           /* sorted hist_boundary (default -3, 3)           */
   int32_t intensity_scale;  /* bool                                            */
   int32_t green_only;       /* bool: output has 1 channel (the G histogram)   */
-  int32_t projection;       /* HG_PROJ_* (rg-chroma: 1 output channel)         */
+  int32_t projection;       /* HG_PROJ_* (rg-chroma / Lab: 1 output channel)   */
 } hg_hist_params;
 
 /* number of pixels per image that enter the histogram after the optional

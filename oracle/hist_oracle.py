@@ -154,6 +154,28 @@ def rg_chroma_hist(x: torch.Tensor, h: int = 64, insz: int = 150, resizing: str 
     return raw / (raw.sum(dim=1).sum(dim=1).sum(dim=1).view(-1, 1, 1, 1) + EPS)
 
 
+def lab_hist(x: torch.Tensor, h: int = 64, insz: int = 150, resizing: str = "interpolation",
+             method: str = "inverse-quadratic", sigma: float = 0.02,
+             intensity_scale: bool = False, hist_boundary=None) -> torch.Tensor:
+    """Restatement of ``histogram_classes/LabHistBlock.py:73-145``: (a, b) soft histogram of an
+    image already in Lab/[0,1], weighted by L when intensity_scale."""
+    if hist_boundary is None:
+        hist_boundary = [0, 1]
+    lo, hi = sorted(hist_boundary)
+    thr = (abs(lo) + abs(hi)) / h
+    centres = torch.tensor(bin_centres(lo, hi, h))
+    xs = preprocess(x, h, insz, resizing)
+    out = []
+    for img in torch.unbind(xs, dim=0):
+        I = torch.t(img.reshape(3, -1))
+        Il = I[:, 0].unsqueeze(1) if intensity_scale else 1
+        Ka = _soft_assign(I[:, 1], centres, method, sigma, thr)
+        Kb = _soft_assign(I[:, 2], centres, method, sigma, thr)
+        out.append(torch.mm(torch.t(Il * Ka), Kb).unsqueeze(0))
+    raw = torch.stack(out, dim=0)
+    return raw / (raw.sum(dim=1).sum(dim=1).sum(dim=1).view(-1, 1, 1, 1) + EPS)
+
+
 SCALE = 1 / np.sqrt(2.0)  # histoGAN/histoGAN.py:54
 
 

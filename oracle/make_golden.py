@@ -82,17 +82,29 @@ CHROMA_CASES = [
 ]
 
 
+LAB_CASES = [
+    ("lab_default_2x48", ho.synth_uniform, 2, 48, 3, dict()),
+    ("lab_interp_intensity_2x160", ho.synth_signed, 2, 160, 4, dict(insz=100, intensity_scale=True, h=32)),
+    ("lab_rbf_sampling_2x160", ho.synth_generator_like, 2, 160, 3, dict(insz=100, resizing="sampling", method="RBF", sigma=0.05)),
+]
+
+
 def make_chroma_goldens():
-    """histogram_classes/rgChromaHistBlock.py run unmodified on CPU."""
+    """histogram_classes/{rgChromaHistBlock,LabHistBlock}.py run unmodified on CPU."""
     import importlib
     ref_shim._ensure_path()
-    mod = importlib.import_module("histogram_classes.rgChromaHistBlock")
-    for name, maker, B, S, Cc, kwargs in CHROMA_CASES:
+    _one_channel_goldens(importlib.import_module("histogram_classes.rgChromaHistBlock").rgChromaHistBlock,
+                         CHROMA_CASES)
+    _one_channel_goldens(importlib.import_module("histogram_classes.LabHistBlock").LabHistBlock, LAB_CASES)
+
+
+def _one_channel_goldens(cls, cases):
+    for name, maker, B, S, Cc, kwargs in cases:
         x = maker(B, S, seed=0, C=Cc)
         h = kwargs.get("h", 64)
         w = ho.synth_random_target(B, h=h, seed=1, nc=1)
         xr = x.clone().requires_grad_(True)
-        hist = mod.rgChromaHistBlock(device="cpu", **kwargs)(xr)
+        hist = cls(device="cpu", **kwargs)(xr)
         (grad,) = torch.autograd.grad((hist * w).sum(), xr)
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + ".npz"), x=x.numpy(), target=w.numpy(),
                             hist=hist.detach().numpy(), grad_x_lin=grad.numpy(),

@@ -160,10 +160,13 @@ def test_clamp_and_relu_masks(cuda_device):
     parity.assert_grad(got, ref, "clamp mask")
 
 
-@pytest.mark.parametrize("name", parity.golden_names("chroma_"))
+@pytest.mark.parametrize("name", parity.golden_names("chroma_") + parity.golden_names("lab_"))
 def test_rg_chroma_block_against_reference_golden(name, cuda_device):
-    """rgChromaHistBlock on the generic CUDA kernels vs the unmodified reference."""
-    from histogan_b200 import rgChromaHistBlock
+    """rgChromaHistBlock / LabHistBlock on the generic CUDA kernels vs the
+    unmodified reference classes."""
+    from histogan_b200 import rgChromaHistBlock, LabHistBlock
+    if name.startswith("lab_"):
+        rgChromaHistBlock = LabHistBlock
     g = parity.load_golden(name)
     kw = {k: (list(v) if isinstance(v, list) else v) for k, v in g["kwargs"].items()}
     x = g["x"].cuda().requires_grad_(True)

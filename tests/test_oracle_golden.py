@@ -43,12 +43,13 @@ def test_hist_invariants():
     assert torch.isfinite(hb).all()
 
 
-@pytest.mark.parametrize("name", parity.golden_names("chroma_"))
+@pytest.mark.parametrize("name", parity.golden_names("chroma_") + parity.golden_names("lab_"))
 def test_chroma_oracle_matches_golden(name):
     g = parity.load_golden(name)
-    hist = ho.rg_chroma_hist(g["x"], **g["kwargs"])
+    fn = ho.lab_hist if name.startswith("lab_") else ho.rg_chroma_hist
+    hist = fn(g["x"], **g["kwargs"])
     assert hist.shape == g["hist"].shape
     assert parity.rel_err(hist, g["hist"], 1e-7).max().item() < 2e-6
     x = g["x"].clone().requires_grad_(True)
-    (gx,) = torch.autograd.grad((ho.rg_chroma_hist(x, **g["kwargs"]) * g["target"]).sum(), x)
+    (gx,) = torch.autograd.grad((fn(x, **g["kwargs"]) * g["target"]).sum(), x)
     parity.assert_grad(gx, g["grad_x_lin"], name)
