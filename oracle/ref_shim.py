@@ -60,3 +60,18 @@ def ref_gan_module():
     finally:
         torch.cuda.is_available = saved
     return mod
+
+
+def ref_rehisto_module():
+    """``ReHistoGAN.rehistoGAN`` of the reference (needs the same stubs as histoGAN.histoGAN)."""
+    import torch
+    ref_gan_module()
+    saved = torch.cuda.is_available
+    torch.cuda.is_available = lambda: True
+    try:
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return importlib.import_module("ReHistoGAN.rehistoGAN")
+    finally:
+        torch.cuda.is_available = saved
