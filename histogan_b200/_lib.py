@@ -79,6 +79,14 @@ _SIGNATURES = {
     "hg_bias_act_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_float, C.c_void_p]),
     "hg_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),
+    "hg_instnorm_lrelu_fwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_float, C.c_float,
+                                                                         C.c_int32, C.c_void_p]),
+    "hg_instnorm_lrelu_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 3 + [C.c_float, C.c_float,
+                                                                         C.c_int32, C.c_void_p]),
+    "hg_laplacian_l1_workspace_bytes": (C.c_size_t, []),
+    "hg_laplacian_l1_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_size_t] + [C.c_int32] * 3 + [C.c_void_p]),
+    "hg_laplacian_l1_bwd": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 3 + [C.c_void_p]),
+    "hg_depthwise_conv": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 6 + [C.c_void_p]),
     "hg_hellinger_workspace_bytes": (C.c_size_t, []),
     "hg_hellinger_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -56,16 +56,16 @@ def _upsample_modulate_round(x, mod):
 
 class _ModConvLayer(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, mod, w, d, inoise, nw, nb, slope, upsample):
+    def forward(ctx, x, mod, w, d, inoise, nw, nb, slope, upsample, act=True):
         k = w.shape[2]
         pad = (k - 1) // 2
         mod = mod.contiguous()
         x, xm = (_upsample_modulate_round if upsample else _modulate_round)(x.float(), mod)
         ctx.upsample = upsample
         y = _conv.conv2d_nhwc(xm, ops._packs.get(w, 0), 1, pad, cout=w.shape[0], scale=d,
-                              noise=inoise, noise_w=nw, noise_b=nb, lrelu=True, slope=slope)
+                              noise=inoise, noise_w=nw, noise_b=nb, lrelu=act, slope=slope)
         ctx.save_for_backward(x, xm, mod, w, d, inoise, nw, nb, y)
-        ctx.slope = slope
+        ctx.slope = slope if act else 1.0       # no activation == LeakyReLU with slope 1
         return y
 
     @staticmethod
@@ -107,7 +107,7 @@ class _ModConvLayer(torch.autograd.Function):
                 _lib.check(rc, "hg_modulate_bwd")
         if ctx.needs_input_grad[2]:
             dw = _conv.conv2d_wgrad_nhwc(dz, xm, k, 1, (k - 1) // 2)
-        return dx, gmod, dw, gd, None, gnw, gnb, None, None
+        return dx, gmod, dw, gd, None, gnw, gnb, None, None, None
 
 
 def fusable(x, w):
@@ -115,10 +115,12 @@ def fusable(x, w):
     return x.is_cuda and w.shape[0] % 4 == 0 and w.shape[1] % 4 == 0
 
 
-def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e-8, upsample=False):
+def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e-8, upsample=False,
+                   act=True):
     """LeakyReLU(Conv2DMod(up(x), style) + to_noise(inoise).permute(0,3,2,1)) in one fused op.
     style (B,Cin); inoise (B,S,S,1) image noise or None; noise_lin = the nn.Linear(1, Cout);
-    upsample=True folds the block's 2x bilinear nn.Upsample of x into the op."""
+    upsample=True folds the block's 2x bilinear nn.Upsample of x into the op; act=False drops
+    the LeakyReLU (a bare Conv2DMod.forward, histoGAN.py:420-440)."""
     mod = style + 1                                                    # histoGAN.py:423-425
     d = None
     if demod:                                                          # :427-429
@@ -129,7 +131,7 @@ def mod_conv_layer(x, style, weight, demod, inoise, noise_lin, slope=0.2, eps=1e
         nz = inoise.reshape(inoise.shape[0], inoise.shape[1], inoise.shape[2])
         nw = noise_lin.weight.reshape(-1)
         nb = noise_lin.bias
-    return _ModConvLayer.apply(x, mod, weight, d, nz, nw, nb, slope, bool(upsample))
+    return _ModConvLayer.apply(x, mod, weight, d, nz, nw, nb, slope, bool(upsample), bool(act))
 
 
 class _ToRGB(torch.autograd.Function):

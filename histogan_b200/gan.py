@@ -67,6 +67,9 @@ class Conv2DMod(nn.Module):
             raise NotImplementedError("Conv2DMod on the sm_100a path supports stride=dilation=1 "
                                       "(all the reference ever instantiates)")
         h = x.shape[2]
+        if (USE_FUSED and fused.fusable(x, self.weight) and x.shape[1] == self.weight.shape[1]
+                and self.kernel in (1, 3)):
+            return fused.mod_conv_layer(x, y, self.weight, self.demod, None, None, act=False)
         mod = y + 1                                                   # :423-425
         z = ops.conv2d(x * mod[:, :, None, None], self.weight, None, 1,
                        self._get_same_padding(h, self.kernel, self.dilation, self.stride))

@@ -246,6 +246,39 @@ int hg_diffgrad_step(int32_t count, float* const* p, const float* const* g, floa
                      float beta2, float eps, float step_size, float weight_decay,
                      hg_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * ReHistoGAN recolouring step (ReHistoGAN/rehistoGAN.py), SURVEY 8f-1.
+ * ------------------------------------------------------------------------ */
+
+/* nn.InstanceNorm2d(affine=False) + LeakyReLU of EncoderBlock (:489-495) on an NHWC
+ * activation x (B,HW,C), C % 4 == 0: y = lrelu((x - mean_bc) * rsqrt(var_bc + eps)), biased
+ * variance; `stats` (B*C*2 doubles: sum, sum of squares) is written by fwd and read by bwd.
+ * round_tf32: store y / dx rounded to TF32 (they feed a tensor-core convolution).
+ * bwd: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * lrelu'(xhat); `ws` is
+ * B*C*2 doubles of scratch.                                                             */
+int hg_instnorm_lrelu_fwd(const float* x, float* y, double* stats, int32_t B, int32_t HW, int32_t C,
+                          float eps, float slope, int32_t round_tf32, hg_stream_t stream);
+int hg_instnorm_lrelu_bwd(const float* dy, const float* x, const double* stats, float* dx, double* ws,
+                          int32_t B, int32_t HW, int32_t C, float eps, float slope,
+                          int32_t round_tf32, hg_stream_t stream);
+
+/* reconstruction_loss('2nd gradient').compute_loss (:293-299,321-324): a, b planar (B,3,H,W);
+ * loss[0] = mean over (B,H,W) of | lap(sum_c a_c) - lap(sum_c b_c) |, 5-point laplacian with
+ * zero padding; `sign` (B*H*W int8) keeps sign(lap a - lap b) for the backward, which writes
+ * d loss / d b = -(gout[0] / (B*H*W)) * lap(sign) into all three planes of db.           */
+size_t hg_laplacian_l1_workspace_bytes(void);
+int hg_laplacian_l1_fwd(const float* a, const float* b, float* loss, int8_t* sign, void* ws,
+                        size_t ws_bytes, int32_t B, int32_t H, int32_t W, hg_stream_t stream);
+int hg_laplacian_l1_bwd(const int8_t* sign, const float* gout, float* db, int32_t B, int32_t H,
+                        int32_t W, hg_stream_t stream);
+
+/* gaussian_op (:228-232; the filter of get_gaussian_kernel :207-225 repeated over the planes):
+ * y[pl] = x[pl] (*) kernel (K x K, K <= 15), zero padding `pad` on every side, output
+ * (H + 2 pad - K + 1) x (W + 2 pad - K + 1).  pad = 0 is the reference's valid convolution;
+ * pad = K - 1 with flip = 1 is its adjoint (the backward).                               */
+int hg_depthwise_conv(const float* x, const float* kernel, float* y, int32_t planes, int32_t H,
+                      int32_t W, int32_t K, int32_t pad, int32_t flip, hg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
