@@ -220,7 +220,11 @@ def gaussian_op(x, kernel=None):
     if kernel is None:
         kernel = get_gaussian_kernel(kernel_size=15, sigma=15, channels=3).to(x.device)
     w = kernel.weight
-    if x.is_cuda and w.shape[-1] <= 15 and bool((w == w[0:1]).all()):
+    uniform = getattr(kernel, '_hg_uniform', None)       # same filter on every plane? (checked once)
+    if uniform is None:
+        uniform = bool((w == w[0:1]).all()) and w.shape[-1] <= 15 and w.shape[1] == 1
+        kernel._hg_uniform = uniform
+    if x.is_cuda and uniform:
         return _DepthwiseConv.apply(x, w[0, 0])
     return kernel(x)
 

@@ -19,7 +19,7 @@ def load(name):
 
 def rel(a, b):
     a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a)).double()
-    b = torch.as_tensor(np.asarray(b)).double()
+    b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b)).double()
     return ((a - b).norm() / b.norm().clamp_min(1e-300)).item()
 
 

