@@ -2,7 +2,7 @@
 """bench.py -- HistoGAN training hot path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload train|hist]
+                    [--workload train|hist|rehisto]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Two workloads:
@@ -455,6 +455,167 @@ def run_train(args):
     dv.close()
 
 
+# ---------------------------------------------------------- rehisto workload --
+RH_BATCH = 16            # BASELINE config C5: ReHistoGAN step, 256^2, batch 16
+RH_ALPHA, RH_BETA, RH_GAMMA = 32.0, 1.5, 4.0
+
+
+class RecolorLoader:
+    def __init__(self, rank, dev=None):
+        g = torch.Generator().manual_seed(200 + rank)
+        self.x = torch.rand(RH_BATCH, 3, S, S, generator=g)
+        t = torch.rand(RH_BATCH, 3, H_BINS, H_BINS, generator=g)
+        self.t = t / t.sum(dim=(1, 2, 3), keepdim=True)
+        if torch.cuda.is_available():
+            self.x, self.t = self.x.pin_memory(), self.t.pin_memory()
+        if dev is not None:
+            self.x, self.t = self.x.to(dev), self.t.to(dev)
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        return {"images": self.x, "histograms": self.t}
+
+
+def rehisto_step_flops(B):
+    """algorithmic conv FLOPs of one recoloringTrainer.train step (no GP): encoder-decoder +
+    head forward x2 (the D-phase pass has no backward) + backward (2x), D fwd x3 + D bwd x2."""
+    c = CAPACITY
+    enc = [c * 2 ** i for i in range(7)]                      # 16 .. 1024
+    f = _conv_flops(B, 3, c, 3, S)                            # mapping
+    for i, (ci, co) in enumerate(zip(enc[:-1], enc[1:])):
+        h = S // 2 ** i
+        f += _conv_flops(B, ci, co, 1, h) + _conv_flops(B, ci, co, 3, h) + _conv_flops(B, co, co, 3, h)
+        f += _conv_flops(B, co, co, 3, h // 2)
+    dec = enc[::-1][:5]                                        # 1024 .. 64
+    for i, (ci, co) in enumerate(zip(dec[:-1], dec[1:])):
+        h = 4 * 2 ** i
+        f += _conv_flops(B, ci, ci, 3, h) + _conv_flops(B, 2 * ci, co, 3, h) + _conv_flops(B, ci, co, 1, h)
+        f += _conv_flops(B, co, co, 3, h) + _conv_flops(B, co, 3, 1, h)
+    f += _conv_flops(B, dec[-1], 8 * c, 1, 64)                 # decoder_mapping
+    f += _conv_flops(B, 4 * c, 4 * c, 3, 128) + _conv_flops(B, 2 * c, 2 * c, 3, 256)     # skip mod-convs
+    for ci, co, h in ((8 * c, 4 * c, 128), (4 * c, 2 * c, 256)):                         # head
+        f += _conv_flops(B, ci, co, 3, h) + _conv_flops(B, co, co, 3, h) + _conv_flops(B, co, 3, 1, h)
+    d = sum(_conv_flops(B, ci, co, k, h // s) for n, ci, co, k, s, h in conv_layer_table() if n == "D")
+    return f * (2 + 2) + d * (3 + 2 * 2), f, d
+
+
+def make_cpu_rehisto_step():
+    """closure: one ReHistoGAN step (D phase + G phase with all four loss terms; no GP, no
+    optimiser update) at B=1 on the CPU with the oracle's reference-style arithmetic."""
+    from histogan_b200 import rehistogan as rh
+    from histogan_b200.gan import Discriminator, HistVectorizer
+    from oracle import gan_oracle as go
+    from oracle import rehisto_oracle as ro
+
+    def sd_of(m, seed):
+        shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+        return {k: v.requires_grad_(True) for k, v in go.seeded_state_dict(shapes, seed).items()}
+
+    with torch.device("meta"):
+        mods = (rh.RecoloringEncoderDecoder(S, CAPACITY, skip_conn_to_GAN=True), HistVectorizer(H_BINS, 512, 8),
+                rh.RecoloringGAN(S, 512, CAPACITY), Discriminator(S, CAPACITY))
+    sd_ed, sd_h, sd_g, sd_d = [sd_of(m, i + 11) for i, m in enumerate(mods)]
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(min(avail, 32))
+    ld = RecolorLoader(0)
+    x, t = ld.x[:1].clone(), ld.t[:1].clone()
+    nz = torch.rand(1, S, S, 1)
+
+    def step():
+        with torch.no_grad():
+            fake = ro.g_phase(sd_ed, sd_h, sd_g, sd_d, x, t, nz, S, variance=False)["generated"]
+        d_loss = (F.relu(1 + go.discriminator(sd_d, x, S)) + F.relu(1 - go.discriminator(sd_d, fake, S))).mean()
+        torch.autograd.grad(d_loss, list(sd_d.values()))
+        out = ro.g_phase(sd_ed, sd_h, sd_g, sd_d, x, t, nz, S, RH_ALPHA, RH_BETA, RH_GAMMA)
+        params = [v for k, v in list(sd_ed.items()) + list(sd_h.items()) + list(sd_g.items())
+                  if "conv_out_rgb" not in k]
+        torch.autograd.grad(out["gen_loss"], params)
+    return step
+
+
+def run_rehisto(args):
+    from histogan_b200 import _lib
+    from histogan_b200.rehistogan import recoloringTrainer
+    dv = Dist(args.gpus)
+    lib = _lib.load()
+    _lib.check(lib.hg_device_check(dv.local_rank), "hg_device_check")
+    out_dir = os.path.join(ROOT, "gpurun_out", f"bench_rehisto_rank{dv.rank}")
+    torch.manual_seed(4321 + dv.rank)
+    tr = recoloringTrainer("bench", os.path.join(out_dir, "results"), os.path.join(out_dir, "models"),
+                           image_size=S, network_capacity=CAPACITY, batch_size=RH_BATCH,
+                           gradient_accumulate_every=1, skip_conn_to_GAN=True, initialize_gan=True,
+                           save_every=10 ** 9, fast_rng=True)
+    sampler = ClockSampler(dv.local_rank) if dv.rank == 0 else None
+
+    def timed(loader, steps, warmup):
+        tr.loader = loader
+        tr.steps = FIRST_STEP - warmup
+        for _ in range(warmup):
+            tr.train(RH_ALPHA, RH_BETA, RH_GAMMA)
+        dv.barrier()
+        n0 = lib.hg_launch_count()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(steps):
+            tr.train(RH_ALPHA, RH_BETA, RH_GAMMA)
+        e.record()
+        dv.barrier()
+        return dv.max_over_ranks(s.elapsed_time(e) * 1e-3), lib.hg_launch_count() - n0
+
+    timed(RecolorLoader(dv.rank, dv.dev), 2, 2)
+    t_dev, launches = timed(RecolorLoader(dv.rank, dv.dev), args.steps, args.warmup)
+    host = RecolorLoader(dv.rank)
+    t_e2e, _ = timed(host, args.steps, 1)
+    mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
+    losses = {"d": tr.d_loss, "g": tr.g_loss, "h": tr.h_loss, "r": tr.r_loss, "v": tr.var_loss,
+              "gp": tr.last_gp_loss}
+    clocks = sampler.stop() if sampler else {}
+    if dv.rank == 0:
+        _, bf16_peak, _, peak_kind = load_peaks()
+        n_imgs = RH_BATCH * dv.world * args.steps
+        step_flops, ed_f, d_f = rehisto_step_flops(RH_BATCH)
+        step_s = t_dev / args.steps
+        out = {
+            "metric": "training images/sec", "value": round(n_imgs / t_dev, 2), "unit": "images/s",
+            "n_gpus": dv.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(step_s * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "tf32 operands (round-to-nearest) / fp32 accumulate + fp32",
+            "data": "synthetic",
+            "config": {"workload": "ReHistoGAN recoloringTrainer.train step (D phase + G phase: adversarial "
+                                   "+ histogram + laplacian reconstruction + variance loss, GP every 4th "
+                                   "step, DiffGrad), 256x256, network_capacity=16, batch 16 per GPU, "
+                                   "skip_conn_to_GAN, hist 'sampling'",
+                       "global_batch": RH_BATCH * dv.world,
+                       "parallelism": f"dp{dv.world}" + (" + NCCL grad all-reduce" if dv.world > 1 else ""),
+                       "l2_flush": "not needed: the step's working set >> 126 MB L2",
+                       "timed_steps": f"trainer.steps {FIRST_STEP}..{FIRST_STEP + args.steps - 1}",
+                       "cuda_graphs": False, "peak_mem_gib": round(mem_gb, 2), "final_losses": losses},
+            "e2e": {"value": round(n_imgs / t_e2e, 2), "unit": "images/s",
+                    "h2d_bytes_per_step": 2 * (host.x.numel() + host.t.numel()) * 4,
+                    "d2h_bytes_per_step": 4 * 6},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "whole step: algorithmic conv FLOPs / step time "
+                                                      "(a lower bound of the conv kernels' own rate; the "
+                                                      "per-layer kernel figures are in the train workload)",
+                         "achieved": round(step_flops / step_s / 1e12, 1), "peak": bf16_peak,
+                         "unit": "TFLOP/s", "frac": round(step_flops / step_s / 1e12 / bf16_peak, 4),
+                         "traffic": None, "peak_kind": peak_kind,
+                         "step_algorithmic_conv_tflop": round(step_flops / 1e12, 3)},
+        }
+        if dv.world == 1:
+            step = make_cpu_rehisto_step()
+            t0 = time.perf_counter()
+            step()
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": round(1.0 / dt, 4), "unit": "images/s",
+                                   "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "1 image (of the 16-image batch) for 1 step, 256x256, capacity 16"}
+        emit(out)
+    dv.close()
+
+
 # ------------------------------------------------------- reference / CPU arm --
 
 def cpu_hist_step(x, t, insz=256):
@@ -564,6 +725,11 @@ def run_reference(args):
         step, sample, what = (lambda: cpu_hist_step(x, t)), 2, \
             "RGBuvHistBlock fwd + Hellinger loss + bwd, 256x256, h=64, insz=256"
         warm = 1
+    elif args.workload == "rehisto":
+        step, sample, what = make_cpu_rehisto_step(), 1, \
+            ("ReHistoGAN train step (D + G phase, four loss terms; no GP/optimiser), 256x256, capacity 16; "
+             "CPU restatement of the reference")
+        warm = 0
     else:
         step, sample, what = make_cpu_train_step(), 1, \
             ("HistoGAN train step (D + G phase with histogram loss; no GP/PL/optimiser), 256x256, "
@@ -578,7 +744,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     val = round(sample * steps / dt, 4)
     out = {
-        "impl": "reference", "metric": "training images/sec" if args.workload == "train" else "images/sec",
+        "impl": "reference", "metric": "images/sec" if args.workload == "hist" else "training images/sec",
         "value": val, "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": round(dt / steps * 1e3, 1), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 (f64 soft-binning, as the reference)", "data": "synthetic",
@@ -618,14 +784,14 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="train", choices=["train", "hist"])
+    ap.add_argument("--workload", default="train", choices=["train", "hist", "rehisto"])
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
         args.warmup = max(args.warmup, 3)
-        (run_train if args.workload == "train" else run_hist)(args)
+        {"train": run_train, "hist": run_hist, "rehisto": run_rehisto}[args.workload](args)
 
 
 if __name__ == "__main__":

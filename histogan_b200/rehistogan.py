@@ -700,6 +700,7 @@ class recoloringTrainer():
         # -------------------------------------------------------- generator --
         GAN.G_opt.zero_grad()
         g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        set_requires_grad(GAN.D, False)       # D's parameter gradients of this phase are never used
         for _ in range(accum):
             batch = next(self.loader)
             image_batch = batch['images'].cuda(non_blocking=True).detach()
@@ -718,6 +719,7 @@ class recoloringTrainer():
             total_rec_loss += rec.detach() / accum
             total_gen_loss += d_loss.detach() / accum
             total_hist_loss += histogram_loss.detach() / accum
+        set_requires_grad(GAN.D, True)
         # one host read for all the logged scalars
         g, r, h, v = torch.stack((total_gen_loss, total_rec_loss, total_hist_loss, total_var_loss)).tolist()
         self.g_loss, self.r_loss, self.h_loss = g, r, h

@@ -387,6 +387,9 @@ class Trainer:
         # -------------------------------------------------------- generator --
         GAN.G_opt.zero_grad()
         g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        # the reference lets this phase's backward fill D's parameter gradients too, only to
+        # zero them at the next D_opt.zero_grad() (:886): skip that dead wgrad work
+        set_requires_grad(GAN.D, False)
         for _ in range(accum):
             style, inoise = self._sample_latents(get_latents_fn, batch_size, num_layers,
                                                  latent_dim, image_size)
@@ -416,6 +419,7 @@ class Trainer:
             gen_loss.backward()
             total_gen_loss += loss.detach().item() / accum
             total_hist_loss += histogram_loss.detach().item() / accum
+        set_requires_grad(GAN.D, True)
         self.g_loss = float(total_gen_loss)
         self.h_loss = float(total_hist_loss)
         _allreduce_mean_grads(g_params)
@@ -465,9 +469,9 @@ class Trainer:
     def _phase_d(self, apply_gp):
         GAN, st = self.GAN, self._static
         B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
-        # gradients live in PERSISTENT buffers shared by every graph (see _static_grads): zero
-        # them in place (captured as fill kernels) instead of dropping them
-        GAN.D_opt.zero_grad(set_to_none=False)
+        # the backward allocates this graph's own gradient tensors (kept alive by _graphed and
+        # re-attached to the parameters after every replay): no zero-fill / accumulate kernels
+        GAN.D_opt.zero_grad(set_to_none=True)
         z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         inoise = torch.rand(B, S_, S_, 1, device='cuda')
@@ -489,38 +493,33 @@ class Trainer:
     def _phase_g(self, alpha):
         GAN, st = self.GAN, self._static
         B, S_ = self.batch_size, GAN.G.image_size
-        GAN.G_opt.zero_grad(set_to_none=False)
+        GAN.G_opt.zero_grad(set_to_none=True)
         z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
         inoise = torch.rand(B, S_, S_, 1, device='cuda')
         h_w = GAN.H(st['hists']).unsqueeze(1)
         fake = GAN.G(self._mixed_styles(z1, z2, st['mask']), torch.cat((h_w, h_w), dim=1), inoise)
-        fake_out, _ = GAN.D(fake)
-        hist_loss = hellinger_loss(st['hists'], self.histBlock(F.relu(fake)), alpha)
-        loss = fake_out.mean()
-        (loss + hist_loss).backward()
+        set_requires_grad(GAN.D, False)          # D's parameter gradients are dead work here
+        try:
+            fake_out, _ = GAN.D(fake)
+            hist_loss = hellinger_loss(st['hists'], self.histBlock(F.relu(fake)), alpha)
+            loss = fake_out.mean()
+            (loss + hist_loss).backward()
+        finally:
+            set_requires_grad(GAN.D, True)
         return loss.detach(), hist_loss.detach()
 
-    def _static_grads(self):
-        """Every captured graph must write the gradients where the optimiser reads them.  A
-        graph that allocates its own .grad tensors (zero_grad(set_to_none=True) inside the
-        capture) leaves `p.grad` pointing at the LAST captured graph's buffers, so replaying an
-        older graph would update memory nobody reads.  Hence: one persistent .grad per
-        parameter, allocated outside any graph pool, zeroed/accumulated in place."""
-        for opt in (self.GAN.D_opt, self.GAN.G_opt):
-            for grp in opt.param_groups:
-                for p in grp['params']:
-                    if p.requires_grad and (p.grad is None or getattr(p, '_hg_static_grad', None) is not p.grad):
-                        p.grad = torch.zeros_like(p)
-                        p._hg_static_grad = p.grad
+    def _graphed(self, key, fn, params):
+        """capture `fn` (one phase: zero_grad + forward + backward) once, then replay.
 
-    def _graphed(self, key, fn):
-        """capture `fn` (one phase: zero_grad + forward + backward) once, then replay"""
+        Each graph writes the gradients of `params` into tensors of its own memory pool; they
+        are kept alive here (stable addresses, refreshed by every replay) and attached to the
+        parameters after the replay, so the optimiser always reads what the graph just wrote
+        -- whichever variant (with / without gradient penalty) ran."""
         from . import ops, _lib
         lib = _lib.load()
         entry = self._graphs.get(key)
         if entry is None:
-            self._static_grads()
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):           # eager warm-up on a side stream
@@ -533,8 +532,11 @@ class Trainer:
                 outs = fn()
             self._graphs.setdefault('pool', g.pool())
             # library kernels recorded in this graph (each replay launches them again)
-            entry = self._graphs[key] = (g, outs, int(lib.hg_launch_count() - n0))
+            grads = [(p, p.grad) for p in params if p.grad is not None]
+            entry = self._graphs[key] = (g, outs, int(lib.hg_launch_count() - n0), grads)
         entry[0].replay()
+        for p, gr in entry[3]:
+            p.grad = gr
         self.graph_replayed_launches += entry[2]
         return entry[1]
 
@@ -560,12 +562,14 @@ class Trainer:
                 st['images'].copy_(batch['images'], non_blocking=True)
 
         stage(next(self.loader), True)
-        divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp))
-        _allreduce_mean_grads(list(GAN.D.parameters()))
+        d_params = list(GAN.D.parameters())
+        g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp), d_params)
+        _allreduce_mean_grads(d_params)
         GAN.D_opt.step()
         stage(next(self.loader), False)
-        g_loss, h_loss = self._graphed(('G', float(alpha)), lambda: self._phase_g(alpha))
-        _allreduce_mean_grads([p for grp in GAN.G_opt.param_groups for p in grp['params']])
+        g_loss, h_loss = self._graphed(('G', float(alpha)), lambda: self._phase_g(alpha), g_params)
+        _allreduce_mean_grads(g_params)
         GAN.G_opt.step()
         # host reads once, after everything has been queued
         self.q_loss = 0.0

@@ -186,16 +186,17 @@ def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
     def grads(params):
         return [p.grad.detach().clone() for p in params if p.grad is not None]
 
-    t._static_grads()
     for key, fn, params in ((('D', True), lambda: t._phase_d(True), list(t.GAN.D.parameters())),
                             (('D', False), lambda: t._phase_d(False), list(t.GAN.D.parameters())),
                             (('G', 2.0), lambda: t._phase_g(2.0), list(t.GAN.G.parameters()))):
         out_e = [o.clone() for o in fn() if o is not None]
         g_e = grads(params)
-        out_g = [o.clone() for o in t._graphed(key, fn) if o is not None]     # capture + replay
+        out_g = [o.clone() for o in t._graphed(key, fn, params) if o is not None]     # capture + replay
         g_g = grads(params)
-        out_g2 = [o.clone() for o in t._graphed(key, fn) if o is not None]    # second replay
-        assert all(p.grad is getattr(p, "_hg_static_grad") for p in params if p.grad is not None)
+        held = [p.grad for p in params]
+        out_g2 = [o.clone() for o in t._graphed(key, fn, params) if o is not None]    # second replay
+        # every replay re-attaches the graph's own gradient tensors to the parameters
+        assert all(p.grad is h for p, h in zip(params, held))
         for a, b in zip(out_e, out_g):
             assert abs(a.item() - b.item()) <= 1e-3 * abs(a.item()) + 1e-6, (key, a.item(), b.item())
         for a, b in zip(out_g, out_g2):
@@ -204,3 +205,11 @@ def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
         worst = max(((a - b).norm() / b.norm().clamp_min(1e-20)).item() for a, b in zip(g_g, g_e))
         print(key, "losses", [o.item() for o in out_e], "max grad rel diff graph vs eager", worst)
         assert worst < 2e-2, (key, worst)      # fp32 atomics reorder sums; TF32 rounding flips
+    # the variants own different buffers: replaying an older graph must hand ITS gradients over
+    d_params = list(t.GAN.D.parameters())
+    t._graphed(('D', True), None, d_params)
+    with_gp = [p.grad for p in d_params]
+    t._graphed(('D', False), None, d_params)
+    assert all(a is not b for a, b in zip(with_gp, [p.grad for p in d_params]))
+    t._graphed(('D', True), None, d_params)
+    assert all(a is b for a, b in zip(with_gp, [p.grad for p in d_params]))
