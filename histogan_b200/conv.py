@@ -33,17 +33,30 @@ def _up32(n):
     return (n + 31) // 32 * 32
 
 
+PACK_FROM_OHWI = 2
+
+
+def is_ohwi(w: torch.Tensor) -> bool:
+    """is the (Cout,Cin,kh,kw) tensor stored channels_last (memory [Cout][kh][kw][Cin])?"""
+    return w.dim() == 4 and w.is_contiguous(memory_format=torch.channels_last)
+
+
 def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
-    """hg_pack_conv_weight: OIHW -> [Np][KH][KW][Kp] K-major TF32, N/K zero-padded to
-    multiples of 32.  mode 1 = dgrad (N = Cin, K = Cout, taps flipped)."""
+    """hg_pack_conv_weight: (Cout,Cin,kh,kw) -> [Np][KH][KW][Kp] K-major TF32, N/K zero-padded
+    to multiples of 32.  mode 1 = dgrad (N = Cin, K = Cout, taps flipped).  The weight may be
+    stored channels_last (what this package's modules do) or plain contiguous."""
     lib = _lib.load()
     _lib.require_cuda(w_oihw, "pack_weight")
-    w = w_oihw.detach().contiguous().float()
+    w = w_oihw.detach().float()
+    ohwi = is_ohwi(w)
+    if not ohwi:
+        w = w.contiguous()
     co, ci, kh, kw = w.shape
     n, k = (ci, co) if mode else (co, ci)
     out = torch.empty((_up32(n), kh, kw, _up32(k)), dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
-        rc = lib.hg_pack_conv_weight(_lib.ptr(w), _lib.ptr(out), co, ci, kh, kw, int(mode),
+        rc = lib.hg_pack_conv_weight(_lib.ptr(w), _lib.ptr(out), co, ci, kh, kw,
+                                     int(mode) | (PACK_FROM_OHWI if ohwi else 0),
                                      _lib.current_stream_ptr(w.device))
     _lib.check(rc, "hg_pack_conv_weight")
     return out
@@ -93,8 +106,10 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: i
 
 def conv2d_wgrad_nhwc(dy: torch.Tensor, x: torch.Tensor, ksize: int, stride: int = 1,
                       pad: int = 1) -> torch.Tensor:
-    """dW in OIHW layout (Cout,Cin,k,k) from dy (B,Cout,OH,OW) and x (B,Cin,H,W), both
-    channels_last float32 (hg_conv2d_wgrad + hg_unpack_conv_wgrad)."""
+    """dW (Cout,Cin,k,k) from dy (B,Cout,OH,OW) and x (B,Cin,H,W), both channels_last float32
+    (hg_conv2d_wgrad).  The result is stored channels_last -- the kernel's own
+    [Cout][k][k][Cin] output viewed as (Cout,Cin,k,k) -- which is also how the modules store
+    their weights, so no layout conversion happens anywhere on the gradient path."""
     lib = _lib.load()
     _lib.require_cuda(x, "conv2d_wgrad_nhwc")
     dy, x = as_nhwc(dy), as_nhwc(x)
@@ -102,11 +117,11 @@ def conv2d_wgrad_nhwc(dy: torch.Tensor, x: torch.Tensor, ksize: int, stride: int
     _, Cout, OH, OW = dy.shape
     p = _lib.ConvParams(B, H, W, Cin, Cout, ksize, ksize, stride, pad, OH, OW)
     dwp = torch.empty((Cout, ksize, ksize, _up32(Cin)), dtype=torch.float32, device=x.device)
-    dw = torch.empty((Cout, Cin, ksize, ksize), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         st = _lib.current_stream_ptr(x.device)
         _lib.check(lib.hg_conv2d_wgrad(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dwp), C.byref(p), st),
                    "hg_conv2d_wgrad")
-        _lib.check(lib.hg_unpack_conv_wgrad(_lib.ptr(dwp), _lib.ptr(dw), Cout, Cin, ksize, ksize, 0, st),
-                   "hg_unpack_conv_wgrad")
+    dw = dwp.permute(0, 3, 1, 2)                     # (Cout, Cin_p, k, k), channels_last strides
+    if dw.shape[1] != Cin:                           # drop the K padding (small-channel layers only)
+        dw = dw[:, :Cin].contiguous(memory_format=torch.channels_last)
     return dw

@@ -291,8 +291,10 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
 //      completed by TMA's out-of-bounds zero fill, the weights by these explicit zeros).
 // mode 0 (forward):  N = Cout, K = Cin : out[co][kh][kw][ci] = w[co][ci][kh][kw]
 // mode 1 (dgrad):    N = Cin, K = Cout : out[ci][kh][kw][co] = w[co][ci][KH-1-kh][KW-1-kw]
+// ohwi: the parameter is stored channels_last (memory [Cout][KH][KW][Cin], what the modules of
+// this package use): mode 0 is then a rounding copy, mode 1 a per-tap transpose (kernel below).
 __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout,
-                                   int Cin, int KH, int KW, int mode, int Np, int Kp) {
+                                   int Cin, int KH, int KW, int mode, int Np, int Kp, int ohwi) {
   const long long total = (long long)Np * KH * KW * Kp;
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= total) return;
@@ -304,10 +306,35 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   const int n = (int)r;
   float v = 0.f;                                   // zero padding of both the N and the K extent
   if (n < N && k < K) {
-    if (mode == 0) v = w[(((long long)n * Cin + k) * KH + kh) * KW + kw];
-    else v = w[(((long long)k * Cin + n) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)];
+    if (ohwi) {
+      if (mode == 0) v = w[(((long long)n * KH + kh) * KW + kw) * Cin + k];
+      else v = w[(((long long)k * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * Cin + n];
+    } else {
+      if (mode == 0) v = w[(((long long)n * Cin + k) * KH + kh) * KW + kw];
+      else v = w[(((long long)k * Cin + n) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)];
+    }
   }
   out[e] = tf32_round(v);
+}
+
+// mode 1 from a channels_last parameter: out[ci][tap][co] = w[co][T-1-tap][ci], a 32x32
+// shared-memory transpose per tap so that both the read (along ci) and the write (along co)
+// are coalesced.  grid (Np/32, Kp/32, KH*KW), block (32, 8).
+__global__ void __launch_bounds__(256)
+pack_weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin,
+                             int T, int Kp) {
+  __shared__ float tile[32][33];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32, tap = blockIdx.z;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < Cout && ci < Cin)
+        ? w[((long long)co * T + (T - 1 - tap)) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;          // ci < Np, co < Kp by the grid
+    out[((long long)ci * T + tap) * Kp + co] = tf32_round(tile[threadIdx.x][r]);
+  }
 }
 
 // ------------------------------------------------------------ host side -----
@@ -361,15 +388,24 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
 
 using namespace hg;
 
-extern "C" int hg_pack_conv_weight(const float* w_oihw, float* w_packed, int32_t Cout, int32_t Cin,
-                                   int32_t KH, int32_t KW, int32_t mode, hg_stream_t stream_) {
-  if (!w_oihw || !w_packed) return set_error(HG_EINVAL, "null tensor pointer");
+extern "C" int hg_pack_conv_weight(const float* w, float* w_packed, int32_t Cout, int32_t Cin,
+                                   int32_t KH, int32_t KW, int32_t mode_, hg_stream_t stream_) {
+  if (!w || !w_packed) return set_error(HG_EINVAL, "null tensor pointer");
   if ((long long)Cout * Cin * KH * KW <= 0) return set_error(HG_EINVAL, "empty weight");
+  if (mode_ < 0 || mode_ > 3) return set_error(HG_EINVAL, "unknown pack mode %d", mode_);
+  const int mode = mode_ & 1, ohwi = (mode_ & HG_PACK_FROM_OHWI) ? 1 : 0;
   const int N = mode ? Cin : Cout, K = mode ? Cout : Cin;
   const int Np = (N + 31) / 32 * 32, Kp = (K + 31) / 32 * 32;
+  if (ohwi && mode == 1 && KH * KW <= 65535) {
+    dim3 grid(Np / 32, Kp / 32, KH * KW);
+    pack_weight_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream_>>>(w, w_packed, Cout, Cin,
+                                                                                 KH * KW, Kp);
+    HG_LAUNCH_OK("pack_weight_transpose_kernel");
+    return 0;
+  }
   const long long total = (long long)Np * KH * KW * Kp;
   pack_weight_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
-      w_oihw, w_packed, Cout, Cin, KH, KW, mode, Np, Kp);
+      w, w_packed, Cout, Cin, KH, KW, mode, Np, Kp, ohwi);
   HG_LAUNCH_OK("pack_weight_kernel");
   return 0;
 }

@@ -41,6 +41,15 @@ def _upsample2x():
     return nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False)
 
 
+def conv_weights_channels_last_(module):
+    """store every nn.Conv2d weight of `module` channels_last (see Conv2DMod); shapes, values
+    and state_dict keys are untouched, load_state_dict copies into this layout."""
+    for m in module.modules():
+        if isinstance(m, nn.Conv2d):
+            m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+    return module
+
+
 # --------------------------------------------------------------- operators ---
 
 class Conv2DMod(nn.Module):
@@ -56,8 +65,11 @@ class Conv2DMod(nn.Module):
         self.kernel = kernel
         self.stride = stride
         self.dilation = dilation
-        self.weight = nn.Parameter(torch.randn((out_chan, in_chan, kernel, kernel)))
-        nn.init.kaiming_normal_(self.weight, a=0, mode='fan_in', nonlinearity='leaky_relu')
+        w = torch.randn((out_chan, in_chan, kernel, kernel))
+        nn.init.kaiming_normal_(w, a=0, mode='fan_in', nonlinearity='leaky_relu')
+        # stored channels_last ([Cout][k][k][Cin] in memory; shape and state_dict unchanged): the
+        # layout of the packed tensor-core operand and of the weight-gradient kernel's output
+        self.weight = nn.Parameter(w.contiguous(memory_format=torch.channels_last))
 
     def _get_same_padding(self, size, kernel, dilation, stride):
         return ((size - 1) * (stride - 1) + dilation * (kernel - 1)) // 2
@@ -186,6 +198,7 @@ class DiscriminatorBlock(nn.Module):
             nn.Conv2d(input_channels, filters, 3, padding=1), leaky_relu(),
             nn.Conv2d(filters, filters, 3, padding=1), leaky_relu())
         self.downsample = nn.Conv2d(filters, filters, 3, padding=1, stride=2) if downsample else None
+        conv_weights_channels_last_(self)
 
     @staticmethod
     def _conv(m: nn.Conv2d, x):

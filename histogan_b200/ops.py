@@ -162,7 +162,9 @@ def _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=Fal
     k = wshape[2]
     dw = _conv.conv2d_wgrad_nhwc(round_tf32_nhwc(dy, dy_rounded), round_tf32_nhwc(x, x_rounded), k,
                                  stride, pad)
-    return dw[:wshape[0], :wshape[1]].contiguous()
+    if tuple(dw.shape[:2]) != tuple(wshape[:2]):
+        dw = dw[:wshape[0], :wshape[1]].contiguous(memory_format=torch.channels_last)
+    return dw
 
 
 class _Conv2d(torch.autograd.Function):

@@ -22,6 +22,14 @@ import torch
 from torch.optim import Optimizer
 
 
+def _dense(t):
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
+def _same_layout(a, b):
+    return a.shape == b.shape and (a.stride() == b.stride() or (a.is_contiguous() and b.is_contiguous()))
+
+
 class DiffGrad(Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         if lr <= 0.0:
@@ -58,8 +66,10 @@ class DiffGrad(Optimizer):
                 by_step.setdefault(st['step'], []).append(p)
             for step, ps in by_step.items():
                 step_size = group['lr'] * math.sqrt(1 - beta2 ** step) / (1 - beta1 ** step)
-                if all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()
-                       and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in ps):
+                # the fused kernel walks raw memory: parameter, gradient and state must share one
+                # dense layout (contiguous, or channels_last for the conv weights)
+                if all(p.is_cuda and p.dtype == torch.float32 and p.grad.dtype == torch.float32
+                       and _dense(p) and _same_layout(p, p.grad) for p in ps):
                     self._fused_step(ps, beta1, beta2, group['eps'], step_size, group['weight_decay'])
                     continue
                 grads = [p.grad for p in ps]

@@ -25,7 +25,8 @@ from torch import nn
 from torch.autograd.function import once_differentiable
 
 from . import _lib, gan, ops
-from .gan import Conv2DMod, Discriminator, GeneratorBlock, HistVectorizer, leaky_relu
+from .gan import (Conv2DMod, Discriminator, GeneratorBlock, HistVectorizer, conv_weights_channels_last_,
+                  leaky_relu)
 from .hist import RGBuvHistBlock, hellinger_loss
 from .optim import DiffGrad
 from .trainer import (NanException, _allreduce_mean_grads, cast_list, default, gradient_penalty,
@@ -293,6 +294,7 @@ class EncoderBlock(nn.Module):
             nn.Conv2d(input_channels, filters, 3, padding=1), nn.InstanceNorm2d(filters), leaky_relu(),
             nn.Conv2d(filters, filters, 3, padding=1), nn.InstanceNorm2d(filters), leaky_relu())
         self.downsample = nn.Conv2d(filters, filters, 3, padding=1, stride=2)
+        conv_weights_channels_last_(self)
 
     def forward(self, x):
         if _fused(x):
@@ -332,6 +334,7 @@ class DecoderBlock(nn.Module):
         else:
             self.to_latent = None
             self.conv_latent = None
+        conv_weights_channels_last_(self)
 
     def forward(self, x, prev_rgb, prev_latent, h=None):
         if _fused(x):
@@ -398,6 +401,7 @@ class RecoloringEncoderDecoder(nn.Module):
         for cin, cout in decoder_pairs:
             self.decoder_blocks.append(DecoderBlock(cin, cout, internal_hist=self.internal_hist,
                                                     latent_dim=latent_dim))
+        conv_weights_channels_last_(self)
 
     def forward(self, x, hists=None):
         if self.skip_conn_to_GAN and not self.internal_hist:

@@ -169,10 +169,16 @@ typedef struct hg_conv_epilogue {
 int hg_conv2d_fwd(const float* x, const float* w_packed, float* y, const hg_conv_params* p,
                   const hg_conv_epilogue* ep, hg_stream_t stream);
 
-/* OIHW parameter -> packed K-major TF32 weight, N and K extents zero-padded to multiples of 32.
+/* (Cout,Cin,KH,KW) parameter -> packed K-major TF32 weight, N and K extents zero-padded to
+ * multiples of 32.
  * mode 0: forward  [Cout_p][KH][KW][Cin_p];
- * mode 1: dgrad    [Cin_p][KH][KW][Cout_p], taps flipped (conv of dy with it = dx).  */
-int hg_pack_conv_weight(const float* w_oihw, float* w_packed, int32_t Cout, int32_t Cin,
+ * mode 1: dgrad    [Cin_p][KH][KW][Cout_p], taps flipped (conv of dy with it = dx);
+ * mode | HG_PACK_FROM_OHWI: `w` is stored channels_last, i.e. memory [Cout][KH][KW][Cin] (the
+ * storage this package's modules give their conv weights: forward packing is then a rounding
+ * copy and the weight gradient of hg_conv2d_wgrad already has the parameter's layout);
+ * otherwise `w` is plain contiguous OIHW (the reference's state_dict storage).          */
+#define HG_PACK_FROM_OHWI 2
+int hg_pack_conv_weight(const float* w, float* w_packed, int32_t Cout, int32_t Cin,
                         int32_t KH, int32_t KW, int32_t mode, hg_stream_t stream);
 
 /* Weight gradient: dw_packed [Cout][KH][KW][round_up(Cin,32)] (fully written) =
