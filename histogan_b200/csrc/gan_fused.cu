@@ -275,70 +275,158 @@ __device__ __forceinline__ float4 up2_sample(const float* __restrict__ xb, int H
   return r;
 }
 
-// one thread = one output pixel x 4 channels
+__device__ __forceinline__ float4 bilerp4(const float4& v00, const float4& v01, const float4& v10,
+                                          const float4& v11, float ly0, float ly1, float lx0, float lx1) {
+  const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 r = f4_axpy(ly0 * lx0, v00, z);
+  r = f4_axpy(ly0 * lx1, v01, r);
+  r = f4_axpy(ly1 * lx0, v10, r);
+  r = f4_axpy(ly1 * lx1, v11, r);
+  return r;
+}
+
+// 3x3 low-resolution neighbourhood of pixel (h, w) (rows / cols h-1, h, h+1 clamped): all the
+// taps of its 2x2 output quad.  Output row 2h+dy uses rows (dy, dy+1) of it with exactly the
+// weights up2_taps returns (at the borders the clamped duplicate row carries the zero weight).
+struct Nbhd { float4 v[3][3]; };
+
+__device__ __forceinline__ void load_nbhd(Nbhd& n, const float* __restrict__ xb, int H, int W, int C,
+                                          int c, int h, int w) {
+  const int ys[3] = {max(h - 1, 0), h, min(h + 1, H - 1)};
+  const int xs[3] = {max(w - 1, 0), w, min(w + 1, W - 1)};
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      n.v[r][q] = *reinterpret_cast<const float4*>(xb + ((long long)ys[r] * W + xs[q]) * C + c);
+}
+
+// one thread = one LOW-resolution pixel x 4 channels -> its 2x2 output quad (9 loads, 4 stores)
+// grid (ceil(H*W*C/4 / 256), B)
 __global__ void __launch_bounds__(256)
 upsample_modulate_round_kernel(const float* __restrict__ x, const float* __restrict__ mod,
-                               float* __restrict__ xm, int B, int H, int W, int C) {
-  const long long n4 = (long long)B * 4 * H * W * (C / 4);
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const int c = (int)(i % (C / 4)) * 4;
-  long long p = i / (C / 4);
-  const int ow = (int)(p % (2 * W)); p /= 2 * W;
-  const int oh = (int)(p % (2 * H));
-  const int b = (int)(p / (2 * H));
-  float4 v = up2_sample(x + (long long)b * H * W * C, H, W, C, c, oh, ow);
+                               float* __restrict__ xm, int H, int W, int C) {
+  const unsigned q4 = (unsigned)C / 4;
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  if (i >= (unsigned)H * W * q4) return;
+  const int c = (int)(i % q4) * 4;
+  const unsigned p = i / q4;
+  const int w = (int)(p % (unsigned)W), h = (int)(p / (unsigned)W);
+  const int b = blockIdx.y;
+  Nbhd n;
+  load_nbhd(n, x + (long long)b * H * W * C, H, W, C, c, h, w);
   const float4 m = *reinterpret_cast<const float4*>(mod + (long long)b * C + c);
-  v.x = tf32_round(v.x * m.x); v.y = tf32_round(v.y * m.y);
-  v.z = tf32_round(v.z * m.z); v.w = tf32_round(v.w * m.w);
-  *reinterpret_cast<float4*>(xm + (((long long)b * 2 * H + oh) * 2 * W + ow) * C + c) = v;
+  float ly[2][2], lx[2][2];
+#pragma unroll
+  for (int d = 0; d < 2; ++d) {
+    int i0, i1;
+    up2_taps(2 * h + d, H, i0, i1, ly[d][0], ly[d][1]);
+    up2_taps(2 * w + d, W, i0, i1, lx[d][0], lx[d][1]);
+  }
+  float* ob = xm + ((long long)b * 2 * H * 2 * W) * C + c;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      float4 o = bilerp4(n.v[dy][dx], n.v[dy][dx + 1], n.v[dy + 1][dx], n.v[dy + 1][dx + 1],
+                         ly[dy][0], ly[dy][1], lx[dx][0], lx[dx][1]);
+      o.x = tf32_round(o.x * m.x); o.y = tf32_round(o.y * m.y);
+      o.z = tf32_round(o.z * m.z); o.w = tf32_round(o.w * m.w);
+      *reinterpret_cast<float4*>(ob + ((long long)(2 * h + dy) * 2 * W + (2 * w + dx)) * C) = o;
+    }
 }
 
 // adjoint: dx[b,h,w,c] = sum over the <=4x4 output pixels that tap (h,w) of weight * dxm * mod,
-//          gmod[b,c]  += sum over this thread's 2x2 output pixels of dxm * bilerp2x(x)
-// grid (C/32, low-res pixel chunks, B); same CTA skeleton as the other kernels
-__global__ void __launch_bounds__(kFusedThreads)
+//          gmod[b,c]  += sum_{h,w} (dx / mod)[b,h,w,c] * x[b,h,w,c]
+// A CTA owns a 4x8 tile of low-resolution pixels x 32 channels and stages the (2*4+2) x (2*8+2)
+// high-resolution gradients it needs in shared memory once.  grid (C/32, tiles, B).
+constexpr int kUpTH = 4, kUpTW = 8;
+constexpr int kUpRows = 2 * kUpTH + 2, kUpCols = 2 * kUpTW + 2;
+
+// weight with which output index o (of 2n) taps input index i
+__device__ __forceinline__ float up2_weight(int o, int n, int i) {
+  if (o < 0 || o >= 2 * n) return 0.f;
+  int i0, i1; float l0, l1;
+  up2_taps(o, n, i0, i1, l0, l1);
+  return (i0 == i ? l0 : 0.f) + (i1 == i ? l1 : 0.f);
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;                       // src-size 0 -> the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 4)
 upsample_modulate_bwd_kernel(const float* __restrict__ dxm, const float* __restrict__ x,
                              const float* __restrict__ mod, float* __restrict__ dx,
-                             float* __restrict__ gmod, int H, int W, int C, int pix_per_cta) {
-  __shared__ float4 red[kPixLanes * 8];
+                             float* __restrict__ gmod, int H, int W, int C, int tiles_w,
+                             int n_tiles, int tiles_per_cta) {
+  __shared__ float4 tiles[2][kUpRows * kUpCols * 8];      // 2 x 22.5 KB (static limit: 48 KB)
+  float4* red = tiles[0];                                 // reused for the final reduction
   const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
   const int c = blockIdx.x * 32 + cl * 4;
   const int b = blockIdx.z;
-  const int HW = H * W;
-  const int p0 = blockIdx.y * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
   const bool cvalid = c < C;
+  const int HW = H * W;
+  const float* gb = dxm + (long long)b * 4 * HW * C;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 acc[1];
-  acc[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (cvalid) {
-    const float4 m = *reinterpret_cast<const float4*>(mod + (long long)b * C + c);
-    const float* xb = x + (long long)b * HW * C;
-    const float* gb = dxm + (long long)b * 4 * HW * C;
-    for (int p = p0 + pl; p < p1; p += kPixLanes) {
-      const int h = p / W, w = p - h * W;
-      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int oh = max(0, 2 * h - 1); oh <= min(2 * H - 1, 2 * h + 2); ++oh) {
-        int y0, y1; float ly0, ly1;
-        up2_taps(oh, H, y0, y1, ly0, ly1);
-        const float wy = (y0 == h ? ly0 : 0.f) + (y1 == h ? ly1 : 0.f);
-        if (wy == 0.f) continue;
-        for (int ow = max(0, 2 * w - 1); ow <= min(2 * W - 1, 2 * w + 2); ++ow) {
-          int x0, x1; float lx0, lx1;
-          up2_taps(ow, W, x0, x1, lx0, lx1);
-          const float wx = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
-          if (wx == 0.f) continue;
-          const float4 gv = *reinterpret_cast<const float4*>(gb + ((long long)oh * 2 * W + ow) * C + c);
-          g = f4_axpy(wy * wx, gv, g);
-          if ((oh >> 1) == h && (ow >> 1) == w) {          // this thread owns output (oh, ow)
-            const float4 xu = up2_sample(xb, H, W, C, c, oh, ow);
-            acc[0].x = fmaf(gv.x, xu.x, acc[0].x); acc[0].y = fmaf(gv.y, xu.y, acc[0].y);
-            acc[0].z = fmaf(gv.z, xu.z, acc[0].z); acc[0].w = fmaf(gv.w, xu.w, acc[0].w);
-          }
-        }
-      }
-      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
-      *reinterpret_cast<float4*>(dx + ((long long)b * HW + p) * C + c) = g;
+  acc[0] = zero;
+  const float4 m = cvalid ? *reinterpret_cast<const float4*>(mod + (long long)b * C + c) : zero;
+  const float* xb = x + (long long)b * HW * C;
+
+  // stage the (2*TH+2) x (2*TW+2) high-resolution gradients of tile t (zero outside the image)
+  auto prefetch = [&](int t, int buf) {
+    const int h0 = (t / tiles_w) * kUpTH, w0 = (t % tiles_w) * kUpTW;
+    for (int e = pl; e < kUpRows * kUpCols; e += kPixLanes) {
+      const int r = e / kUpCols, q = e - r * kUpCols;
+      const int oh = 2 * h0 - 1 + r, ow = 2 * w0 - 1 + q;
+      const bool ok = cvalid && oh >= 0 && oh < 2 * H && ow >= 0 && ow < 2 * W;
+      cp_async16(&tiles[buf][e * 8 + cl], ok ? gb + ((long long)oh * 2 * W + ow) * C + c : gb, ok);
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  // a CTA walks several tiles (double-buffered) and issues ONE atomic per channel at the end
+  const int t_begin = blockIdx.y * tiles_per_cta;
+  const int t_end = min(n_tiles, t_begin + tiles_per_cta);
+  if (t_begin < t_end) prefetch(t_begin, 0);
+  for (int t = t_begin; t < t_end; ++t) {
+    const int buf = (t - t_begin) & 1;
+    const int h0 = (t / tiles_w) * kUpTH, w0 = (t % tiles_w) * kUpTW;
+    const int ty = pl / kUpTW, tx = pl - ty * kUpTW;
+    const int h = h0 + ty, w = w0 + tx;
+    float4 xc = zero;                       // issued before the wait so its latency overlaps
+    if (cvalid && h < H && w < W)
+      xc = *reinterpret_cast<const float4*>(xb + ((long long)h * W + w) * C + c);
+    if (t + 1 < t_end) {
+      prefetch(t + 1, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (cvalid && h < H && w < W) {
+      float wy[4], wx[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        wy[r] = up2_weight(2 * h - 1 + r, H, h);
+        wx[r] = up2_weight(2 * w - 1 + r, W, w);
+      }
+      const float4* t0 = tiles[buf] + ((2 * ty) * kUpCols + 2 * tx) * 8 + cl;
+      float4 g = zero;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g = f4_axpy(wy[r] * wx[q], t0[(r * kUpCols + q) * 8], g);
+      // d/d mod = <dxm, up(x)> = <up^T(dxm), x>: the un-modulated dx times x, no second gather
+      acc[0].x = fmaf(g.x, xc.x, acc[0].x); acc[0].y = fmaf(g.y, xc.y, acc[0].y);
+      acc[0].z = fmaf(g.z, xc.z, acc[0].z); acc[0].w = fmaf(g.w, xc.w, acc[0].w);
+      g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
+      *reinterpret_cast<float4*>(dx + ((long long)b * HW + (long long)h * W + w) * C + c) = g;
+    }
+    __syncthreads();          // everyone is done with tiles[buf] before it is refilled
   }
   reduce_pixel_lanes<1>(acc, red, cl, pl);
   if (pl == 0 && cvalid) atomic_add4(gmod + (long long)b * C + c, acc[0]);
@@ -439,10 +527,12 @@ extern "C" int hg_upsample_modulate_round(const float* x, const float* mod, floa
                                           int32_t H, int32_t W, int32_t C, hg_stream_t stream_) {
   if (!x || !mod || !xm) return set_error(HG_EINVAL, "null tensor pointer");
   if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
-  const long long n4 = (long long)B * 4 * H * W * (C / 4);
-  if (n4 <= 0) return 0;
-  upsample_modulate_round_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(
-      x, mod, xm, B, H, W, C);
+  const long long n4 = (long long)H * W * (C / 4);
+  if (n4 <= 0 || B <= 0) return 0;
+  if (n4 >= (1LL << 31) || B > 65535)
+    return set_error(HG_ENOSUP, "upsample_modulate_round: tensor too large (%d x %d x %d, B=%d)", H, W, C, B);
+  upsample_modulate_round_kernel<<<dim3((unsigned)((n4 + 255) / 256), B), 256, 0, (cudaStream_t)stream_>>>(
+      x, mod, xm, H, W, C);
   HG_LAUNCH_OK("upsample_modulate_round_kernel");
   return 0;
 }
@@ -456,9 +546,15 @@ extern "C" int hg_upsample_modulate_bwd(const float* dxm, const float* x, const 
   if (B <= 0) return 0;
   HG_CUDA_OK(cudaMemsetAsync(gmod, 0, sizeof(float) * (size_t)B * C, stream));
   const int cblocks = (C + 31) / 32;
-  const int per = pick_pix_per_cta(H * W, B, cblocks);
-  dim3 grid(cblocks, (H * W + per - 1) / per, B);
-  upsample_modulate_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(dxm, x, mod, dx, gmod, H, W, C, per);
+  const int tiles_w = (W + kUpTW - 1) / kUpTW, tiles_h = (H + kUpTH - 1) / kUpTH;
+  if (B > 65535) return set_error(HG_ENOSUP, "upsample_modulate_bwd: batch too large (%d)", B);
+  const int n_tiles = tiles_w * tiles_h;
+  long long per = ((long long)n_tiles * cblocks * B + 148 * 16 - 1) / (148 * 16);      // ~16 CTAs per SM in all
+  if (per < 1) per = 1;
+  if (per > n_tiles) per = n_tiles;
+  dim3 grid(cblocks, (unsigned)((n_tiles + per - 1) / per), B);
+  upsample_modulate_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(dxm, x, mod, dx, gmod, H, W, C,
+                                                                   tiles_w, n_tiles, (int)per);
   HG_LAUNCH_OK("upsample_modulate_bwd_kernel");
   return 0;
 }
