@@ -14,7 +14,7 @@ import torch
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libhistogan_b200.so"
 
-HG_ABI_VERSION = 2
+HG_ABI_VERSION = 3
 
 RESIZE_IDS = {"interpolation": 0, "sampling": 1}
 METHOD_IDS = {"thresholding": 0, "RBF": 1, "inverse-quadratic": 2}
@@ -42,7 +42,9 @@ class ConvEpilogue(C.Structure):
     """struct hg_conv_epilogue."""
     _fields_ = [("scale", C.c_void_p), ("bias", C.c_void_p), ("noise", C.c_void_p),
                 ("noise_w", C.c_void_p), ("noise_b", C.c_void_p), ("residual", C.c_void_p),
-                ("noise_size", C.c_int32), ("flags", C.c_int32), ("lrelu_slope", C.c_float)]
+                ("noise_size", C.c_int32), ("flags", C.c_int32), ("lrelu_slope", C.c_float),
+                ("reserved_", C.c_int32), ("out_img_stride", C.c_int64),
+                ("out_row_stride", C.c_int64), ("out_pix_stride", C.c_int64)]
 
 
 _SIGNATURES = {

@@ -65,10 +65,13 @@ def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
 def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: int = 1, *,
                 cout=None, scale=None, bias=None, noise=None, noise_w=None, noise_b=None,
                 residual=None, lrelu: bool = False, slope: float = 0.2,
-                round_tf32: bool = False) -> torch.Tensor:
+                round_tf32: bool = False, out_hw=None, into=None) -> torch.Tensor:
     """y = epilogue(conv(x, w)); x (B,Cin,H,W) channels_last (Cin % 4 == 0), w_packed
     [Cout_p][KH][KW][Cin_p] from pack_weight; `cout` = true number of output channels
-    (% 4 == 0, default Cout_p).  Returns (B,cout,OH,OW) channels_last."""
+    (% 4 == 0, default Cout_p).  Returns (B,cout,OH,OW) channels_last.
+    out_hw: produce this output extent instead of the natural one (the excess windows read
+    zeros); into=(t, oy, ox, step): write output pixel (oh, ow) to t[:, :, oy + step*oh,
+    ox + step*ow] of an existing channels_last tensor t (B,cout,*,*) and return t."""
     lib = _lib.load()
     _lib.require_cuda(x, "conv2d_nhwc")
     assert x.dtype == torch.float32 and x.dim() == 4
@@ -81,8 +84,20 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: i
     assert Cout <= Cout_p and _up32(Cout) == Cout_p, (Cout, Cout_p)
     OH = (H + 2 * pad - KH) // stride + 1
     OW = (W + 2 * pad - KW) // stride + 1
-    y = torch.empty((B, Cout, OH, OW), dtype=torch.float32, device=x.device,
-                    memory_format=torch.channels_last)
+    if out_hw is not None:
+        OH, OW = out_hw
+    strides, y_ptr = (0, 0, 0), None
+    if into is not None:
+        y, oy, ox, step = into
+        assert residual is None and y.is_contiguous(memory_format=torch.channels_last)
+        assert y.shape[0] == B and y.shape[1] == Cout and y.dtype == torch.float32
+        TH_, TW_ = y.shape[2], y.shape[3]
+        assert oy + step * (OH - 1) < TH_ and ox + step * (OW - 1) < TW_
+        strides = (TH_ * TW_ * Cout, step * TW_ * Cout, step * Cout)
+        y_ptr = C.c_void_p(y.data_ptr() + 4 * (oy * TW_ + ox) * Cout)
+    else:
+        y = torch.empty((B, Cout, OH, OW), dtype=torch.float32, device=x.device,
+                        memory_format=torch.channels_last)
     if residual is not None:
         residual = as_nhwc(residual)
         assert residual.shape == y.shape
@@ -96,9 +111,9 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: i
         keep[3].data_ptr() if keep[3] is not None else None,
         keep[4].data_ptr() if keep[4] is not None else None,
         residual.data_ptr() if residual is not None else None,
-        int(noise.shape[1]) if noise is not None else 0, flags, float(slope))
+        int(noise.shape[1]) if noise is not None else 0, flags, float(slope), 0, *strides)
     with torch.cuda.device(x.device):
-        rc = lib.hg_conv2d_fwd(_lib.ptr(x), _lib.ptr(w_packed), _lib.ptr(y), C.byref(p),
+        rc = lib.hg_conv2d_fwd(_lib.ptr(x), _lib.ptr(w_packed), y_ptr or _lib.ptr(y), C.byref(p),
                                C.byref(ep), _lib.current_stream_ptr(x.device))
     _lib.check(rc, "hg_conv2d_fwd")
     return y

@@ -51,6 +51,7 @@ struct ConvArgs {
   const float* noise_b;           // [Cout]  to_noise bias
   const float* residual;          // NHWC like y, added after the activation (or null)
   int noise_size;
+  long long y_img, y_row, y_pix;  // output strides in floats (dense NHWC unless the caller says otherwise)
 };
 
 // HALO variant (3x3, stride 1, 16x8-pixel tiles inside one image): one A box with a one-row
@@ -236,7 +237,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         if (valid && n0 + c0 < a.Cout) {
           const int n = n0 + c0;
           const int ncols = min(32, a.Cout - n);       // Cout % 4 == 0
-          float* yo = a.y + pix * a.Cout + n;
+          float* yo = a.y + (long long)b * a.y_img + (long long)oh * a.y_row + (long long)ow * a.y_pix + n;
           const float* ro = a.residual ? a.residual + pix * a.Cout + n : nullptr;
           const float* sc = a.scale ? a.scale + (long long)b * a.Cout + n : nullptr;
 #define HG_EPILOGUE_4(J)                                                                      \
@@ -420,11 +421,12 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     return set_error(HG_ENOSUP, "conv: Cin=%d and Cout=%d must be multiples of 4 (16-byte TMA rows)",
                      p->Cin, p->Cout);
   if (p->stride < 1 || p->stride > 2) return set_error(HG_ENOSUP, "conv: stride must be 1 or 2");
-  const int OH = (p->H + 2 * p->pad - p->KH) / p->stride + 1;
-  const int OW = (p->W + 2 * p->pad - p->KW) / p->stride + 1;
-  if (OH != p->OH || OW != p->OW)
+  const int OHn = (p->H + 2 * p->pad - p->KH) / p->stride + 1;
+  const int OWn = (p->W + 2 * p->pad - p->KW) / p->stride + 1;
+  const int OH = p->OH, OW = p->OW;          // >= the natural extent: the excess reads zeros
+  if (OH < OHn || OW < OWn || OH < 1 || OW < 1 || OH > p->H + 2 * p->pad || OW > p->W + 2 * p->pad)
     return set_error(HG_EINVAL, "conv: OH/OW (%d,%d) inconsistent with geometry (%d,%d)", p->OH,
-                     p->OW, OH, OW);
+                     p->OW, OHn, OWn);
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) |
        reinterpret_cast<uintptr_t>(y)) & 15)
     return set_error(HG_EINVAL, "conv: pointers must be 16-byte aligned");
@@ -455,6 +457,13 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
   a.noise_b = ep ? ep->noise_b : nullptr;
   a.noise_size = ep ? ep->noise_size : 0;
   a.residual = ep ? ep->residual : nullptr;
+  a.y_img = (long long)OH * OW * p->Cout; a.y_row = (long long)OW * p->Cout; a.y_pix = p->Cout;
+  if (ep && (ep->out_img_stride || ep->out_row_stride || ep->out_pix_stride)) {
+    if (a.residual) return set_error(HG_ENOSUP, "conv: strided output together with a residual");
+    if (ep->out_pix_stride < p->Cout || (ep->out_pix_stride | ep->out_row_stride | ep->out_img_stride) & 3)
+      return set_error(HG_EINVAL, "conv: output strides must be multiples of 4 floats, pixel stride >= Cout");
+    a.y_img = ep->out_img_stride; a.y_row = ep->out_row_stride; a.y_pix = ep->out_pix_stride;
+  }
   if (a.noise && (!a.noise_w || !a.noise_b || a.noise_size < OH || a.noise_size < OW))
     return set_error(HG_EINVAL, "conv: noise needs noise_w/noise_b and noise_size >= OH,OW");
 

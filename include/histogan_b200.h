@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 2
+#define HG_ABI_VERSION 3
 
 /* error codes (negative; positive values are cudaError_t) */
 #define HG_EINVAL   (-1)   /* bad argument (message in hg_last_error)          */
@@ -143,7 +143,9 @@ int hg_hellinger_bwd(const float* target, const float* hist, int64_t numel, int3
 typedef struct hg_conv_params {
   int32_t B, H, W, Cin;
   int32_t Cout, KH, KW, stride, pad;
-  int32_t OH, OW;                       /* (H + 2 pad - KH)/stride + 1, checked   */
+  int32_t OH, OW;                       /* output extent: normally (H + 2 pad - KH)/stride + 1;
+                                         * a larger value (<= H + 2 pad) is allowed -- windows
+                                         * that reach past the input read zeros                */
 } hg_conv_params;
 
 /* Fused epilogue, applied in this order to the accumulator of output (b,oh,ow,co):
@@ -153,7 +155,11 @@ typedef struct hg_conv_params {
  *                                                      spatial transpose (:465-467)
  *   v  = LeakyReLU(v)                                  if HG_CONV_LRELU (:471,476)
  *   v += residual[b][oh][ow][co]                       DiscriminatorBlock (:524)
- * Any pointer may be NULL to skip its step.                                      */
+ * Any pointer may be NULL to skip its step.
+ * out_*_stride (in floats, all three 0 = dense NHWC): where output pixel (b,oh,ow) goes,
+ *   y + b*out_img_stride + oh*out_row_stride + ow*out_pix_stride -- lets a convolution
+ *   write one parity class of a twice-as-large tensor (the stride-2 input gradient is four
+ *   such convolutions over dy, ops.py); `residual` is not supported together with it.    */
 typedef struct hg_conv_epilogue {
   const float* scale;
   const float* bias;
@@ -164,6 +170,8 @@ typedef struct hg_conv_epilogue {
   int32_t noise_size;
   int32_t flags;
   float   lrelu_slope;
+  int32_t reserved_;
+  int64_t out_img_stride, out_row_stride, out_pix_stride;
 } hg_conv_epilogue;
 
 int hg_conv2d_fwd(const float* x, const float* w_packed, float* y, const hg_conv_params* p,
