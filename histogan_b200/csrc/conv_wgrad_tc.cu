@@ -195,6 +195,151 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ---------------------------------------------------------------------------
+// Column-halo variant for 3x3 / stride 1 / pad 1 layers with FEW output channels (the 256^2 ..
+// 64^2 layers, where the pixel reduction is longest and M = Cout would leave the 128-row MMA
+// mostly empty).  Roles are swapped:  dW^T[(kh,ci)][co] = sum_pix x[pix + tap][ci] * dy[pix][co]
+//   A (M side) = the x tile, fetched ONCE per filter column kw as a {32 ci, 16, 4+2, 1} box with a
+//       one-row halo above and below (96 pixel rows x 128 B = 12 KB).  Tap kh of that column is
+//       the same box 16 rows = 2048 B further on, so the three vertical taps are three "32-channel
+//       chunks" of one MN-major operand with LBO = 2048: one M = 128 MMA (chunk 3 reads past the
+//       box; its accumulator rows are never stored) covers kh = 0..2.
+//   B (N side) = the dy tile {32 co, 16, 4, 1} x NC chunks, fetched once.
+// Per 64 pixels: 3 x 8 MMAs instead of 9 x 8, 3 x-boxes instead of 9, one dy fetch instead of 9.
+// CTA = (co tile of NC*32, ci tile of 32, pixel split); accumulators: 3 x (NC*32) TMEM columns.
+constexpr int kColBoxBytes = (4 + 2) * 16 * 128;          // 12 KB
+constexpr int kColSlack = 4096;                            // chunk 3 of the last box reads past it
+
+template <int NC, int STAGES>
+struct WgradColSmem {
+  static constexpr int kStageBytes = NC * kWgChunkBytes + 3 * kColBoxBytes;
+  static constexpr int kTotal = STAGES * kStageBytes + kColSlack + 1024 + 256;
+};
+
+template <int NC, int STAGES>
+__global__ void __launch_bounds__(kWgThreads)
+conv_wgrad_col_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_constant__ CUtensorMap tmx,
+                      const WgradArgs a) {
+  using SM = WgradColSmem<NC, STAGES>;
+  constexpr int N = NC * 32;
+  constexpr uint32_t kTmemCols = NC == 1 ? 128 : (NC == 2 ? 256 : 512);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * SM::kStageBytes + kColSlack);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmdy);
+    ptx::prefetch_tmap(&tmx);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      ptx::mbar_init(tmem_full_bar, 1);
+      ptx::fence_barrier_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int ci_t = blockIdx.x % a.ci_tiles, co_t = blockIdx.x / a.ci_tiles;
+  const int co0 = co_t * N, ci0 = ci_t * 32;
+  const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
+  const int kb0 = (int)((long long)blockIdx.y * kb_total / a.splits);
+  const int kb1 = (int)((long long)(blockIdx.y + 1) * kb_total / a.splits);
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int n_chunks = min(NC, (a.Cout - co0 + 31) / 32);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int tw_i = kb % a.tiles_w;
+        const int th_i = (kb / a.tiles_w) % a.tiles_h;
+        const int b0 = kb / (a.tiles_w * a.tiles_h);
+        const int ow0 = tw_i * 16, oh0 = th_i * 4;
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sDy = base + stage * SM::kStageBytes;
+        uint8_t* sX = sDy + NC * kWgChunkBytes;
+        ptx::mbar_expect_tx(&full_bar[stage], n_chunks * kWgChunkBytes + 3 * kColBoxBytes);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (c < n_chunks)
+            ptx::tma_load_4d(sDy + c * kWgChunkBytes, &tmdy, &full_bar[stage], co0 + 32 * c, ow0, oh0, b0);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          ptx::tma_load_4d(sX + kw * kColBoxBytes, &tmx, &full_bar[stage], ci0, ow0 + kw - 1, oh0 - 1, b0);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc(2 /*tf32*/, 128, N, 1 /*A MN-major*/, 1 /*B MN-major*/);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t sDy = ptx::smem_u32(base + stage * SM::kStageBytes);
+        const uint32_t sX = sDy + NC * kWgChunkBytes;
+        const uint64_t b_desc = ptx::make_smem_desc(sDy, kWgChunkBytes, 512, ptx::kLayoutSW128Base32);
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          // M chunks = vertical taps: 16 pixel rows (2048 B) apart inside the halo box
+          const uint64_t a_desc = ptx::make_smem_desc(sX + kw * kColBoxBytes, 2048, 512,
+                                                      ptx::kLayoutSW128Base32);
+#pragma unroll
+          for (int k = 0; k < kWgPix / 8; ++k)
+            ptx::mma_tf32_ss(tmem_base + (uint32_t)(kw * N), a_desc + (uint64_t)(k * 64),
+                             b_desc + (uint64_t)(k * 64), idesc, (uint32_t)((kb > kb0) | (k != 0)));
+        }
+        ptx::tc_commit(&empty_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+      }
+      ptx::tc_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;                 // TMEM lane quadrant == vertical tap kh (3 = unused rows)
+    const int ci = ci0 + lane;
+    if (kb1 > kb0) {
+      ptx::mbar_wait(tmem_full_bar, 0);
+      ptx::tc_fence_after();
+      if (q < 3) {
+#pragma unroll 1
+        for (int kw = 0; kw < 3; ++kw) {
+#pragma unroll 1
+          for (int cc = 0; cc < N; cc += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * N + cc), v);
+            ptx::tmem_ld_wait();
+            float* o = a.dw + ((long long)(co0 + cc) * 9 + q * 3 + kw) * a.Kp + ci;
+            const int ncols = min(32, a.Cout - (co0 + cc));
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols) atomicAdd(o + (long long)j * 9 * a.Kp, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
 // packed [Cout][KH][KW][Cin] gradient -> OIHW parameter gradient (optionally +=)
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Cout,
                                     int Cin, int KH, int KW, int accumulate) {
@@ -253,6 +398,22 @@ static int launch_wgrad(const CUtensorMap& tmdy, const CUtensorMap& tmx, const W
   return 0;
 }
 
+template <int NC, int STAGES>
+static int launch_wgrad_col(const CUtensorMap& tmdy, const CUtensorMap& tmx, const WgradArgs& a,
+                            int co_tiles, cudaStream_t stream) {
+  using SM = WgradColSmem<NC, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_col_kernel<NC, STAGES>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_set = true;
+  }
+  dim3 grid(co_tiles * a.ci_tiles, a.splits);
+  conv_wgrad_col_kernel<NC, STAGES><<<grid, kWgThreads, SM::kTotal, stream>>>(tmdy, tmx, a);
+  HG_LAUNCH_OK("conv_wgrad_col_kernel");
+  return 0;
+}
+
 }  // namespace hg
 
 using namespace hg;
@@ -274,6 +435,29 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
   WgradArgs a{};
   a.B = p->B; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout; a.KH = p->KH; a.KW = p->KW;
   a.stride = p->stride; a.pad = p->pad; a.OH = OH; a.OW = OW;
+  const int Np = (p->Cout + 31) / 32 * 32;
+  if (p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1 && OW >= 16 && OH >= 4 && Np <= 64 &&
+      (long long)p->B * OH * OW >= 64 * 1024) {
+    // few output channels, many pixels: column-halo variant (see conv_wgrad_col_kernel)
+    a.PW = 16; a.PH = 4; a.PB = 1;
+    a.tiles_w = (OW + 15) / 16; a.tiles_h = (OH + 3) / 4; a.tiles_b = p->B;
+    a.ci_tiles = Kp / 32; a.Kp = Kp;
+    const int NC = Np / 32;                              // 1 or 2
+    const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
+    const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+    int splits = (2 * sms + a.ci_tiles - 1) / a.ci_tiles;
+    if (splits > kb_total / 2) splits = kb_total / 2;
+    if (splits < 1) splits = 1;
+    a.splits = splits; a.atomic = 1; a.dw = dw_packed;
+    HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream));
+    alignas(64) CUtensorMap tmdy, tmx;
+    int rc = encode_nhwc_map(&tmdy, dy, p->Cout, OW, OH, p->B, 16, 4, 1, 1);
+    if (rc) return rc;
+    rc = encode_nhwc_map(&tmx, x, p->Cin, p->W, p->H, p->B, 16, 6, 1, 1);
+    if (rc) return rc;
+    if (NC == 1) return launch_wgrad_col<1, 4>(tmdy, tmx, a, 1, stream);
+    return launch_wgrad_col<2, 4>(tmdy, tmx, a, 1, stream);
+  }
   int PW = 1; while (PW < 16 && PW < OW) PW <<= 1;
   int PH = 1; while (PW * PH < kWgPix && PH < OH) PH <<= 1;
   const int PB = kWgPix / (PW * PH);

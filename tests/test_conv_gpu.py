@@ -100,6 +100,10 @@ WG_CASES = [
     (2, 16, 64, 64, 16, 3, 1),     # all-taps variant (<= 32 input channels, long pixel reduction)
     (4, 32, 64, 64, 64, 3, 2),     # all-taps, stride 2
     (2, 32, 64, 64, 160, 3, 1),    # all-taps, two co tiles with a tail
+    (4, 32, 128, 128, 32, 3, 1),   # column-halo variant (few output channels, >= 64K pixels)
+    (2, 64, 190, 176, 48, 3, 1),   # column-halo: two ci tiles, co tail, ragged tile rows / columns
+    (5, 20, 120, 112, 64, 3, 1),   # column-halo: channel tail in ci, two dy chunks
+    (3, 128, 160, 144, 16, 3, 1),  # column-halo: four ci tiles, 16 output channels
 ]
 
 
