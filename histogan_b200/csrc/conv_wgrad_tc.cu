@@ -436,13 +436,13 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
   a.B = p->B; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout; a.KH = p->KH; a.KW = p->KW;
   a.stride = p->stride; a.pad = p->pad; a.OH = OH; a.OW = OW;
   const int Np = (p->Cout + 31) / 32 * 32;
-  if (p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1 && OW >= 16 && OH >= 4 && Np <= 64 &&
+  if (p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1 && OW >= 16 && OH >= 4 && Np <= 128 && Np != 96 &&
       (long long)p->B * OH * OW >= 64 * 1024) {
     // few output channels, many pixels: column-halo variant (see conv_wgrad_col_kernel)
     a.PW = 16; a.PH = 4; a.PB = 1;
     a.tiles_w = (OW + 15) / 16; a.tiles_h = (OH + 3) / 4; a.tiles_b = p->B;
     a.ci_tiles = Kp / 32; a.Kp = Kp;
-    const int NC = Np / 32;                              // 1 or 2
+    const int NC = Np / 32;                              // 1, 2 or 4
     const int kb_total = a.tiles_w * a.tiles_h * a.tiles_b;
     const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
     int splits = (2 * sms + a.ci_tiles - 1) / a.ci_tiles;
@@ -456,7 +456,8 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
     rc = encode_nhwc_map(&tmx, x, p->Cin, p->W, p->H, p->B, 16, 6, 1, 1);
     if (rc) return rc;
     if (NC == 1) return launch_wgrad_col<1, 4>(tmdy, tmx, a, 1, stream);
-    return launch_wgrad_col<2, 4>(tmdy, tmx, a, 1, stream);
+    if (NC == 2) return launch_wgrad_col<2, 4>(tmdy, tmx, a, 1, stream);
+    return launch_wgrad_col<4, 3>(tmdy, tmx, a, 1, stream);
   }
   int PW = 1; while (PW < 16 && PW < OW) PW <<= 1;
   int PH = 1; while (PW * PH < kWgPix && PH < OH) PH <<= 1;

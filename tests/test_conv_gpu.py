@@ -104,6 +104,8 @@ WG_CASES = [
     (2, 64, 190, 176, 48, 3, 1),   # column-halo: two ci tiles, co tail, ragged tile rows / columns
     (5, 20, 120, 112, 64, 3, 1),   # column-halo: channel tail in ci, two dy chunks
     (3, 128, 160, 144, 16, 3, 1),  # column-halo: four ci tiles, 16 output channels
+    (8, 64, 96, 96, 128, 3, 1),    # column-halo: four dy chunks
+    (8, 32, 96, 96, 96, 3, 1),     # 96 output channels: not a column-halo shape (generic path)
 ]
 
 
