@@ -546,7 +546,8 @@ def run_rehisto(args):
     tr = recoloringTrainer("bench", os.path.join(out_dir, "results"), os.path.join(out_dir, "models"),
                            image_size=S, network_capacity=CAPACITY, batch_size=RH_BATCH,
                            gradient_accumulate_every=1, skip_conn_to_GAN=True, initialize_gan=True,
-                           save_every=10 ** 9, fast_rng=True)
+                           save_every=10 ** 9, fast_rng=True,
+                           cuda_graphs=os.environ.get("HG_CUDA_GRAPHS", "1") != "0")
     sampler = ClockSampler(dv.local_rank) if dv.rank == 0 else None
 
     def timed(loader, steps, warmup):
@@ -555,16 +556,17 @@ def run_rehisto(args):
         for _ in range(warmup):
             tr.train(RH_ALPHA, RH_BETA, RH_GAMMA)
         dv.barrier()
-        n0 = lib.hg_launch_count()
+        n0 = lib.hg_launch_count() + tr.graph_replayed_launches
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(steps):
             tr.train(RH_ALPHA, RH_BETA, RH_GAMMA)
         e.record()
         dv.barrier()
-        return dv.max_over_ranks(s.elapsed_time(e) * 1e-3), lib.hg_launch_count() - n0
+        return (dv.max_over_ranks(s.elapsed_time(e) * 1e-3),
+                lib.hg_launch_count() + tr.graph_replayed_launches - n0)
 
-    timed(RecolorLoader(dv.rank, dv.dev), 2, 2)
+    timed(RecolorLoader(dv.rank, dv.dev), 4, 2)        # allocator warm-up + graph capture (both D variants)
     t_dev, launches = timed(RecolorLoader(dv.rank, dv.dev), args.steps, args.warmup)
     host = RecolorLoader(dv.rank)
     t_e2e, _ = timed(host, args.steps, 1)
@@ -591,7 +593,8 @@ def run_rehisto(args):
                        "parallelism": f"dp{dv.world}" + (" + NCCL grad all-reduce" if dv.world > 1 else ""),
                        "l2_flush": "not needed: the step's working set >> 126 MB L2",
                        "timed_steps": f"trainer.steps {FIRST_STEP}..{FIRST_STEP + args.steps - 1}",
-                       "cuda_graphs": False, "peak_mem_gib": round(mem_gb, 2), "final_losses": losses},
+                       "cuda_graphs": bool(tr.cuda_graphs), "peak_mem_gib": round(mem_gb, 2),
+                       "final_losses": losses},
             "e2e": {"value": round(n_imgs / t_e2e, 2), "unit": "images/s",
                     "h2d_bytes_per_step": 2 * (host.x.numel() + host.t.numel()) * 4,
                     "d2h_bytes_per_step": 4 * 6},

@@ -29,8 +29,8 @@ from .gan import (Conv2DMod, Discriminator, GeneratorBlock, HistVectorizer, conv
                   leaky_relu)
 from .hist import RGBuvHistBlock, hellinger_loss
 from .optim import DiffGrad
-from .trainer import (NanException, _allreduce_mean_grads, cast_list, default, gradient_penalty,
-                      image_noise, raise_if_nan, set_requires_grad)
+from .trainer import (NanException, Trainer, _allreduce_mean_grads, cast_list, default,
+                      gradient_penalty, image_noise, raise_if_nan, set_requires_grad)
 
 EPS = 1e-8
 SCALE = 1 / 2 ** 0.5          # rehistoGAN.py:58
@@ -531,6 +531,11 @@ class recoloringTrainer():
                  initialize_gan=False, variance_loss=True, internal_hist=False,
                  change_hyperparameters=False, change_hyperparameters_after=100000, *args, **kwargs):
         self.fast_rng = bool(kwargs.pop('fast_rng', False))
+        # cuda_graphs=True: each phase (forward + backward) of a step is replayed as one CUDA graph
+        self.cuda_graphs = bool(kwargs.pop('cuda_graphs', False))
+        self._graphs = {}
+        self._static = None
+        self.graph_replayed_launches = 0
         self.GAN_params = [args, kwargs]
         self.GAN = None
         self.hist_method = hist_method
@@ -653,6 +658,95 @@ class recoloringTrainer():
                 input_std - torch.std(torch.std(generated_gauss, dim=2), dim=2)))
         return d_loss, histogram_loss, rec, var_loss
 
+    # ---------------------------------------------------------- CUDA-graph path --
+    _graphed = Trainer._graphed          # capture once / replay / re-attach the graph's gradients
+
+    def _phase_d(self, apply_gp):
+        GAN, st = self.GAN, self._static
+        GAN.D_opt.zero_grad(set_to_none=True)
+        noise = torch.rand(self.batch_size, GAN.G.image_size, GAN.G.image_size, 1, device='cuda')
+        with torch.no_grad():
+            fake = self._recolor(st['images'], st['hists'], noise)
+        images = st['images'].detach().requires_grad_(True) if apply_gp else st['images']
+        fake_out, _ = GAN.D(fake)
+        real_out, _ = GAN.D(images)
+        divergence = (F.relu(1 + real_out) + F.relu(1 - fake_out)).mean()
+        loss, gp = divergence, None
+        if apply_gp:
+            gp = gradient_penalty(images, real_out)
+            loss = loss + gp
+        loss.backward()
+        return divergence.detach(), (gp.detach() if gp is not None else None)
+
+    def _phase_g(self, alpha, beta, gamma):
+        GAN, st = self.GAN, self._static
+        GAN.G_opt.zero_grad(set_to_none=True)
+        noise = torch.rand(self.batch_size, GAN.G.image_size, GAN.G.image_size, 1, device='cuda')
+        generated = self._recolor(st['images'], st['hists'], noise)
+        set_requires_grad(GAN.D, False)
+        try:
+            d_loss, h_loss, r_loss, v_loss = self.g_losses(st['images'], st['hists'], generated,
+                                                           alpha, beta, gamma)
+            total = d_loss + h_loss + r_loss
+            if v_loss is not None:
+                total = total + v_loss
+            total.backward()
+        finally:
+            set_requires_grad(GAN.D, True)
+        return (d_loss.detach(), h_loss.detach(), r_loss.detach(),
+                v_loss.detach() if v_loss is not None else None)
+
+    def _train_graphed(self, alpha, beta, gamma, apply_gp):
+        GAN = self.GAN
+        B, S_ = self.batch_size, GAN.G.image_size
+        if self._static is None:
+            self._static = {'images': torch.zeros(B, 3, S_, S_, device='cuda'),
+                            'hists': torch.zeros(B, 3, self.hist_bin, self.hist_bin, device='cuda')}
+        st = self._static
+
+        def stage(batch):
+            st['images'].copy_(batch['images'], non_blocking=True)
+            st['hists'].copy_(batch['histograms'], non_blocking=True)
+
+        d_params = list(GAN.D.parameters())
+        g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        stage(next(self.loader))
+        divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp), d_params)
+        _allreduce_mean_grads(d_params)
+        GAN.D_opt.step()
+        stage(next(self.loader))
+        key = ('G', float(alpha), float(beta), float(gamma))
+        d_loss, h_loss, r_loss, v_loss = self._graphed(key, lambda: self._phase_g(alpha, beta, gamma),
+                                                       g_params)
+        _allreduce_mean_grads([p for p in g_params if p.grad is not None])
+        GAN.G_opt.step()
+        if gp is not None:
+            self.last_gp_loss = gp.item()
+        vals = torch.stack((divergence, d_loss, r_loss, h_loss,
+                            v_loss if v_loss is not None else torch.zeros_like(d_loss))).tolist()
+        self.d_loss, self.g_loss, self.r_loss, self.h_loss = vals[:4]
+        if self.variance_loss is True:
+            self.var_loss = vals[4]
+        self.q_loss = 0.0
+        return divergence.clone(), d_loss.clone()
+
+    def _finish_step(self, total_disc_loss, total_gen_loss):
+        checkpoint_num = floor(self.steps / self.save_every)
+        nan_flag = torch.isnan(total_gen_loss) | torch.isnan(total_disc_loss)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            f = nan_flag.float()
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)
+            nan_flag = f > 0
+        if bool(nan_flag):
+            print(f'NaN detected for generator or discriminator. Loading from checkpoint '
+                  f'#{checkpoint_num}')
+            self.load(checkpoint_num)
+            raise NanException
+        if self.steps % self.save_every == 0 and self._is_main():
+            self.save(checkpoint_num)
+        self.steps += 1
+        self.av = None
+
     def train(self, alpha=32, beta=1.5, gamma=4):
         assert self.loader is not None, ('You must first initialize the data source with '
                                          '`. set_data_src(<folder of images>)`')
@@ -663,6 +757,8 @@ class recoloringTrainer():
             self.init_GAN()
         GAN = self.GAN
         GAN.train()
+        if self.cuda_graphs and self.gradient_accumulate_every == 1:
+            return self._finish_step(*self._train_graphed(alpha, beta, gamma, self.steps % 4 == 0))
         dev = torch.device('cuda', torch.cuda.current_device())
         total_disc_loss = torch.zeros((), device=dev)
         total_gen_loss = torch.zeros((), device=dev)
@@ -732,21 +828,7 @@ class recoloringTrainer():
         _allreduce_mean_grads([p for p in g_params if p.grad is not None])
         GAN.G_opt.step()
 
-        checkpoint_num = floor(self.steps / self.save_every)
-        nan_flag = torch.isnan(total_gen_loss) | torch.isnan(total_disc_loss)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            f = nan_flag.float()
-            dist.all_reduce(f, op=dist.ReduceOp.MAX)
-            nan_flag = f > 0
-        if bool(nan_flag):
-            print(f'NaN detected for generator or discriminator. Loading from checkpoint '
-                  f'#{checkpoint_num}')
-            self.load(checkpoint_num)
-            raise NanException
-        if self.steps % self.save_every == 0 and self._is_main():
-            self.save(checkpoint_num)
-        self.steps += 1
-        self.av = None
+        self._finish_step(total_disc_loss, total_gen_loss)
 
     # --------------------------------------------------------------- storage --
     def print_log(self):

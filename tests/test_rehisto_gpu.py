@@ -165,3 +165,49 @@ def test_recoloring_train_steps_run_and_learn(cuda_device, tmp_path):
     unmoved = [k for k, v in t.GAN.named_parameters()
                if torch.equal(v, before[k]) and "conv_out_rgb" not in k]
     assert not unmoved, unmoved
+
+
+def test_recoloring_graph_path(cuda_device, tmp_path, monkeypatch):
+    """cuda_graphs=True: captured D / G phases reproduce the eager phases (same noise) and a few
+    full steps run (both D variants: with and without the gradient penalty)."""
+    from histogan_b200 import rehistogan as rh
+    from histogan_b200.trainer import SyntheticLoader
+    torch.manual_seed(0)
+    t = rh.recoloringTrainer("g", str(tmp_path / "res"), str(tmp_path / "mod"), 64, 16, batch_size=4,
+                             skip_conn_to_GAN=True, initialize_gan=True, save_every=10 ** 9,
+                             fast_rng=True, cuda_graphs=True)
+    t.loader = SyntheticLoader(4, 64, seed=0)
+    t.init_GAN()
+    t.GAN.train()
+    batch = next(t.loader)
+    t._static = {'images': batch['images'].clone(), 'hists': batch['histograms'].clone()}
+    fixed = torch.rand(4, 64, 64, 1, device='cuda')
+    monkeypatch.setattr(rh.torch, "rand", lambda *a, **k: fixed)
+    d_params = list(t.GAN.D.parameters())
+    g_params = [p for grp in t.GAN.G_opt.param_groups for p in grp['params']]
+    for key, fn, params in ((('D', True), lambda: t._phase_d(True), d_params),
+                            (('D', False), lambda: t._phase_d(False), d_params),
+                            (('G', 32.0, 1.5, 4.0), lambda: t._phase_g(32.0, 1.5, 4.0), g_params)):
+        out_e = [o.clone() for o in fn() if o is not None]
+        g_e = [p.grad.detach().clone() for p in params if p.grad is not None]
+        out_g = [o.clone() for o in t._graphed(key, fn, params) if o is not None]
+        g_g = [p.grad.detach().clone() for p in params if p.grad is not None]
+        for a, b in zip(out_e, out_g):
+            assert abs(a.item() - b.item()) <= 1e-3 * abs(a.item()) + 1e-6, (key, a.item(), b.item())
+        assert len(g_e) == len(g_g) > 0
+        worst = max(((a - b).norm() / b.norm().clamp_min(1e-20)).item() for a, b in zip(g_g, g_e))
+        print(key, "max grad rel diff graph vs eager", worst)
+        assert worst < 2e-2, (key, worst)
+    monkeypatch.undo()
+    t._graphs.clear()
+    t._static = None
+    t.steps = 3
+    before = {k: v.detach().clone() for k, v in t.GAN.named_parameters()}
+    for _ in range(4):                       # steps 3, 4 (gradient penalty), 5, 6
+        t.train()
+    assert t.steps == 7 and t.graph_replayed_launches > 0
+    for v in (t.d_loss, t.g_loss, t.r_loss, t.h_loss, t.var_loss, t.last_gp_loss):
+        assert math.isfinite(v)
+    unmoved = [k for k, v in t.GAN.named_parameters()
+               if torch.equal(v, before[k]) and "conv_out_rgb" not in k]
+    assert not unmoved, unmoved
