@@ -23,6 +23,7 @@
 // issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> fused
 // scale / bias / noise / LeakyReLU / residual -> NHWC global).  The kernel is
 // persistent (one CTA per SM) with two TMEM accumulator stages.
+#include <cstdlib>
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -52,6 +53,9 @@ struct ConvArgs {
   const float* residual;          // NHWC like y, added after the activation (or null)
   int noise_size;
   long long y_img, y_row, y_pix;  // output strides in floats (dense NHWC unless the caller says otherwise)
+  int ksplit;                     // > 1: the K loop (taps x 32-channel chunks) is split over ksplit work
+                                  // items per output tile; raw partial sums are atomically added to a
+                                  // zeroed y and conv_finish_kernel applies the epilogue afterwards
 };
 
 // HALO variant (3x3, stride 1, 16x8-pixel tiles inside one image): one A box with a one-row
@@ -119,7 +123,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   const uint32_t tmem_base = *tmem_ptr;
 
   const int n_tiles = a.n_tiles;
-  const int total_tiles = a.m_tiles * n_tiles;
+  const int ksplit = HALO ? 1 : a.ksplit;
+  const int total_tiles = a.m_tiles * n_tiles * ksplit;      // work items; the split index runs fastest
   const int taps = a.KH * a.KW;
   const int total_kb = taps * a.kc_per_tap;
 
@@ -127,7 +132,8 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
+        const int tile = item / ksplit, ks = item - tile * ksplit;
         const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BLOCK_N;
         const int tw_i = mt % a.tiles_w;
         const int th_i = (mt / a.tiles_w) % a.tiles_h;
@@ -150,17 +156,18 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             }
           }
         } else {
-          for (int tap = 0; tap < taps; ++tap) {
+          const int it0 = (int)((long long)ks * total_kb / ksplit);
+          const int it1 = (int)((long long)(ks + 1) * total_kb / ksplit);
+          for (int it = it0; it < it1; ++it) {
+            const int tap = it / a.kc_per_tap, kc = it - tap * a.kc_per_tap;
             const int kh = tap / a.KW, kw = tap - kh * a.KW;
-            for (int kc = 0; kc < a.kc_per_tap; ++kc) {
-              ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-              uint8_t* sA = base + stage * SM::kStageBytes;
-              uint8_t* sB = sA + kABytes;
-              ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
-              ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
-              ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Kp + kc * kBlockK, n0);
-              if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sA = base + stage * SM::kStageBytes;
+            uint8_t* sB = sA + kABytes;
+            ptx::mbar_expect_tx(&full_bar[stage], kABytes + SM::kBBytes);
+            ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0 + kh, b0);
+            ptx::tma_load_2d(sB, &tmw, &full_bar[stage], tap * a.Kp + kc * kBlockK, n0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
           }
         }
       }
@@ -171,13 +178,16 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++t) {
         const int acc = t & 1;
         const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
         ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);   // epilogue drained this stage
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
-        const int iters = HALO ? 3 * a.kc_per_tap : total_kb;
+        const int ks = item % ksplit;
+        const int iters = HALO ? 3 * a.kc_per_tap
+                               : (int)((long long)(ks + 1) * total_kb / ksplit) -
+                                     (int)((long long)ks * total_kb / ksplit);
         for (int kb = 0; kb < iters; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -208,9 +218,10 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     const int row = q * 32 + lane;
     const int tw = row % a.TW, th = (row / a.TW) % a.TH, tb = row / (a.TW * a.TH);
     int t = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+    for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++t) {
       const int acc = t & 1;
       const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
+      const int tile = item / ksplit;
       const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BLOCK_N;
       const int tw_i = mt % a.tiles_w;
       const int th_i = (mt / a.tiles_w) % a.tiles_h;
@@ -240,6 +251,14 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           float* yo = a.y + (long long)b * a.y_img + (long long)oh * a.y_row + (long long)ow * a.y_pix + n;
           const float* ro = a.residual ? a.residual + pix * a.Cout + n : nullptr;
           const float* sc = a.scale ? a.scale + (long long)b * a.Cout + n : nullptr;
+          if (ksplit > 1) {             // raw partial sums; conv_finish_kernel does the rest
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)      // constant indices keep v[] in registers
+              if (j < ncols)
+                ptx::red_add_f32x4(yo + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            continue;
+          }
 #define HG_EPILOGUE_4(J)                                                                      \
           {                                                                                   \
             float o[4];                                                                       \
@@ -283,6 +302,39 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+constexpr bool kSplitKDefault = false;     // HG_CONV_SPLITK=1 enables it (pending GPU verification)
+
+// epilogue of a split-K convolution: the same element-wise chain as HG_EPILOGUE_4, applied in
+// place to the dense NHWC y that holds the summed partial products
+__global__ void __launch_bounds__(256)
+conv_finish_kernel(const ConvArgs a) {
+  const long long n4 = (long long)a.B * a.OH * a.OW * (a.Cout / 4);
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int n = (int)(i % (a.Cout / 4)) * 4;
+  const long long pix = i / (a.Cout / 4);
+  const int ow = (int)(pix % a.OW);
+  const int oh = (int)((pix / a.OW) % a.OH);
+  const int b = (int)(pix / ((long long)a.OW * a.OH));
+  float* yo = a.y + pix * a.Cout + n;
+  float4 v4 = *reinterpret_cast<const float4*>(yo);
+  float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  float nz = 0.f;
+  if (a.noise) nz = a.noise[((long long)b * a.noise_size + ow) * a.noise_size + oh];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float tv = v[e];
+    if (a.scale) tv *= a.scale[(long long)b * a.Cout + n + e];
+    if (a.bias) tv += a.bias[n + e];
+    if (a.noise) tv = fmaf(nz, a.noise_w[n + e], tv + a.noise_b[n + e]);
+    if (a.flags & HG_CONV_LRELU) tv = tv > 0.f ? tv : tv * a.slope;
+    if (a.residual) tv += a.residual[pix * a.Cout + n + e];
+    if (a.flags & HG_CONV_ROUND_TF32) tv = tf32_round(tv);
+    v[e] = tv;
+  }
+  *reinterpret_cast<float4*>(yo) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // ------------------------------------------------- weight packing kernel ----
@@ -377,11 +429,20 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set = true;
   }
-  const int total = m_tiles * a.n_tiles;
+  const int total = m_tiles * a.n_tiles * (HALO ? 1 : a.ksplit);
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int grid = total < sms ? total : sms;
+  const bool split = !HALO && a.ksplit > 1;
+  if (split)
+    HG_CUDA_OK(cudaMemsetAsync(a.y, 0, sizeof(float) * (size_t)a.B * a.OH * a.OW * a.Cout, stream));
   conv_tf32_kernel<BLOCK_N, STAGES, HALO><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
   HG_LAUNCH_OK("conv_tf32_kernel");
+  if (split && (a.scale || a.bias || a.noise || a.residual ||
+                (a.flags & (HG_CONV_LRELU | HG_CONV_ROUND_TF32)))) {
+    const long long n4 = (long long)a.B * a.OH * a.OW * (a.Cout / 4);
+    conv_finish_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a);
+    HG_LAUNCH_OK("conv_finish_kernel");
+  }
   return 0;
 }
 
@@ -486,6 +547,24 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
   const int Ktot = p->KH * p->KW * Kp;
   const int BN = (Np % 128 == 0) ? 128 : (Np % 64 == 0 ? 64 : 32);
   a.n_tiles = Np / BN;
+  // few output tiles but a long K loop (the 4x4 / 2x2 layers stream up to 151 MB of weights
+  // through a handful of SMs): split K over several CTAs per tile
+  a.ksplit = 1;
+  {
+    const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+    const int base = m_tiles * a.n_tiles, iters = p->KH * p->KW * a.kc_per_tap;
+    const bool dense_out = a.y_pix == p->Cout && a.y_row == (long long)OW * p->Cout &&
+                           a.y_img == (long long)OH * OW * p->Cout;
+    static const bool enabled = [] {
+      const char* e = getenv("HG_CONV_SPLITK");
+      return e ? e[0] != '0' : kSplitKDefault;
+    }();
+    if (enabled && !halo && dense_out && 2 * base <= sms && iters >= 32) {
+      int ks = sms / base;
+      if (ks > iters / 8) ks = iters / 8;
+      if (ks >= 2) a.ksplit = ks;
+    }
+  }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Np};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 4};

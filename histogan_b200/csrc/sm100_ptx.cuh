@@ -160,6 +160,12 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t m, uint
          ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// vectorised fp32 reduction to global memory (sm_90+): *(float4*)p += (a, b, c, d), no return value
+__device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
 }  // namespace ptx
 
 // round-to-nearest(-even) of the 13 low mantissa bits: the value tcgen05 kind::tf32

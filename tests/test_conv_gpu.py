@@ -70,6 +70,34 @@ def test_conv_epilogue(cuda_device):
     assert torch.equal(y2, conv.tf32_round(conv.conv2d_nhwc(x, wp, 1, 1)))
 
 
+def test_conv_epilogue_split_k(cuda_device):
+    """few output tiles + a long K loop -> split-K: partial sums by atomics into a zeroed y, the
+    fused epilogue chain applied by the finishing kernel."""
+    from histogan_b200 import conv
+    B, Cin, S, Cout = 4, 256, 4, 128
+    g = torch.Generator().manual_seed(5)
+    x = conv.tf32_round(torch.randn(B, Cin, S, S, generator=g)).cuda()
+    w = conv.tf32_round(torch.randn(Cout, Cin, 3, 3, generator=g) / 48).cuda()
+    scale = torch.rand(B, Cout, generator=g).cuda() + 0.5
+    bias = torch.randn(Cout, generator=g).cuda()
+    noise = torch.rand(B, 8, 8, generator=g).cuda()
+    nw, nb = torch.randn(Cout, generator=g).cuda(), torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(B, Cout, S, S, generator=g).cuda()
+    wp = conv.pack_weight(w, 0)
+    y = conv.conv2d_nhwc(x, wp, 1, 1, scale=scale, bias=bias, noise=noise, noise_w=nw, noise_b=nb,
+                         residual=res, lrelu=True)
+    ref = _ref(x, w, 1, 1) * scale[:, :, None, None] + bias[None, :, None, None]
+    nz = noise[:, :S, :S].transpose(1, 2)
+    ref = ref + nz[:, None] * nw[None, :, None, None] + nb[None, :, None, None]
+    ref = F.leaky_relu(ref, 0.2) + res
+    err = (y - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 2e-5, err
+    y2 = conv.conv2d_nhwc(x, wp, 1, 1, bias=bias, round_tf32=True)
+    assert bool(((y2.view(torch.int32) & 0x1FFF) == 0).all())
+    plain = conv.conv2d_nhwc(x, wp, 1, 1)
+    assert (plain - _ref(x, w, 1, 1)).abs().max().item() / ref.abs().max().item() < 2e-5
+
+
 def test_dgrad_weight_packing(cuda_device):
     """conv(dy, pack(w, mode=1)) == d/dx of conv(x, w) for stride 1."""
     from histogan_b200 import conv
