@@ -66,33 +66,44 @@ struct ConvArgs {
 // layers.
 constexpr int kHaloABytes = (8 + 2) * 16 * kBlockK * 4;   // 20 KB
 
-template <int BLOCK_N, int STAGES, bool HALO = false>
+// RESW (halo variant, one n-tile, whole filter <= 72 KB -- the 32-channel 256^2 / 128^2 layers):
+// the packed filter is loaded into shared memory ONCE per CTA and stays resident while the CTA
+// walks its tiles; the ring then carries activation boxes only.  These layers are bound by the
+// bytes TMA moves into shared memory (~30 B/clk/SM measured), of which the per-tile filter
+// re-fetch was 36 of 96 KB.
+constexpr int kResWBytes = 72 * 1024;
+
+template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
 struct ConvSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
   static constexpr int kAStage = HALO ? kHaloABytes : kABytes;
-  static constexpr int kStageBytes = kAStage + (HALO ? 3 : 1) * kBBytes;
-  static constexpr int kTotal = STAGES * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStageBytes = kAStage + (RESW ? 0 : (HALO ? 3 : 1) * kBBytes);
+  static constexpr int kRing = STAGES * kStageBytes;
+  static constexpr int kTotal = kRing + (RESW ? kResWBytes : 0) + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // Persistent kernel: one CTA per SM walks output tiles (n fastest, so the CTAs running
 // together share A tiles through L2).  Two TMEM accumulator stages let the epilogue of
 // tile t overlap the main loop of tile t+1; the smem ring (STAGES deep) runs straight
 // through tile boundaries.
-template <int BLOCK_N, int STAGES, bool HALO = false>
+template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                  const ConvArgs a) {
-  using SM = ConvSmem<BLOCK_N, STAGES, HALO>;
+  static_assert(!RESW || HALO, "resident weights: halo variant only");
+  using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW>;
   constexpr uint32_t kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + STAGES * SM::kStageBytes);
+  uint8_t* wres = base + SM::kRing;                  // RESW: [tap][kc] filter tiles, kBBytes each
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + SM::kRing + (RESW ? kResWBytes : 0));
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* wres_bar = tmem_empty_bar + 2;           // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(wres_bar + 1);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
@@ -111,6 +122,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         ptx::mbar_init(&tmem_full_bar[s], 1);
         ptx::mbar_init(&tmem_empty_bar[s], 4);        // one arrival per epilogue warp
       }
+      ptx::mbar_init(wres_bar, 1);
       ptx::fence_barrier_init();
     }
     __syncwarp();
@@ -132,6 +144,14 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     if (ptx::elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      if (RESW) {                                    // the whole filter, once
+        const int n_w = 9 * a.kc_per_tap;
+        ptx::mbar_expect_tx(wres_bar, n_w * SM::kBBytes);
+        for (int i = 0; i < n_w; ++i) {
+          const int tap = i / a.kc_per_tap, kc = i - tap * a.kc_per_tap;
+          ptx::tma_load_2d(wres + i * SM::kBBytes, &tmw, wres_bar, tap * a.Kp + kc * kBlockK, 0);
+        }
+      }
       for (int item = blockIdx.x; item < total_tiles; item += gridDim.x) {
         const int tile = item / ksplit, ks = item - tile * ksplit;
         const int mt = tile / n_tiles, n0 = (tile - mt * n_tiles) * BLOCK_N;
@@ -148,10 +168,12 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
               uint8_t* sB = sA + SM::kAStage;
               ptx::mbar_expect_tx(&full_bar[stage], SM::kStageBytes);
               ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0 + kw, ih0, b0);
+              if (!RESW) {
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh)
-                ptx::tma_load_2d(sB + kh * SM::kBBytes, &tmw, &full_bar[stage],
-                                 (kh * 3 + kw) * a.Kp + kc * kBlockK, n0);
+                for (int kh = 0; kh < 3; ++kh)
+                  ptx::tma_load_2d(sB + kh * SM::kBBytes, &tmw, &full_bar[stage],
+                                   (kh * 3 + kw) * a.Kp + kc * kBlockK, n0);
+              }
               if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
           }
@@ -178,6 +200,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       int t = 0;
+      if (RESW) ptx::mbar_wait(wres_bar, 0);           // filter resident
       for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++t) {
         const int acc = t & 1;
         const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
@@ -197,8 +220,12 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             // HALO: vertical tap kh = the same box 16 pixel rows (2 swizzle atoms) further down
             const uint64_t a_desc = ptx::make_smem_desc(sA + (uint32_t)(kh * 2048), 16, 1024,
                                                         ptx::kLayoutSW128);
-            const uint64_t b_desc = ptx::make_smem_desc(sA + SM::kAStage + (uint32_t)(kh * SM::kBBytes),
-                                                        16, 1024, ptx::kLayoutSW128);
+            // HALO iteration kb = (kw, kc): kw = kb / kc_per_tap
+            const uint32_t sBt =
+                RESW ? ptx::smem_u32(wres) + (uint32_t)(((kh * 3 + kb / a.kc_per_tap) * a.kc_per_tap +
+                                                        kb % a.kc_per_tap) * SM::kBBytes)
+                     : sA + SM::kAStage + (uint32_t)(kh * SM::kBBytes);
+            const uint64_t b_desc = ptx::make_smem_desc(sBt, 16, 1024, ptx::kLayoutSW128);
 #pragma unroll
             for (int k = 0; k < kBlockK / 8; ++k) {
               // advance 8 tf32 = 32 B along K inside the 128 B swizzle row: +2 in (addr >> 4) units
@@ -304,6 +331,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
+constexpr bool kResidentWDefault = false;  // HG_CONV_RESIDENT_W=1 enables it (pending GPU verification)
 constexpr bool kSplitKDefault = false;     // HG_CONV_SPLITK=1 enables it (pending GPU verification)
 
 // epilogue of a split-K convolution: the same element-wise chain as HG_EPILOGUE_4, applied in
@@ -419,13 +447,13 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
   return 0;
 }
 
-template <int BLOCK_N, int STAGES, bool HALO = false>
+template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
                        int m_tiles, cudaStream_t stream) {
-  using SM = ConvSmem<BLOCK_N, STAGES, HALO>;
+  using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW>;
   static bool attr_set = false;
   if (!attr_set) {
-    HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES, HALO>,
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_set = true;
   }
@@ -435,7 +463,7 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
   const bool split = !HALO && a.ksplit > 1;
   if (split)
     HG_CUDA_OK(cudaMemsetAsync(a.y, 0, sizeof(float) * (size_t)a.B * a.OH * a.OW * a.Cout, stream));
-  conv_tf32_kernel<BLOCK_N, STAGES, HALO><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
+  conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
   HG_LAUNCH_OK("conv_tf32_kernel");
   if (split && (a.scale || a.bias || a.noise || a.residual ||
                 (a.flags & (HG_CONV_LRELU | HG_CONV_ROUND_TF32)))) {
@@ -574,6 +602,17 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     if (rc) return rc;
   }
   if (halo) {
+    static const bool resw_enabled = [] {
+      const char* e = getenv("HG_CONV_RESIDENT_W");
+      return e ? e[0] != '0' : kResidentWDefault;
+    }();
+    // whole filter resident in shared memory (one n-tile, <= 72 KB, enough tiles per CTA to pay
+    // for the up-front load)
+    if (resw_enabled && a.n_tiles == 1 && 9 * a.kc_per_tap * BN * kBlockK * 4 <= kResWBytes &&
+        m_tiles >= 4 * 148) {
+      if (BN == 64) return launch_conv<64, 6, true, true>(tmx, tmw, a, m_tiles, stream);
+      if (BN == 32) return launch_conv<32, 7, true, true>(tmx, tmw, a, m_tiles, stream);
+    }
     if (BN == 128) return launch_conv<128, 3, true>(tmx, tmw, a, m_tiles, stream);
     if (BN == 64) return launch_conv<64, 4, true>(tmx, tmw, a, m_tiles, stream);
     return launch_conv<32, 6, true>(tmx, tmw, a, m_tiles, stream);

@@ -23,6 +23,10 @@ CASES = [
     (2, 16, 32, 32, 32, 1, 1),
     (2, 32, 32, 32, 16, 3, 2),
     (2, 48, 16, 16, 80, 3, 1),     # channel tails inside a k-block / an n-tile
+    (8, 32, 128, 128, 32, 3, 1),   # >= 592 tiles, one n-tile, 36 KB filter: resident-filter halo variant
+    (4, 64, 128, 160, 32, 3, 1),   # resident filter, two k-chunks per tap
+    (4, 32, 128, 160, 64, 3, 1),   # resident filter, BLOCK_N = 64
+    (5, 20, 120, 136, 24, 3, 1),   # resident filter with channel tails and ragged tiles
 ]
 
 
