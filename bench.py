@@ -547,7 +547,7 @@ def run_rehisto(args):
                            image_size=S, network_capacity=CAPACITY, batch_size=RH_BATCH,
                            gradient_accumulate_every=1, skip_conn_to_GAN=True, initialize_gan=True,
                            save_every=10 ** 9, fast_rng=True,
-                           cuda_graphs=os.environ.get("HG_CUDA_GRAPHS_REHISTO", "0") != "0")
+                           cuda_graphs=os.environ.get("HG_CUDA_GRAPHS", "1") != "0")
     sampler = ClockSampler(dv.local_rank) if dv.rank == 0 else None
 
     def timed(loader, steps, warmup):

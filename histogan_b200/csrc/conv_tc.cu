@@ -54,8 +54,10 @@ struct ConvArgs {
   int noise_size;
   long long y_img, y_row, y_pix;  // output strides in floats (dense NHWC unless the caller says otherwise)
   int ksplit;                     // > 1: the K loop (taps x 32-channel chunks) is split over ksplit work
-                                  // items per output tile; raw partial sums are atomically added to a
-                                  // zeroed y and conv_finish_kernel applies the epilogue afterwards
+                                  // items per output tile; each writes its raw partial sums to its own
+                                  // slice of `partial`, conv_finish_kernel adds the slices in a fixed
+                                  // order (deterministic) and applies the epilogue
+  float* partial;                 // [ksplit][B*OH*OW][Cout]
 };
 
 // HALO variant (3x3, stride 1, 16x8-pixel tiles inside one image): one A box with a one-row
@@ -279,11 +281,13 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           const float* ro = a.residual ? a.residual + pix * a.Cout + n : nullptr;
           const float* sc = a.scale ? a.scale + (long long)b * a.Cout + n : nullptr;
           if (ksplit > 1) {             // raw partial sums; conv_finish_kernel does the rest
+            float* po = a.partial + ((long long)(item - tile * ksplit) * a.B * a.OH * a.OW + pix) * a.Cout + n;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)      // constant indices keep v[] in registers
               if (j < ncols)
-                ptx::red_add_f32x4(yo + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                *reinterpret_cast<float4*>(po + j) =
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
             continue;
           }
 #define HG_EPILOGUE_4(J)                                                                      \
@@ -331,11 +335,11 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
 }
 
-constexpr bool kResidentWDefault = false;  // HG_CONV_RESIDENT_W=1 enables it (pending GPU verification)
-constexpr bool kSplitKDefault = false;     // HG_CONV_SPLITK=1 enables it (pending GPU verification)
+constexpr bool kResidentWDefault = true;   // HG_CONV_RESIDENT_W=0 disables it
+constexpr bool kSplitKDefault = true;      // HG_CONV_SPLITK=0 disables it
 
-// epilogue of a split-K convolution: the same element-wise chain as HG_EPILOGUE_4, applied in
-// place to the dense NHWC y that holds the summed partial products
+// epilogue of a split-K convolution: adds the ksplit partial slices in index order and applies
+// the same element-wise chain as HG_EPILOGUE_4; writes the dense NHWC y
 __global__ void __launch_bounds__(256)
 conv_finish_kernel(const ConvArgs a) {
   const long long n4 = (long long)a.B * a.OH * a.OW * (a.Cout / 4);
@@ -347,8 +351,12 @@ conv_finish_kernel(const ConvArgs a) {
   const int oh = (int)((pix / a.OW) % a.OH);
   const int b = (int)(pix / ((long long)a.OW * a.OH));
   float* yo = a.y + pix * a.Cout + n;
-  float4 v4 = *reinterpret_cast<const float4*>(yo);
-  float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  const long long slice = (long long)a.B * a.OH * a.OW * a.Cout;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int ks = 0; ks < a.ksplit; ++ks) {
+    const float4 p4 = *reinterpret_cast<const float4*>(a.partial + ks * slice + pix * a.Cout + n);
+    v[0] += p4.x; v[1] += p4.y; v[2] += p4.z; v[3] += p4.w;
+  }
   float nz = 0.f;
   if (a.noise) nz = a.noise[((long long)b * a.noise_size + ow) * a.noise_size + oh];
 #pragma unroll
@@ -447,6 +455,26 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
   return 0;
 }
 
+// Per-device scratch for the split-K partial sums: ONE fixed 64 MB allocation made on first use
+// (never during stream capture, never freed or moved -- captured CUDA graphs keep its address).
+// A convolution that would need more, or whose first use falls inside a capture, runs unsplit.
+// Calls are ordered by the stream they are issued on, like every other buffer of this library.
+constexpr size_t kSplitKWsBytes = 64u << 20;
+
+static float* splitk_workspace(size_t bytes, cudaStream_t stream) {
+  static float* ws[16] = {};
+  if (bytes > kSplitKWsBytes) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (ws[dev]) return ws[dev];
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+  float* p = nullptr;
+  if (cudaMalloc(&p, kSplitKWsBytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ws[dev] = p;
+  return p;
+}
+
 template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
                        int m_tiles, cudaStream_t stream) {
@@ -461,12 +489,9 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int grid = total < sms ? total : sms;
   const bool split = !HALO && a.ksplit > 1;
-  if (split)
-    HG_CUDA_OK(cudaMemsetAsync(a.y, 0, sizeof(float) * (size_t)a.B * a.OH * a.OW * a.Cout, stream));
   conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
   HG_LAUNCH_OK("conv_tf32_kernel");
-  if (split && (a.scale || a.bias || a.noise || a.residual ||
-                (a.flags & (HG_CONV_LRELU | HG_CONV_ROUND_TF32)))) {
+  if (split) {
     const long long n4 = (long long)a.B * a.OH * a.OW * (a.Cout / 4);
     conv_finish_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a);
     HG_LAUNCH_OK("conv_finish_kernel");
@@ -590,7 +615,10 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     if (enabled && !halo && dense_out && 2 * base <= sms && iters >= 32) {
       int ks = sms / base;
       if (ks > iters / 8) ks = iters / 8;
-      if (ks >= 2) a.ksplit = ks;
+      if (ks >= 2) {
+        a.partial = splitk_workspace(sizeof(float) * (size_t)ks * p->B * OH * OW * p->Cout, stream);
+        if (a.partial) a.ksplit = ks;
+      }
     }
   }
   {
@@ -608,8 +636,10 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     }();
     // whole filter resident in shared memory (one n-tile, <= 72 KB, enough tiles per CTA to pay
     // for the up-front load)
-    if (resw_enabled && a.n_tiles == 1 && 9 * a.kc_per_tap * BN * kBlockK * 4 <= kResWBytes &&
-        m_tiles >= 4 * 148) {
+    // (measured: 197 -> 180 us on 32->32 @256^2; with two k-chunks per tap, 64->32, it is a
+    // loss -- 242 -> 255 us -- so one chunk per tap only)
+    if (resw_enabled && a.n_tiles == 1 && a.kc_per_tap == 1 &&
+        9 * a.kc_per_tap * BN * kBlockK * 4 <= kResWBytes && m_tiles >= 4 * 148) {
       if (BN == 64) return launch_conv<64, 6, true, true>(tmx, tmw, a, m_tiles, stream);
       if (BN == 32) return launch_conv<32, 7, true, true>(tmx, tmw, a, m_tiles, stream);
     }

@@ -538,7 +538,11 @@ class Trainer:
         for p, gr in entry[3]:
             p.grad = gr
         self.graph_replayed_launches += entry[2]
-        return entry[1]
+        # The graphs share one memory pool: a graph captured EARLIER may use, as scratch, the block
+        # in which a later-captured graph keeps an output.  Gradients are consumed (all-reduce +
+        # optimiser) before the next replay; the scalar outputs are read at the end of the step,
+        # so hand out copies that live outside the pool.
+        return tuple(o.clone() if o is not None else None for o in entry[1])
 
     def _train_graphed(self, alpha, apply_gp):
         GAN = self.GAN

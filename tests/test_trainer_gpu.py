@@ -150,6 +150,9 @@ def test_cuda_graph_training_path(tmp_path, cuda_device):
     # initial ~110) and the penalty read-out must be a valid non-negative number
     assert 0.2 < tg.d_loss / te.d_loss < 5, (tg.d_loss, te.d_loss)
     assert tg.last_gp_loss >= 0
+    # the read-out must be THIS trainer's penalty, not whatever a later graph left in the shared
+    # pool: same order of magnitude as the eager trainer's (same data, same initial weights)
+    assert 0.05 < tg.last_gp_loss / te.last_gp_loss < 20, (tg.last_gp_loss, te.last_gp_loss)
     moved = sum(not torch.equal(p, q) for p, q in zip(tg.GAN.G.parameters(), te.GAN.G.parameters()))
     assert moved > 10          # different random latents -> different but comparable trajectories
     tg.steps = 2528                        # a path-length step runs eagerly inside a graphed trainer
