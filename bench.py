@@ -442,7 +442,11 @@ def run_train(args):
                                              "with Cin,Cout % 4 == 0, forward, CUDA events)",
                 "achieved": round(conv_tf, 1), "peak": bf16_peak,
                 "unit": "TFLOP/s", "frac": round(conv_tf / bf16_peak, 4),
-                "traffic": None, "peak_kind": peak_kind,
+                # dram__bytes_read+write of ONE launch of this kernel on the 32->32 3x3 @256^2 layer
+                # (ncu --set full, profiles/r01_conv_fwd_32ch_256_ncu.md); algorithmic = 536.9 MB
+                "traffic": 486.8e6, "traffic_layer": "32->32 3x3 @256^2, batch 32: algorithmic 536.9e6 B "
+                                                     "(x read once + y written once)",
+                "peak_kind": peak_kind,
                 "note": "operands are TF32 (half the bf16 rate): fraction of the TF32 ceiling = 2x frac",
                 "per_layer_tflops": conv_rows,
                 "step_algorithmic_conv_tflop": round(step_flops / 1e12, 3),

@@ -54,6 +54,14 @@ def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
     co, ci, kh, kw = w.shape
     n, k = (ci, co) if mode else (co, ci)
     out = torch.empty((_up32(n), kh, kw, _up32(k)), dtype=torch.float32, device=w.device)
+    if ohwi and mode == 0 and co % 32 == 0 and ci % 32 == 0:
+        # channels_last parameter, nothing to pad: the packed forward operand IS the parameter's
+        # memory, TF32-rounded -- one vectorised copy (hg_modulate_round without a modulation)
+        with torch.cuda.device(w.device):
+            rc = lib.hg_modulate_round(_lib.ptr(w), None, _lib.ptr(out), 1, co * kh * kw, ci, 1,
+                                       _lib.current_stream_ptr(w.device))
+        _lib.check(rc, "hg_modulate_round")
+        return out
     with torch.cuda.device(w.device):
         rc = lib.hg_pack_conv_weight(_lib.ptr(w), _lib.ptr(out), co, ci, kh, kw,
                                      int(mode) | (PACK_FROM_OHWI if ohwi else 0),

@@ -38,9 +38,13 @@ def test_full_size_properties(insz, cuda_device):
         assert parity.fro_rel(hs[:, 0], h[:2, 2].transpose(1, 2)) < 1e-6
         assert parity.fro_rel(hs[:, 2], h[:2, 0].transpose(1, 2)) < 1e-6
         assert parity.fro_rel(hs[:, 1], h[:2, 1].transpose(1, 2)) < 1e-6
-    # one image against the CPU oracle, full resolution, with loss + grad
+    # one image against the CPU oracle, full resolution, with loss + grad.  The oracle is run
+    # here, on the GPU box's host, whose libm / SLEEF logf may be 1 ulp off the correctly rounded
+    # value the kernels use (that alone moves the Frobenius distance to ~4e-6 on some hosts): the
+    # strict comparison therefore feeds the oracle the device's logarithms, the comparison with
+    # the host's own log gets the end-to-end tolerance times ten.
     t = ho.synth_random_target(1, seed=2)
-    rh, rl, rg = ho.hist_loss_and_grad(x[:1].cpu(), t, 2.0, insz=insz)
+    rh, rl, rg = ho.hist_loss_and_grad(x[:1].cpu(), t, 2.0, insz=insz, log_fn=parity.device_log)
     xc = x[:1].clone().requires_grad_(True)
     hc = blk(F.relu(xc))
     loss = hellinger_loss(t.cuda(), hc, 2.0)
@@ -48,6 +52,8 @@ def test_full_size_properties(insz, cuda_device):
     parity.assert_hist_e2e(hc, rh, f"full-size insz={insz}")
     parity.assert_loss(loss.item(), rl.item())
     parity.assert_grad(xc.grad, rg, f"full-size grad insz={insz}")
+    rh_host, _, _ = ho.hist_loss_and_grad(x[:1].cpu(), t, 2.0, insz=insz)
+    assert parity.fro_rel(hc.detach().cpu(), rh_host) <= 10 * parity.E2E_FRO_REL
 
 
 def test_gradient_is_directional_derivative(cuda_device):
