@@ -22,6 +22,7 @@ __device__ __forceinline__ void reduce_pixel_lanes(float4 (&acc)[NQ], float4* sm
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4      // (fully unrolled, ptxas hoisted all 32 x NQ loads and spilled ~1.4 KB)
       for (int k = 0; k < kPixLanes; ++k) {
         const float4 v = smem[(q * kPixLanes + k) * 8 + cl];
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
