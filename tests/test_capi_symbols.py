@@ -60,3 +60,37 @@ def test_block_rejects_cpu_and_bad_args():
     b = [3, -3]
     RGBuvHistBlock(hist_boundary=b)
     assert b == [-3, 3]                               # sorted in place (RGBuvHistBlock.py:68)
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    """the ctypes mirrors of the ABI structs have the size / field offsets a C compiler gives the
+    declarations in include/histogan_b200.h (compiled here with gcc as plain C)."""
+    import shutil
+    import subprocess
+    from histogan_b200 import _lib
+    if not shutil.which("gcc"):
+        pytest.skip("gcc not available")
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "histogan_b200.h"
+int main(void) {
+  printf("%zu %zu %zu\n", sizeof(hg_hist_params), offsetof(hg_hist_params, sigma), offsetof(hg_hist_params, projection));
+  printf("%zu %zu\n", sizeof(hg_conv_params), offsetof(hg_conv_params, OW));
+  printf("%zu %zu %zu %zu\n", sizeof(hg_conv_epilogue), offsetof(hg_conv_epilogue, noise_size),
+         offsetof(hg_conv_epilogue, lrelu_slope), offsetof(hg_conv_epilogue, out_pix_stride));
+  printf("%d\n", HG_ABI_VERSION);
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = list(map(int, out))
+    H, P, E = _lib.HistParams, _lib.ConvParams, _lib.ConvEpilogue
+    want = [C.sizeof(H), H.sigma.offset, H.projection.offset,
+            C.sizeof(P), P.OW.offset,
+            C.sizeof(E), E.noise_size.offset, E.lrelu_slope.offset, E.out_pix_stride.offset,
+            _lib.HG_ABI_VERSION]
+    assert got == want, (got, want)
