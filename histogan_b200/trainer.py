@@ -18,6 +18,7 @@ EMA / NaN guard / checkpointing on the same schedule) but
 from __future__ import annotations
 
 import json
+import os
 from math import floor, log2
 from pathlib import Path
 from random import random
@@ -227,6 +228,50 @@ def _allreduce_mean_grads(params, bucket_bytes=128 << 20):
         flat.div_(world)
         pieces = flat.split([t.numel() for t in tensors])
         torch._foreach_copy_(tensors, [p.view_as(t) for p, t in zip(pieces, tensors)])
+
+
+class _GradOverlap:
+    """EXPERIMENTAL, off unless HG_OVERLAP_ALLREDUCE=1 (not yet measured on >1 GPU): all-reduce each
+    gradient as soon as autograd has accumulated it, on the process group's own stream, so that the
+    exchange overlaps the rest of the backward pass instead of following it.  Used inside the
+    captured phases (NCCL collectives are capturable), which puts the collectives INTO the CUDA
+    graph; ``finish()`` waits for them and turns the sums into means.
+
+        with _GradOverlap(params) as ov:
+            loss.backward()
+        ov.finish()
+    """
+
+    def __init__(self, params, force=None):
+        on = os.environ.get('HG_OVERLAP_ALLREDUCE', '0') != '0' if force is None else force
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.enabled = bool(on) and self.world > 1
+        self.params = [p for p in params if p.requires_grad]
+        self.works, self.handles = [], []
+
+    def _hook(self, p):
+        self.works.append((dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, async_op=True), p))
+
+    def __enter__(self):
+        if self.enabled:
+            self.handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        return self
+
+    def __exit__(self, *exc):
+        for h in self.handles:
+            h.remove()
+        self.handles = []
+        return False
+
+    def finish(self):
+        if not self.enabled:
+            return
+        for w, _ in self.works:
+            w.wait()
+        grads = [p.grad for _, p in self.works]
+        if grads:
+            torch._foreach_div_(grads, self.world)
+        self.works = []
 
 
 class Trainer:
@@ -501,7 +546,9 @@ class Trainer:
         if apply_gp:
             gp = gradient_penalty(images, real_out)
             loss = loss + gp
-        loss.backward()
+        with _GradOverlap(GAN.D.parameters()) as ov:
+            loss.backward()
+        ov.finish()
         return divergence.detach(), (gp.detach() if gp is not None else None)
 
     def _phase_g(self, alpha):
@@ -518,7 +565,9 @@ class Trainer:
             fake_out, _ = GAN.D(fake)
             hist_loss = hellinger_loss(st['hists'], self.histBlock(F.relu(fake)), alpha)
             loss = fake_out.mean()
-            (loss + hist_loss).backward()
+            with _GradOverlap([p for grp in GAN.G_opt.param_groups for p in grp['params']]) as ov:
+                (loss + hist_loss).backward()
+            ov.finish()
         finally:
             set_requires_grad(GAN.D, True)
         return loss.detach(), hist_loss.detach()
@@ -582,12 +631,15 @@ class Trainer:
         stage(next(self.loader), True)
         d_params = list(GAN.D.parameters())
         g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        overlapped = _GradOverlap([]).enabled       # the collectives then live inside the graphs
         divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp), d_params)
-        _allreduce_mean_grads(d_params)
+        if not overlapped:
+            _allreduce_mean_grads(d_params)
         GAN.D_opt.step()
         stage(next(self.loader), False)
         g_loss, h_loss = self._graphed(('G', float(alpha)), lambda: self._phase_g(alpha), g_params)
-        _allreduce_mean_grads(g_params)
+        if not overlapped:
+            _allreduce_mean_grads(g_params)
         GAN.G_opt.step()
         # host reads once, after everything has been queued
         self.q_loss = 0.0

@@ -42,6 +42,25 @@ def _worker(rank, world, port, q):
     _allreduce_mean_grads(params, bucket_bytes=4096)               # several buckets
     ok = all(torch.allclose(p.grad, e, atol=1e-6) for p, e in zip(params, expected))
     ok = ok and params[-1].grad is None
+    # experimental overlapped exchange: every gradient is all-reduced by a hook as soon as autograd
+    # has accumulated it; finish() turns the sums into means -> same result as above
+    from histogan_b200.trainer import _GradOverlap
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    for q_ in net.parameters():
+        dist.broadcast(q_.data, src=0)
+    xs = [torch.randn(4, 6, generator=torch.Generator().manual_seed(7 + r)) for r in range(world)]
+    want = [torch.zeros_like(q_) for q_ in net.parameters()]
+    for r in range(world):
+        net.zero_grad()
+        net(xs[r]).pow(2).sum().backward()
+        for acc, q_ in zip(want, net.parameters()):
+            acc += q_.grad / world
+    net.zero_grad()
+    with _GradOverlap(net.parameters(), force=True) as ov:
+        net(xs[rank]).pow(2).sum().backward()
+    ov.finish()
+    ok = ok and ov.enabled and all(torch.allclose(q_.grad, wnt, atol=1e-6)
+                                   for q_, wnt in zip(net.parameters(), want))
     # NaN flag agreement (Trainer.train): MAX-reduce of a per-rank flag
     f = torch.tensor([1.0 if rank == 1 else 0.0])
     dist.all_reduce(f, op=dist.ReduceOp.MAX)
