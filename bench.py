@@ -49,6 +49,14 @@ H_BINS = 64
 ALPHA = 2.0
 L2_FLUSH_BYTES = 256 << 20
 FIRST_STEP = 2501       # past the reference's "evaluate every 100 steps < 2500" window
+PL_STEP = 2528          # a multiple of 32: gradient penalty AND path-length regulariser
+
+
+def window_start(steps):
+    """first trainer.steps value of the timed window: centred on PL_STEP so that any K >= 2 holds
+    one path-length step and every 4th step a gradient penalty (K = 32 is exactly the steady-state
+    mix; shorter windows over-weight the PL step, i.e. are conservative)"""
+    return max(FIRST_STEP, PL_STEP - steps // 2)
 
 
 def load_peaks():
@@ -382,7 +390,8 @@ def run_train(args):
 
     def timed(loader, steps, warmup):
         tr.loader = loader
-        tr.steps = FIRST_STEP - warmup
+        first = window_start(steps)
+        tr.steps = first - warmup
         for _ in range(warmup):
             tr.train(alpha=ALPHA)
         dv.barrier()
@@ -393,12 +402,32 @@ def run_train(args):
             tr.train(alpha=ALPHA)
         e.record()
         dv.barrier()
+        assert tr.steps == first + steps
         return (dv.max_over_ranks(s.elapsed_time(e) * 1e-3),
                 lib.hg_launch_count() + tr.graph_replayed_launches - n0)
 
-    # allocator / one-time kernel-attribute warm-up beyond the requested W (not timed)
-    timed(DeviceLoader(dv.rank, dv.dev), 2, 2)
+    def step_kind_ms(first, n, stride):
+        """median device time of `n` single steps starting at trainer.steps = first, first+stride.."""
+        ts = []
+        for i in range(n):
+            tr.steps = first + i * stride
+            dv.barrier()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(); tr.train(alpha=ALPHA); e.record()
+            dv.barrier()
+            ts.append(dv.max_over_ranks(s.elapsed_time(e) * 1e-3))
+        return round(sorted(ts)[len(ts) // 2] * 1e3, 3)
+
+    # allocator / one-time kernel-attribute warm-up and capture of every graph variant (plain,
+    # gradient-penalty, path-length) beyond the requested W (not timed)
+    tr.loader = DeviceLoader(dv.rank, dv.dev)
+    for st in (PL_STEP, PL_STEP + 1, PL_STEP + 2, PL_STEP + 4):
+        tr.steps = st
+        tr.train(alpha=ALPHA)
     t_dev, launches = timed(DeviceLoader(dv.rank, dv.dev), args.steps, args.warmup)
+    step_ms = {"plain": step_kind_ms(PL_STEP + 1, 5, 4), "gp": step_kind_ms(PL_STEP + 4, 3, 8),
+               "gp+pl": step_kind_ms(PL_STEP, 3, 32)}
+    step_ms["steady_state_32"] = round((24 * step_ms["plain"] + 7 * step_ms["gp"] + step_ms["gp+pl"]) / 32, 3)
     host = HostLoader(dv.rank)
     t_e2e, _ = timed(host, args.steps, 1)
     mem_gb = torch.cuda.max_memory_allocated() / 2 ** 30
@@ -429,7 +458,13 @@ def run_train(args):
                        "global_batch": B_PER_GPU * dv.world,
                        "parallelism": f"dp{dv.world}" + (" + NCCL grad all-reduce" if dv.world > 1 else ""),
                        "l2_flush": "not needed: the step's working set (GBs of activations) >> 126 MB L2",
-                       "timed_steps": f"trainer.steps {FIRST_STEP}..{FIRST_STEP + args.steps - 1}",
+                       "timed_steps": f"trainer.steps {window_start(args.steps)}.."
+                                      f"{window_start(args.steps) + args.steps - 1}: "
+                                      f"{sum(1 for k in range(window_start(args.steps), window_start(args.steps) + args.steps) if k % 4 == 0)} "
+                                      f"gradient-penalty and "
+                                      f"{sum(1 for k in range(window_start(args.steps), window_start(args.steps) + args.steps) if k % 32 == 0)} "
+                                      f"path-length step(s) inside the window",
+                       "step_ms": step_ms,
                        "rng": "device-side latent / noise generation (fast_rng=True)",
                        "cuda_graphs": bool(tr_graphs),
                        "peak_mem_gib": round(mem_gb, 2), "final_losses": losses},
@@ -666,60 +701,84 @@ def cpu_baseline_hist(sample_images=2, reps=2):
                       f"after 1 warm-up"}
 
 
-def cpu_train_step(sd_g, sd_d, sd_s, sd_h, B):
-    """one HistoGAN step (D phase + G phase with histogram loss; no GP/PL, no optimiser
-    update) on the CPU with the oracle's reference-style arithmetic."""
+class CpuTrainer:
+    """the reference's train step on the CPU (oracle/train_oracle.py: the restatement pinned
+    against the unmodified reference Trainer.train by tests/test_train_oracle.py): D phase with the
+    gradient penalty every 4th step, G phase with the histogram loss and the path-length
+    regulariser every 32nd step, DiffGrad updates -- the same loss terms and schedule as the GPU
+    arm, on a bounded sample of `B` images per step."""
+
+    def __init__(self, B=1):
+        from histogan_b200.gan import Discriminator, Generator, HistVectorizer, StyleVectorizer
+        from oracle import gan_oracle as go
+
+        def sd_of(m, seed):
+            shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+            return {k: v.requires_grad_(True) for k, v in go.seeded_state_dict(shapes, seed).items()}
+
+        with torch.device("meta"):
+            mods = (Generator(S, 512, CAPACITY), Discriminator(S, CAPACITY), StyleVectorizer(512, 8),
+                    HistVectorizer(H_BINS, 512, 8))
+        self.sd_g, self.sd_d, self.sd_s, self.sd_h = [sd_of(m, i + 1) for i, m in enumerate(mods)]
+        self.B = B
+        _, self.t = make_inputs(0, B=B)
+        self.x = torch.rand(B, 3, S, S)
+        self.opt_d, self.opt_g, self.pl_mean = {}, {}, 0.0
+        self.steps = 0
+
+    def step(self):
+        from oracle import train_oracle as to
+        k = self.steps
+        dr = to.draw_step_inputs(self.B, 5, 512, S, path_penalty=k % 32 == 0)
+        d = to.d_phase(self.sd_g, self.sd_d, self.sd_s, self.sd_h, self.x, self.t, dr["d_style"],
+                       dr["d_noise"], S, apply_gp=k % 4 == 0)
+        names = list(self.sd_d)
+        to.diffgrad_step_tensors([self.sd_d[n] for n in names], [d["grads"][n] for n in names], self.opt_d)
+        g = to.g_phase(self.sd_g, self.sd_d, self.sd_s, self.sd_h, self.t, dr["g_style"], dr["g_noise"], S,
+                       ALPHA, hist_kw=dict(h=H_BINS, insz=150), pl_noise=dr["pl_noise"], pl_mean=self.pl_mean)
+        named = [("G." + n, v) for n, v in self.sd_g.items()] + [("S." + n, v) for n, v in self.sd_s.items()] + \
+                [("H." + n, v) for n, v in self.sd_h.items()]
+        to.diffgrad_step_tensors([v for _, v in named], [g["grads"][n] for n, _ in named], self.opt_g)
+        if g["avg_pl"] is not None:
+            self.pl_mean = 0.99 * self.pl_mean + 0.01 * g["avg_pl"]
+        self.steps += 1
+
+
+def cpu_train_threads(tr):
+    """thread count for the CPU arm, calibrated on the discriminator forward+backward of the
+    sample (torch's intra-op pool oversubscribes on many-core hosts)"""
     from oracle import gan_oracle as go
-    from oracle import hist_oracle as ho
-    _, t = make_inputs(0, B=B)
-    x = torch.rand(B, 3, S, S)
-    z = torch.randn(B, 512)
-    nz = torch.rand(B, S, S, 1)
 
-    def gen():
-        w = go.mlp(sd_s, "net", 8, z).unsqueeze(1).expand(-1, 5, -1)
-        hw = go.mlp(sd_h, "fcs", 8, t.reshape(B, -1)).unsqueeze(1).expand(-1, 2, -1)
-        return go.generator(sd_g, w, hw, nz, S)
-
-    with torch.no_grad():
-        fake = gen()
-    d_loss = (F.relu(1 + go.discriminator(sd_d, x, S)) + F.relu(1 - go.discriminator(sd_d, fake, S))).mean()
-    torch.autograd.grad(d_loss, list(sd_d.values()))
-    fake = gen()
-    hist = ho.rgb_uv_hist(F.relu(fake), h=H_BINS, insz=150)
-    g_loss = go.discriminator(sd_d, fake, S).mean() + ho.hellinger_loss(t, hist, ALPHA)
-    torch.autograd.grad(g_loss, list(sd_g.values()) + list(sd_s.values()) + list(sd_h.values()))
+    def probe():
+        out = go.discriminator(tr.sd_d, tr.x, S)
+        torch.autograd.grad(out.sum(), list(tr.sd_d.values()), allow_unused=True)
+    return pick_cpu_threads(probe)
 
 
-def make_cpu_train_step():
-    """closure running one CPU train step at B=1 with seeded weights (oracle arithmetic)"""
-    from histogan_b200.gan import Discriminator, Generator, HistVectorizer, StyleVectorizer
-    from oracle import gan_oracle as go
-
-    def sd_of(m, seed):
-        shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
-        return {k: v.requires_grad_(True) for k, v in go.seeded_state_dict(shapes, seed).items()}
-
-    with torch.device("meta"):
-        mods = (Generator(S, 512, CAPACITY), Discriminator(S, CAPACITY), StyleVectorizer(512, 8),
-                HistVectorizer(H_BINS, 512, 8))
-    sds = [sd_of(m, i + 1) for i, m in enumerate(mods)]
-    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    torch.set_num_threads(min(avail, 32))
-    return lambda: cpu_train_step(*sds, 1)
-
-
-def cpu_baseline_train():
-    """the reference's train-step algorithm (torch-CPU restatement, per-sample grouped convs)
-    on a bounded sample: ONE image instead of the 32-image batch, one step."""
-    step = make_cpu_train_step()
+def run_cpu_train(steps, warmup):
+    """(images/s, threads, description) of the CPU arm over `steps` timed steps"""
+    tr = CpuTrainer(1)
+    threads = cpu_train_threads(tr)
+    tr.steps = window_start(steps) - warmup
+    for _ in range(warmup):
+        tr.step()
     t0 = time.perf_counter()
-    step()
+    for _ in range(steps):
+        tr.step()
     dt = time.perf_counter() - t0
-    return {"value": round(1.0 / dt, 4), "unit": "images/s", "cores": torch.get_num_threads(),
-            "kind": "port",
-            "what": "HistoGAN train step (D + G phase with histogram loss; no GP/PL/optimiser update)",
-            "sample": "1 image (of the 32-image batch) for 1 step, 256x256, capacity 16"}
+    first = window_start(steps)
+    kinds = [("gp+pl" if k % 32 == 0 else "gp" if k % 4 == 0 else "plain") for k in range(first, first + steps)]
+    return steps * tr.B / dt, threads, dt / steps, kinds
+
+
+def cpu_baseline_train(steps=3, warmup=1):
+    val, threads, _, kinds = run_cpu_train(steps, warmup)
+    return {"value": round(val, 4), "unit": "images/s", "cores": threads, "kind": "port",
+            "what": "HistoGAN train step, same loss terms as the GPU arm (D: hinge + gradient penalty; G: "
+                    "adversarial + histogram loss + path-length regulariser; DiffGrad updates), reference "
+                    "arithmetic (per-sample weights + grouped convs, float64 soft-binning)",
+            "sample": f"1 image (of the 32-image batch) per step, {steps} steps ({', '.join(kinds)}) after "
+                      f"{warmup} warm-up, 256x256, capacity 16"}
 
 
 def run_reference(args):
@@ -738,10 +797,25 @@ def run_reference(args):
              "CPU restatement of the reference")
         warm = 0
     else:
-        step, sample, what = make_cpu_train_step(), 1, \
-            ("HistoGAN train step (D + G phase with histogram loss; no GP/PL/optimiser), 256x256, "
-             "capacity 16; CPU restatement with per-sample grouped convs as the reference")
-        warm = 0
+        steps, warm = max(3, min(args.steps, 4)), max(1, min(args.warmup, 1))
+        val, threads, per_step, kinds = run_cpu_train(steps, warm)
+        val = round(val, 4)
+        emit({
+            "impl": "reference", "metric": "training images/sec", "value": val, "unit": "images/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": round(per_step * 1e3, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (f64 soft-binning, as the reference)", "data": "synthetic",
+            "config": {"workload": "HistoGAN Trainer.train step on the host CPU: same loss terms and schedule "
+                                   "as the GPU arm (gradient penalty every 4th, path-length every 32nd step, "
+                                   "DiffGrad), 256x256, network_capacity=16; oracle/train_oracle.py (pinned "
+                                   "against the unmodified reference Trainer.train)",
+                       "global_batch": 1, "timed_steps": kinds},
+            "cpu_baseline": {"value": val, "unit": "images/s", "cores": threads, "kind": "port",
+                             "sample": f"1 image per step (bounded sample of the 32-image batch), {steps} "
+                                       f"steps after {warm} warm-up"},
+            "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        })
+        return
     steps = max(1, min(args.steps, 3))
     for _ in range(warm):
         step()
@@ -761,6 +835,130 @@ def run_reference(args):
                                                    f"32-image batch), {steps} step(s)"},
         "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    emit(out)
+
+
+# ------------------------------------------- reference's own eager GPU path --
+
+def _import_reference_gpu():
+    """the UNMODIFIED reference modules from baseline/_ref (staged by oracle/make_baseline_ref.py),
+    with the three un-vendored packages stubbed; DiffGrad = a pure-torch restatement (no kernel of
+    this repo is on that path)."""
+    import types
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "histoGAN", "histoGAN.py")):
+        return None
+
+    class TorchDiffGrad(torch.optim.Optimizer):
+        def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+            super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+
+        @torch.no_grad()
+        def step(self):
+            import math
+            for gr in self.param_groups:
+                b1, b2 = gr["betas"]
+                for p in gr["params"]:
+                    if p.grad is None:
+                        continue
+                    st = self.state[p]
+                    if not st:
+                        st["step"] = 0
+                        st["m"], st["v"], st["g"] = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+                    st["step"] += 1
+                    g = p.grad
+                    st["m"].mul_(b1).add_(g, alpha=1 - b1)
+                    st["v"].mul_(b2).addcmul_(g, g, value=1 - b2)
+                    xi = torch.sigmoid((st["g"] - g).abs())
+                    st["g"] = g.clone()
+                    ss = gr["lr"] * math.sqrt(1 - b2 ** st["step"]) / (1 - b1 ** st["step"])
+                    p.addcdiv_(st["m"] * xi, st["v"].sqrt().add_(gr["eps"]), value=-ss)
+
+    class _Missing:
+        def __init__(self, *a, **k):
+            raise RuntimeError("stubbed third-party class")
+
+    for name, attrs in (("torch_optimizer", {"DiffGrad": TorchDiffGrad}),
+                        ("vector_quantize_pytorch", {"VectorQuantize": _Missing}),
+                        ("linear_attention_transformer", {"ImageLinearAttention": _Missing})):
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+    # `utils`, `histoGAN`, `histogram_classes` must resolve to the reference's packages
+    sys.path.insert(0, ref)
+    import importlib
+    return importlib.import_module("histoGAN.histoGAN"), importlib.import_module("histogram_classes.RGBuvHistBlock")
+
+
+def run_reference_gpu(args):
+    """CONTEXT arm (not the driver's `--impl reference`): the reference's own eager-PyTorch GPU path
+    on the same B200 -- RGBuvHistBlock(device='cuda') at C2 and Trainer.train at C3."""
+    mods = _import_reference_gpu()
+    if mods is None:
+        emit({"impl": "reference-gpu", "unavailable": "baseline/_ref not staged (python -m oracle.make_baseline_ref)"})
+        return
+    gm, hm = mods
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    out = {"impl": "reference-gpu", "n_gpus": 1, "data": "synthetic",
+           "note": "unmodified reference code (baseline/_ref), eager PyTorch + cuDNN/cuBLAS on the same GPU; "
+                   "torch_optimizer.DiffGrad replaced by a pure-torch restatement"}
+    # ---- C2: histogram block fwd + Hellinger + bwd, 32 x 3 x 256 x 256, insz 256 and 150
+    x, t = make_inputs(0, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    for insz in (256, 150):
+        blk = hm.RGBuvHistBlock(h=H_BINS, insz=insz, device="cuda")
+
+        def step():
+            xg = x.detach().requires_grad_(True)
+            hist = blk(F.relu(xg))
+            loss = ALPHA * (1 / 2 ** 0.5) * torch.sqrt(torch.sum((torch.sqrt(t) - torch.sqrt(hist)) ** 2)) / t.shape[0]
+            loss.backward()
+        dt = time_call(step, flush, reps=5)
+        out[f"hist_insz{insz}"] = {"ms_per_step": round(dt * 1e3, 3), "images_per_s": round(B_PER_GPU / dt, 2),
+                                   "us_per_image": round(dt / B_PER_GPU * 1e6, 2)}
+    del x, t, flush
+    torch.cuda.empty_cache()
+    # ---- C3: Trainer.train, 256^2, capacity 16, batch 32 (smaller if it does not fit)
+    out_dir = os.path.join(ROOT, "gpurun_out", "bench_refgpu")
+    for B in (32, 16, 8):
+        try:
+            torch.manual_seed(1234)
+            tr = gm.Trainer("ref", os.path.join(out_dir, "results"), os.path.join(out_dir, "models"), image_size=S,
+                            network_capacity=CAPACITY, batch_size=B, gradient_accumulate_every=1, hist_insz=150,
+                            hist_resizing="interpolation", save_every=10 ** 9)
+            xb = torch.rand(B, 3, S, S, device=dev)
+            _, tb = make_inputs(0, B=B, device=dev)
+            batch = {"images": xb, "histograms": tb}
+            tr.loader = iter(lambda: batch, None)
+            tr.loader_evaluate = iter(lambda: {"histograms": tb[:4]}, None)
+            steps = max(3, min(args.steps, 8))
+            first = window_start(steps)
+            tr.steps = first - 2
+            for _ in range(2):
+                tr.train(alpha=ALPHA)
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(steps):
+                tr.train(alpha=ALPHA)
+            e.record()
+            torch.cuda.synchronize()
+            dt = s.elapsed_time(e) * 1e-3
+            out.update({"metric": "training images/sec", "value": round(B * steps / dt, 2), "unit": "images/s",
+                        "steps": steps, "warmup": 2, "ms_per_step": round(dt / steps * 1e3, 2),
+                        "higher_is_better": True, "dtype": "fp32 (cuDNN/cuBLAS defaults of torch 2.11)",
+                        "config": {"workload": "reference Trainer.train, 256x256, network_capacity=16, "
+                                               f"batch {B}, hist_insz=150 interpolation",
+                                   "global_batch": B,
+                                   "timed_steps": f"trainer.steps {first}..{first + steps - 1}",
+                                   "peak_mem_gib": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1)}})
+            break
+        except torch.cuda.OutOfMemoryError:
+            out.setdefault("oom_at_batch", []).append(B)
+            del tr
+            torch.cuda.empty_cache()
     emit(out)
 
 
@@ -788,14 +986,16 @@ def emit(obj):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
     ap.add_argument("--workload", default="train", choices=["train", "hist", "rehisto"])
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-gpu":
+        run_reference_gpu(args)
     else:
         args.warmup = max(args.warmup, 3)
         {"train": run_train, "hist": run_hist, "rehisto": run_rehisto}[args.workload](args)

@@ -24,6 +24,7 @@
 // scale / bias / noise / LeakyReLU / residual -> NHWC global).  The kernel is
 // persistent (one CTA per SM) with two TMEM accumulator stages.
 #include <cstdlib>
+#include <mutex>
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -478,14 +479,18 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_
 // Per-device scratch for the split-K partial sums: ONE fixed 64 MB allocation made on first use
 // (never during stream capture, never freed or moved -- captured CUDA graphs keep its address).
 // A convolution that would need more, or whose first use falls inside a capture, runs unsplit.
-// Calls are ordered by the stream they are issued on, like every other buffer of this library.
+// CONTRACT: one scratch per device => split-K convolutions of one device must be issued on ONE
+// stream (or on streams ordered against each other); the Trainer does exactly that.  Creation is
+// guarded by a mutex (several host threads / devices).
 constexpr size_t kSplitKWsBytes = 64u << 20;
 
 static float* splitk_workspace(size_t bytes, cudaStream_t stream) {
-  static float* ws[16] = {};
+  static float* ws[64] = {};
+  static std::mutex mu;
   if (bytes > kSplitKWsBytes) return nullptr;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
   if (ws[dev]) return ws[dev];
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
@@ -499,11 +504,11 @@ template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
                        int m_tiles, cudaStream_t stream) {
   using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
+    attr_once.mark();
   }
   const int total = m_tiles * a.n_tiles * (HALO ? 1 : a.ksplit);
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;

@@ -386,11 +386,11 @@ template <int BN, int STAGES, int TAPS = 1>
 static int launch_wgrad(const CUtensorMap& tmdy, const CUtensorMap& tmx, const WgradArgs& a,
                         cudaStream_t stream) {
   using SM = WgradSmem<BN, STAGES, TAPS>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_tf32_kernel<BN, STAGES, TAPS>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
+    attr_once.mark();
   }
   dim3 grid((a.KH * a.KW / TAPS) * a.co_tiles * a.ci_tiles, a.splits);
   conv_wgrad_tf32_kernel<BN, STAGES, TAPS><<<grid, kWgThreads, SM::kTotal, stream>>>(tmdy, tmx, a);
@@ -402,11 +402,11 @@ template <int NC, int STAGES>
 static int launch_wgrad_col(const CUtensorMap& tmdy, const CUtensorMap& tmx, const WgradArgs& a,
                             int co_tiles, cudaStream_t stream) {
   using SM = WgradColSmem<NC, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.need()) {
     HG_CUDA_OK(cudaFuncSetAttribute(conv_wgrad_col_kernel<NC, STAGES>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_set = true;
+    attr_once.mark();
   }
   dim3 grid(co_tiles * a.ci_tiles, a.splits);
   conv_wgrad_col_kernel<NC, STAGES><<<grid, kWgThreads, SM::kTotal, stream>>>(tmdy, tmx, a);

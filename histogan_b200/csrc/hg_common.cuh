@@ -1,6 +1,7 @@
 // hg_common.cuh -- shared host/device helpers for libhistogan_b200.so (sm_100a).
 #pragma once
 
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -46,6 +47,21 @@ struct DeviceInfo {
   bool ok = false;
 };
 const DeviceInfo& device_info();   // for the current device (cached)
+
+// "has this one-time, per-DEVICE setup (cudaFuncSetAttribute: function attributes belong to the
+// current device's context) been done?" -- one atomic bit per device ordinal.  A process that
+// drives several GPUs gets the attribute set on each of them.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  bool need() {                      // true: the caller must do the setup now (idempotent if raced)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bit = 1ull << (dev & 63);
+    return !(done.load(std::memory_order_acquire) & bit);
+  }
+  void mark() { done.fetch_or(bit, std::memory_order_release); }
+  static thread_local unsigned long long bit;
+};
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 

@@ -235,6 +235,9 @@ constexpr int kGBThreads = 64;
 
 __device__ __forceinline__ double kernel_grad_f64(float u, double c, int method, double sigma2,
                                                   double k) {
+  // thresholding: the mask is a comparison -- a constant for autograd (RGBuvHistBlock.py:126-131);
+  // only the intensity weight Iy carries a gradient then
+  if (method == HG_METHOD_THRESHOLDING) return 0.0;
   const double d = (double)u - c;
   const double w = -2.0 * d / sigma2 * k;
   return method == HG_METHOD_INVERSE_QUADRATIC ? w * k : w;
@@ -451,7 +454,10 @@ extern "C" int hg_hist_bwd(const float* x, const hg_hist_params* p, const float*
     return set_error(HG_EINVAL, "null tensor pointer");
   const long long per_img = (long long)g.C * g.H * g.W;
   dim3 egrid((unsigned)((per_img + 255) / 256), g.B);
-  if (g.method == HG_METHOD_THRESHOLDING) {     // comparison op: no gradient
+  // thresholding: the bin masks are comparison results, constants for autograd; what remains is
+  // d hist / d Iy (RGBuvHistBlock.py:105-110,131-132) and the normalisation.  Without
+  // intensity_scale the reference's hist does not require grad at all: zeros.
+  if (g.method == HG_METHOD_THRESHOLDING && !g.intensity) {
     zero_strided_kernel<<<egrid, 256, 0, stream>>>(g, grad_x);
     HG_LAUNCH_OK("zero_strided_kernel");
     return 0;

@@ -9,6 +9,7 @@ namespace hg {
 
 thread_local char g_err[512] = "";
 unsigned long long g_launches = 0;
+thread_local unsigned long long PerDeviceOnce::bit = 1;
 
 const DeviceInfo& device_info() {
   static DeviceInfo infos[64];

@@ -104,6 +104,9 @@ class DiffGrad(Optimizer):
             return arr(*[t.data_ptr() for t in ts])
 
         st = [self.state[p] for p in ps]
+        # the kernel indexes p, g and the three state tensors with ONE linear offset
+        assert all(_same_layout(p, s[k]) for p, s in zip(ps, st)
+                   for k in ('exp_avg', 'exp_avg_sq', 'previous_grad')), "optimizer state layout"
         numel = (C.c_int64 * n)(*[p.numel() for p in ps])
         dev = ps[0].device
         with torch.cuda.device(dev):

@@ -601,6 +601,7 @@ class recoloringTrainer():
 
     def init_GAN(self):
         args, kwargs = self.GAN_params
+        self._graphs, self._static = {}, None       # captured graphs belong to the old GAN
         self.GAN = recoloringGAN(lr=self.lr, image_size=self.image_size,
                                  network_capacity=self.network_capacity, transparent=self.transparent,
                                  fq_layers=self.fq_layers, fq_dict_size=self.fq_dict_size,

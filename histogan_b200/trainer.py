@@ -287,8 +287,9 @@ class Trainer:
         if aug_types is None:
             aug_types = ['translation', 'cutout']
         self.fast_rng = bool(kwargs.pop('fast_rng', False))
-        # cuda_graphs=True: replay each phase (forward + backward) of a regular step as one
-        # CUDA graph (see _train_graphed); steps with the path-length regulariser stay eager
+        # cuda_graphs=True: replay each phase (forward + backward) of a step as one CUDA graph
+        # (see _train_graphed): D with / without gradient penalty, G with / without the
+        # path-length regulariser
         self.cuda_graphs = bool(kwargs.pop('cuda_graphs', False))
         self._graphs = {}
         self._static = None
@@ -342,6 +343,10 @@ class Trainer:
     # ------------------------------------------------------------ plumbing --
     def init_GAN(self):
         args, kwargs = self.GAN_params
+        # captured graphs hold the OLD parameter / gradient tensors: a new GAN (first call, or
+        # load() -> load_config() after a NaN) must be captured afresh
+        self._graphs = {}
+        self._static = None
         self.GAN = HistoGAN(lr=self.lr, image_size=self.image_size,
                             network_capacity=self.network_capacity, transparent=self.transparent,
                             fq_layers=self.fq_layers, fq_dict_size=self.fq_dict_size,
@@ -407,9 +412,11 @@ class Trainer:
         apply_gradient_penalty = self.steps % 4 == 0
         apply_path_penalty = self.steps % 32 == 0
         avg_pl_length = self.pl_mean
-        if self.cuda_graphs and accum == 1 and not apply_path_penalty:
-            total_disc_loss, total_gen_loss, total_hist_loss = self._train_graphed(
-                alpha, apply_gradient_penalty)
+        if self.cuda_graphs and accum == 1:
+            total_disc_loss, total_gen_loss, total_hist_loss, pl = self._train_graphed(
+                alpha, apply_gradient_penalty, apply_path_penalty)
+            if pl is not None:
+                avg_pl_length = pl
             return self._finish_step(total_disc_loss, total_gen_loss, total_hist_loss,
                                      apply_path_penalty, avg_pl_length)
 
@@ -525,15 +532,28 @@ class Trainer:
         m = mask[None, :, None]
         return w1 * m + w2 * (1 - m)
 
+    def _device_draws(self, phase, with_pl=False):
+        """latents / image noise of one captured phase, drawn on the device inside the graph
+        (a replay advances the graph's Philox offset).  Tests pin them via _static['fixed']."""
+        GAN, st = self.GAN, self._static
+        fixed = st.get('fixed')
+        if fixed is not None:
+            return fixed[phase]
+        B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
+        out = {'z1': torch.randn(B, GAN.G.latent_dim, device='cuda'),
+               'z2': torch.randn(B, GAN.G.latent_dim, device='cuda'),
+               'inoise': torch.rand(B, S_, S_, 1, device='cuda')}
+        if with_pl:
+            out['pl_noise'] = torch.randn(B, L, GAN.G.latent_dim, device='cuda')
+        return out
+
     def _phase_d(self, apply_gp):
         GAN, st = self.GAN, self._static
-        B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
         # the backward allocates this graph's own gradient tensors (kept alive by _graphed and
         # re-attached to the parameters after every replay): no zero-fill / accumulate kernels
         GAN.D_opt.zero_grad(set_to_none=True)
-        z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
-        z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
-        inoise = torch.rand(B, S_, S_, 1, device='cuda')
+        dr = self._device_draws('d')
+        z1, z2, inoise = dr['z1'], dr['z2'], dr['inoise']
         with torch.no_grad():
             h_w = GAN.H(st['hists']).unsqueeze(1)
             fake = GAN.G(self._mixed_styles(z1, z2, st['mask']), torch.cat((h_w, h_w), dim=1), inoise)
@@ -551,26 +571,39 @@ class Trainer:
         ov.finish()
         return divergence.detach(), (gp.detach() if gp is not None else None)
 
-    def _phase_g(self, alpha):
+    def _phase_g(self, alpha, apply_pl=False):
+        """G phase (histoGAN.py:934-989).  apply_pl: + the path-length regulariser (:965-975)
+        with `pl_mean` read from a device scalar, so that PL steps are capturable too; the
+        reference's host-side `if not isnan(pl_loss)` becomes a select on the device."""
         GAN, st = self.GAN, self._static
-        B, S_ = self.batch_size, GAN.G.image_size
         GAN.G_opt.zero_grad(set_to_none=True)
-        z1 = torch.randn(B, GAN.G.latent_dim, device='cuda')
-        z2 = torch.randn(B, GAN.G.latent_dim, device='cuda')
-        inoise = torch.rand(B, S_, S_, 1, device='cuda')
-        h_w = GAN.H(st['hists']).unsqueeze(1)
-        fake = GAN.G(self._mixed_styles(z1, z2, st['mask']), torch.cat((h_w, h_w), dim=1), inoise)
+        dr = self._device_draws('g', apply_pl)
+        z1, z2, inoise = dr['z1'], dr['z2'], dr['inoise']
+        hists = st['hists']      # the reference's hist_batch.requires_grad_() (:940) is never used
+        h_w = GAN.H(hists).unsqueeze(1)
+        h_w = torch.cat((h_w, h_w), dim=1)
+        w_styles = self._mixed_styles(z1, z2, st['mask'])
+        fake = GAN.G(w_styles, h_w, inoise)
         set_requires_grad(GAN.D, False)          # D's parameter gradients are dead work here
+        avg_pl = None
         try:
             fake_out, _ = GAN.D(fake)
-            hist_loss = hellinger_loss(st['hists'], self.histBlock(F.relu(fake)), alpha)
+            hist_loss = hellinger_loss(hists, self.histBlock(F.relu(fake)), alpha)
             loss = fake_out.mean()
+            gen_loss = loss + hist_loss
+            if apply_pl:
+                std = 0.1 / (w_styles.std(dim=0, keepdim=True) + EPS)
+                pl_images = GAN.G(w_styles + dr['pl_noise'] / (std + EPS), h_w, inoise)
+                pl_lengths = ((pl_images - fake) ** 2).mean(dim=(1, 2, 3))
+                avg_pl = pl_lengths.detach().mean()
+                pl_loss = ((pl_lengths - st['pl_mean']) ** 2).mean()
+                gen_loss = gen_loss + torch.where(torch.isnan(pl_loss), torch.zeros_like(pl_loss), pl_loss)
             with _GradOverlap([p for grp in GAN.G_opt.param_groups for p in grp['params']]) as ov:
-                (loss + hist_loss).backward()
+                gen_loss.backward()
             ov.finish()
         finally:
             set_requires_grad(GAN.D, True)
-        return loss.detach(), hist_loss.detach()
+        return loss.detach(), hist_loss.detach(), avg_pl
 
     def _graphed(self, key, fn, params):
         """capture `fn` (one phase: zero_grad + forward + backward) once, then replay.
@@ -607,7 +640,7 @@ class Trainer:
         # so hand out copies that live outside the pool.
         return tuple(o.clone() if o is not None else None for o in entry[1])
 
-    def _train_graphed(self, alpha, apply_gp):
+    def _train_graphed(self, alpha, apply_gp, apply_pl=False):
         GAN = self.GAN
         B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
         if self._static is None:
@@ -615,20 +648,31 @@ class Trainer:
                 'images': torch.zeros(B, 3, S_, S_, device='cuda'),
                 'hists': torch.zeros(B, 3, self.hist_bin, self.hist_bin, device='cuda'),
                 'mask': torch.ones(L, device='cuda'),
-                'mask_host': torch.ones(L).pin_memory(),
+                'pl_mean': torch.zeros((), device='cuda'),
+                # one pinned staging buffer per phase: the G-phase mask must not overwrite the
+                # D-phase one while its H2D copy may still be queued
+                'mask_host': [torch.ones(L).pin_memory(), torch.ones(L).pin_memory()],
+                'mask_event': [None, None],
             }
         st = self._static
+        # mixed or not is drawn ONCE per step and reused by the G phase (histoGAN.py:891,936);
+        # each phase draws its own split point, as mixed_list does (:174-176)
+        get_mixed = random() < self.mixed_prob
 
-        def stage(batch, with_images):
-            get_mixed = random() < self.mixed_prob           # same draws as the eager path
+        def stage(batch, phase):
             tt = int(torch.rand(()).numpy() * L) if get_mixed else L
-            st['mask_host'].copy_((torch.arange(L) < tt).float())
-            st['mask'].copy_(st['mask_host'], non_blocking=True)
+            ev = st['mask_event'][phase]
+            if ev is not None:
+                ev.synchronize()             # last step's copy out of this pinned buffer is done
+            st['mask_host'][phase].copy_((torch.arange(L) < tt).float())
+            st['mask'].copy_(st['mask_host'][phase], non_blocking=True)
+            st['mask_event'][phase] = torch.cuda.Event()
+            st['mask_event'][phase].record()
             st['hists'].copy_(batch['histograms'], non_blocking=True)
-            if with_images:
+            if phase == 0:
                 st['images'].copy_(batch['images'], non_blocking=True)
 
-        stage(next(self.loader), True)
+        stage(next(self.loader), 0)
         d_params = list(GAN.D.parameters())
         g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
         overlapped = _GradOverlap([]).enabled       # the collectives then live inside the graphs
@@ -636,8 +680,11 @@ class Trainer:
         if not overlapped:
             _allreduce_mean_grads(d_params)
         GAN.D_opt.step()
-        stage(next(self.loader), False)
-        g_loss, h_loss = self._graphed(('G', float(alpha)), lambda: self._phase_g(alpha), g_params)
+        stage(next(self.loader), 1)
+        if apply_pl:
+            st['pl_mean'].fill_(float(self.pl_mean))
+        g_loss, h_loss, avg_pl = self._graphed(('G', float(alpha), bool(apply_pl)),
+                                               lambda: self._phase_g(alpha, apply_pl), g_params)
         if not overlapped:
             _allreduce_mean_grads(g_params)
         GAN.G_opt.step()
@@ -648,7 +695,8 @@ class Trainer:
         self.d_loss = float(divergence.item())
         self.g_loss = float(g_loss.item())
         self.h_loss = float(h_loss.item())
-        return divergence.clone(), g_loss.clone(), h_loss.clone()
+        return divergence.clone(), g_loss.clone(), h_loss.clone(), \
+            (float(avg_pl.item()) if avg_pl is not None else None)
 
     # ------------------------------------------------------------ evaluate --
     @torch.no_grad()

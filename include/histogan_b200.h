@@ -96,8 +96,10 @@ int hg_hist_fwd(const float* x, const hg_hist_params* p,
 /* Backward: grad_x (same geometry / strides as x, fully written, channels >= 3
  * get zeros) = d<grad_hist, hist>/dx, i.e. what autograd produces for the
  * reference forward given the upstream gradient grad_hist (B, nc, h, h).
- * method == thresholding has no gradient: grad_x is zero-filled (as autograd
- * does for the comparison op, RGBuvHistBlock.py:126-127).                       */
+ * method == thresholding: the bin masks are comparison results (constants for
+ * autograd, RGBuvHistBlock.py:126-131), so the gradient flows only through the
+ * intensity weight Iy and the normalisation; with intensity_scale == 0 the
+ * reference's output does not require grad and grad_x is zero-filled.           */
 int hg_hist_bwd(const float* x, const hg_hist_params* p,
                 const float* hist, const float* hist_sum,
                 const float* grad_hist, float* grad_x,

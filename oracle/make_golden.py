@@ -48,8 +48,9 @@ def run_reference_hist(x, target, alpha, kwargs):
     scale = 1 / np.sqrt(2.0)
     loss = alpha * scale * (torch.sqrt(torch.sum(torch.pow(
         torch.sqrt(target) - torch.sqrt(hist), 2)))) / target.shape[0]
-    differentiable = kwargs.get("method", "inverse-quadratic") != "thresholding"
-    if differentiable:
+    # thresholding: the masks are constants for autograd but Iy (intensity_scale) still
+    # carries a gradient -- ask the reference instead of assuming
+    if hist.requires_grad:
         # (a) the training loss; (b) a linear functional <hist, target> that stays
         # finite where the Hellinger gradient is NaN (RBF underflows to exact zeros)
         (grad,) = torch.autograd.grad(loss, xr, retain_graph=True)
@@ -60,8 +61,10 @@ def run_reference_hist(x, target, alpha, kwargs):
     return hist.detach(), loss.detach(), grad, grad_lin
 
 
-def make_hist_goldens():
+def make_hist_goldens(only=None):
     for name, maker, B, S, Cc, kwargs, alpha in HIST_CASES:
+        if only and name not in only:
+            continue
         x = maker(B, S, seed=0, C=Cc)
         h = kwargs.get("h", 64)
         nc = 1 if kwargs.get("green_only", False) else 3

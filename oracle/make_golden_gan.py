@@ -96,5 +96,78 @@ def main():
     print("discriminator: logits", logits.detach().numpy(), "gp", gp.item())
 
 
+# ---------------------------------------------------------------------------------------
+# The BENCHMARKED shape: image 256, capacity 16 (7 generator blocks 64->2048->...->32, 8
+# discriminator blocks 3->16->...->2048), batch 2.  Large tensors are stored as fingerprints
+# (float64 norm + evenly strided entries, make_golden_step.fingerprint) so the fixture stays
+# ~2 MB: full `rgb`, per-block activation norms / samples, every parameter gradient.
+
+IMAGE_SIZE_L, B_L = 256, 2
+ACT_SAMPLES = 4096
+
+
+def strided(t, n):
+    flat = t.detach().contiguous().reshape(-1)
+    idx = (torch.arange(min(n, flat.numel()), dtype=torch.int64) * flat.numel()) // min(n, flat.numel())
+    return flat[idx].float().numpy()
+
+
+def grad_fingerprints(named_params):
+    from .make_golden_step import fingerprint
+    names, norms, samples = [], [], []
+    for k, p in named_params:
+        n, s = fingerprint(p.grad)
+        names.append(k); norms.append(n); samples.append(s)
+    return json.dumps(names), np.array(norms, dtype=np.float64), np.concatenate(samples)
+
+
+def main_256():
+    assert ref_shim.available()
+    gm = ref_shim.ref_gan_module()
+    torch.set_num_threads(os.cpu_count() or 1)
+    inp = gan_inputs(IMAGE_SIZE_L, B_L, seed=5)
+
+    G = gm.Generator(IMAGE_SIZE_L, LATENT, network_capacity=CAPACITY)
+    shapes = {k: list(v.shape) for k, v in G.state_dict().items()}
+    G.load_state_dict(go.seeded_state_dict(shapes, seed=1))
+    styles = inp["styles"].clone().requires_grad_(True)
+    hists = inp["hists"].clone().requires_grad_(True)
+    acts = []
+    hooks = [blk.register_forward_hook(lambda m, i, o: acts.append(o[0].detach())) for blk in G.blocks]
+    rgb = G(styles, hists, inp["noise"])
+    for h in hooks:
+        h.remove()
+    loss = (rgb * inp["w_rgb"]).sum()
+    loss.backward()
+    names, norms, samples = grad_fingerprints(G.named_parameters())
+    out = dict(shapes=json.dumps(shapes), rgb=rgb.detach().numpy(),
+               act_norms=np.array([a.double().norm().item() for a in acts]),
+               act_samples=np.stack([strided(a, ACT_SAMPLES) for a in acts]),
+               loss=np.float64(loss.item()), g_styles=styles.grad.numpy(), g_hists=hists.grad.numpy(),
+               grad_names=names, grad_norms=norms, grad_samples=samples)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "gan_generator_256.npz"), **out)
+    print("generator 256: rgb", tuple(rgb.shape), "loss", loss.item(), "act norms", out["act_norms"])
+    del G, acts, rgb
+
+    D = gm.Discriminator(IMAGE_SIZE_L, network_capacity=CAPACITY)
+    dshapes = {k: list(v.shape) for k, v in D.state_dict().items()}
+    D.load_state_dict(go.seeded_state_dict(dshapes, seed=2))
+    images = inp["images"].clone().requires_grad_(True)
+    logits, q = D(images)
+    gp = gradient_penalty(images, logits)
+    (logits.sum() + gp * GP_WEIGHT_IN_TEST).backward()
+    names, norms, samples = grad_fingerprints(D.named_parameters())
+    dout = dict(shapes=json.dumps(dshapes), logits=logits.detach().numpy(), gp=np.float64(gp.item()),
+                g_images_norm=np.float64(images.grad.double().norm().item()),
+                g_images_samples=strided(images.grad, 65536),
+                grad_names=names, grad_norms=norms, grad_samples=samples)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "gan_discriminator_256.npz"), **dout)
+    print("discriminator 256: logits", logits.detach().numpy(), "gp", gp.item())
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if len(sys.argv) > 1 and sys.argv[1] == "256":
+        main_256()
+    else:
+        main()

@@ -97,3 +97,64 @@ def max_rel_between(a: dict, b: dict):
             worst, key = r, k
     print("per-tensor relative difference:", {k: f"{v:.1e}" for k, v in sorted(table.items(), key=lambda kv: -kv[1])})
     return worst, key
+
+
+# ------------------------------------------------------- the benchmarked shape (256^2) ----
+
+def _fingerprint_table(named_params, g):
+    from tests import step_checks as sc
+    names = json.loads(str(g["grad_names"]))
+    params = dict(named_params)
+    return sc.compare_grads({k: params[k].grad for k in names}, names, g["grad_norms"], g["grad_samples"])
+
+
+def generator_errors_256(device):
+    """Generator at image 256 / capacity 16 (7 blocks, 64 -> 2048 -> ... -> 32 channels: the
+    resident-filter, column-halo wgrad and split-K paths) against the reference golden."""
+    from histogan_b200.gan import Generator
+    from tests import step_checks as sc
+    g = load("gan_generator_256.npz")
+    G = Generator(mg.IMAGE_SIZE_L, mg.LATENT, network_capacity=mg.CAPACITY)
+    shapes = json.loads(str(g["shapes"]))
+    assert {k: list(v.shape) for k, v in G.state_dict().items()} == shapes
+    G.load_state_dict(go.seeded_state_dict(shapes, seed=1))
+    G.to(device)
+    inp = {k: v.to(device) for k, v in mg.gan_inputs(mg.IMAGE_SIZE_L, mg.B_L, seed=5).items()}
+    styles = inp["styles"].clone().requires_grad_(True)
+    hists = inp["hists"].clone().requires_grad_(True)
+    acts = []
+    hooks = [b.register_forward_hook(lambda m, i, o: acts.append(o[0].detach())) for b in G.blocks]
+    rgb = G(styles, hists, inp["noise"])
+    for h in hooks:
+        h.remove()
+    e = {"rgb": rel(rgb, g["rgb"]),
+         "rgb_max_abs": float((rgb.detach().cpu() - torch.from_numpy(g["rgb"])).abs().max() /
+                              np.abs(g["rgb"]).max()),
+         "act_norms": float(np.max(np.abs(np.array([a.double().norm().item() for a in acts]) / g["act_norms"] - 1))),
+         "act_samples": max(rel(mg.strided(a.cpu(), mg.ACT_SAMPLES), s) for a, s in zip(acts, g["act_samples"]))}
+    loss = (rgb * inp["w_rgb"]).sum()
+    e["loss"] = abs(loss.item() - float(g["loss"])) / abs(float(g["loss"]))
+    loss.backward()
+    e["g_styles"] = rel(styles.grad, g["g_styles"])
+    e["g_hists"] = rel(hists.grad, g["g_hists"])
+    return e, _fingerprint_table(G.named_parameters(), g)
+
+
+def discriminator_errors_256(device):
+    from histogan_b200.gan import Discriminator
+    from histogan_b200.trainer import gradient_penalty
+    g = load("gan_discriminator_256.npz")
+    D = Discriminator(mg.IMAGE_SIZE_L, network_capacity=mg.CAPACITY)
+    shapes = json.loads(str(g["shapes"]))
+    assert {k: list(v.shape) for k, v in D.state_dict().items()} == shapes
+    D.load_state_dict(go.seeded_state_dict(shapes, seed=2))
+    D.to(device)
+    images = mg.gan_inputs(mg.IMAGE_SIZE_L, mg.B_L, seed=5)["images"].to(device).requires_grad_(True)
+    logits, _ = D(images)
+    e = {"logits": rel(logits, g["logits"])}
+    gp = gradient_penalty(images, logits)
+    e["gp"] = abs(gp.item() - float(g["gp"])) / float(g["gp"])
+    (logits.sum() + gp * mg.GP_WEIGHT_IN_TEST).backward()
+    e["g_images_norm"] = abs(images.grad.double().norm().item() - float(g["g_images_norm"])) / float(g["g_images_norm"])
+    e["g_images_samples"] = rel(mg.strided(images.grad.cpu(), 65536), g["g_images_samples"])
+    return e, _fingerprint_table(D.named_parameters(), g)

@@ -60,6 +60,21 @@ def device_log(v):
     return DeviceLog.apply(v)
 
 
+RECORD_PATH = os.path.join(os.path.dirname(GOLDEN_DIR), os.pardir, "gpurun_out", "parity_records.jsonl")
+
+
+def record(what, values):
+    """append the MEASURED errors of one parity check to gpurun_out/parity_records.jsonl (travels
+    back from the GPU box; scripts/parity_table.py turns it into profiles/rNN_parity_table.md)."""
+    try:
+        os.makedirs(os.path.dirname(RECORD_PATH), exist_ok=True)
+        clean = {k: (float(v) if isinstance(v, (int, float, np.floating)) else str(v)) for k, v in values.items()}
+        with open(RECORD_PATH, "a") as f:
+            f.write(json.dumps({"check": what, **clean}) + "\n")
+    except OSError:
+        pass
+
+
 def fro_rel(a, ref):
     a = a.detach().double().cpu()
     ref = ref.detach().double().cpu()
@@ -68,6 +83,7 @@ def fro_rel(a, ref):
 
 def assert_hist_strict(a, ref, what=""):
     r = rel_err(a, ref)
+    record("hist_strict:" + what, dict(max=r.max().item(), fro=fro_rel(a, ref)))
     assert r.max().item() <= STRICT_MAX_REL, f"{what}: strict max rel {r.max().item():.3e}"
 
 
@@ -75,6 +91,7 @@ def assert_hist_e2e(a, ref, what="", atol_frac=1e-9):
     r = rel_err(a, ref, atol_frac)
     fr = fro_rel(a, ref)
     p999 = torch.quantile(r.flatten()[:: max(1, r.numel() // 1_000_000)], 0.999).item()
+    record("hist_e2e:" + what, dict(fro=fr, p999=p999, max=r.max().item()))
     assert fr <= E2E_FRO_REL, f"{what}: Frobenius rel {fr:.3e}"
     assert p999 <= E2E_P999_REL, f"{what}: 99.9th percentile rel {p999:.3e}"
     assert r.max().item() <= E2E_MAX_REL, f"{what}: max rel {r.max().item():.3e}"
@@ -83,6 +100,7 @@ def assert_hist_e2e(a, ref, what="", atol_frac=1e-9):
 
 def assert_loss(a, ref, what=""):
     a = float(a); ref = float(ref)
+    record("loss:" + what, dict(rel=abs(a - ref) / max(abs(ref), 1e-300)))
     assert abs(a - ref) <= LOSS_REL * abs(ref), f"{what}: loss {a!r} vs {ref!r}"
 
 

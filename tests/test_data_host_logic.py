@@ -39,3 +39,49 @@ def test_folder_batches(tmp_path):
     singles = [ho.rgb_uv_hist(train._load(p).unsqueeze(0), h=64, insz=150, resizing="sampling")[0]
                for p in train.paths]
     assert all(any(torch.allclose(h, s1, atol=1e-7) for s1 in singles) for h in e["histograms"])
+
+
+def _make_images(tmp_path, sizes):
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    for i, (w, h) in enumerate(sizes):
+        Image.fromarray(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)).save(tmp_path / f"im{i:02d}.png")
+
+
+def test_epoch_without_replacement_and_batched_calls(tmp_path):
+    """reference loader semantics (shuffle=True, drop_last=True, histoGAN.py:840-845): every image
+    once per epoch; the 2 x batch histogram sources are evaluated with ONE block call per
+    distinct image size."""
+    _make_images(tmp_path, [(40, 40)] * 4 + [(52, 36)] * 2)
+    calls = []
+
+    class Blk(_OracleBlock):
+        def __call__(self, x):
+            calls.append(tuple(x.shape))
+            return super().__call__(x)
+
+    class Tr(_FakeTrainer):
+        histBlock = Blk()
+
+    train, _ = data.make_loaders(Tr(), str(tmp_path))
+    seen = []
+    orig = train._next_indices
+    train._next_indices = lambda: (seen.append(orig()) or seen[-1])
+    next(train); n_calls = len(calls); next(train)
+    assert sorted(int(i) for b in seen for i in b) == list(range(6))        # one epoch = every image once
+    assert n_calls <= 2 and all(c[0] >= 1 for c in calls)                   # <= one call per distinct size
+    assert sum(c[0] for c in calls[:n_calls]) == 6                          # 2 sources x batch of 3
+
+
+def test_ranks_see_disjoint_shards(tmp_path, monkeypatch):
+    """every rank used to draw the same indices; now the epoch permutation is shared
+    and sharded, the histogram sources are per-rank."""
+    _make_images(tmp_path, [(32, 32)] * 12)
+    loaders = []
+    for r in (0, 1):
+        monkeypatch.setattr(data, "_rank_world", lambda r=r: (r, 2))
+        loaders.append(data.make_loaders(_FakeTrainer(), str(tmp_path))[0])
+    a = [int(i) for _ in range(2) for i in loaders[0]._next_indices()]
+    b = [int(i) for _ in range(2) for i in loaders[1]._next_indices()]
+    assert not set(a) & set(b) and sorted(a + b) == list(range(12))
+    assert not np.array_equal(loaders[0].rng.integers(0, 12, 8), loaders[1].rng.integers(0, 12, 8))

@@ -58,6 +58,8 @@ def test_generator(use_fused, cuda_device, monkeypatch):
     with emulated_conv(round_operands=True):
         e_emu, out_emu = gan_checks.generator_errors("cpu")
     print("generator vs golden (GPU):", {k: f"{v:.2e}" for k, v in e_gpu.items()})
+    from tests import parity
+    parity.record(f"generator_32[{'fused' if use_fused else 'composed'}]", e_gpu)
     print("generator vs golden (CPU TF32 emulation):", {k: f"{v:.2e}" for k, v in e_emu.items()})
     worst, key = gan_checks.max_rel_between(out_gpu, out_emu)
     print("generator GPU vs emulation: worst", f"{worst:.2e}", key)
@@ -74,9 +76,41 @@ def test_discriminator_and_gradient_penalty(use_fused, cuda_device, monkeypatch)
     with emulated_conv(round_operands=True):
         e_emu, out_emu = gan_checks.discriminator_errors("cpu")
     print("discriminator vs golden (GPU):", {k: f"{v:.2e}" for k, v in e_gpu.items()})
+    from tests import parity
+    parity.record(f"discriminator_32[{'fused' if use_fused else 'composed'}]", e_gpu)
     print("discriminator vs golden (CPU TF32 emulation):", {k: f"{v:.2e}" for k, v in e_emu.items()})
     worst, key = gan_checks.max_rel_between(out_gpu, out_emu)
     print("discriminator GPU vs emulation: worst", f"{worst:.2e}", key)
     assert e_gpu["logits"] < ACT_TOL
     assert gan_checks.rel(out_gpu["logits"], out_emu["logits"]) < VS_EMULATION_ACT_TOL
     _within_noise_floor(e_gpu, e_emu)
+
+
+# ---- parity at the BENCHMARKED shape: image 256, capacity 16 (reference goldens, batch 2) ----
+GRAD_NORM_TOL_256, GRAD_COS_256 = 3e-2, 0.999
+
+
+def _report(tag, e, table):
+    from tests import step_checks as sc
+    print(f"{tag} vs reference golden:", {k: f"{v:.2e}" for k, v in e.items()})
+    print(f"{tag} parameter gradients worst:", sc.worst(table))
+    from tests import parity
+    parity.record(tag, {**e, **{"grad_" + k: v[1] for k, v in sc.worst(table).items()}})
+
+
+def test_generator_256_matches_reference(cuda_device):
+    e, table = gan_checks.generator_errors_256("cuda")
+    _report("generator_256", e, table)
+    assert e["rgb"] < ACT_TOL and e["act_norms"] < ACT_TOL and e["act_samples"] < ACT_TOL
+    assert e["loss"] < 5e-3 and e["g_styles"] < 3e-2 and e["g_hists"] < 3e-2
+    bad = {k: v for k, v in table.items() if v[0] > GRAD_NORM_TOL_256 or v[1] < GRAD_COS_256}
+    assert not bad, bad
+
+
+def test_discriminator_256_matches_reference(cuda_device):
+    e, table = gan_checks.discriminator_errors_256("cuda")
+    _report("discriminator_256", e, table)
+    assert e["logits"] < ACT_TOL and e["gp"] < 5e-3
+    assert e["g_images_norm"] < 1e-2 and e["g_images_samples"] < 3e-2
+    bad = {k: v for k, v in table.items() if v[0] > GRAD_NORM_TOL_256 or v[1] < GRAD_COS_256}
+    assert not bad, bad

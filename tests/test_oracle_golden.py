@@ -11,9 +11,7 @@ from tests import parity
 @pytest.mark.parametrize("name", parity.golden_names("hist_"))
 def test_hist_oracle_matches_golden(name):
     g = parity.load_golden(name)
-    hist, loss, grad = ho.hist_loss_and_grad(g["x"], g["target"], g["alpha"], **g["kwargs"]) \
-        if g["kwargs"].get("method") != "thresholding" else \
-        (ho.rgb_uv_hist(torch.relu(g["x"]), **g["kwargs"]), None, None)
+    hist, loss, grad = ho.hist_loss_and_grad(g["x"], g["target"], g["alpha"], **g["kwargs"])
     # same ops, same machine class: identical up to a last-bit reduction-order effect
     assert parity.rel_err(hist, g["hist"]).max().item() < 2e-6
     assert parity.fro_rel(hist, g["hist"]) < 1e-7

@@ -110,6 +110,25 @@ def test_fused_diffgrad_matches_foreach(cuda_device):
     assert pa[0]._version > v0
 
 
+def test_fused_diffgrad_matches_scalar_oracle(cuda_device):
+    """hg_diffgrad_step against the from-the-paper scalar restatement kept in oracle/
+    (train_oracle.diffgrad_step: python floats, one element at a time) -- not against optim.py."""
+    from histogan_b200.optim import DiffGrad
+    from oracle import train_oracle as to
+    torch.manual_seed(3)
+    p = torch.nn.Parameter(torch.randn(257, device="cuda"))
+    opt = DiffGrad([p], lr=2e-4, betas=(0.5, 0.9))
+    ref, state = p.detach().double().cpu().tolist(), {}
+    for _ in range(6):
+        g = torch.randn(257) * 10 ** float(torch.randint(-3, 2, ()).item())
+        p.grad = g.cuda()
+        opt.step()
+        ref = to.diffgrad_step(ref, g.double().tolist(), state, lr=2e-4, betas=(0.5, 0.9))
+    err = (p.detach().double().cpu() - torch.tensor(ref, dtype=torch.float64)).abs().max().item()
+    print("fused DiffGrad vs scalar oracle: max abs", err)
+    assert err < 5e-7          # fp32 state vs float64 oracle after 6 steps of |dp| <= 2e-4
+
+
 def test_optimizer_step_invalidates_packed_weights(cuda_device):
     from histogan_b200 import ops
     from histogan_b200.optim import DiffGrad
@@ -139,7 +158,7 @@ def test_cuda_graph_training_path(tmp_path, cuda_device):
         t.steps = 2501
         for _ in range(9):                 # 2501..2509: graphs incl. two GP steps
             t.train(alpha=2)
-    assert set(tg._graphs) >= {('D', False), ('D', True), ('G', 2.0)}
+    assert set(tg._graphs) >= {('D', False), ('D', True), ('G', 2.0, False)}
     for name in ("d_loss", "g_loss", "h_loss", "last_gp_loss"):
         a, b = getattr(tg, name), getattr(te, name)
         assert a == a and abs(a) < 1e7, (name, a)
@@ -155,8 +174,18 @@ def test_cuda_graph_training_path(tmp_path, cuda_device):
     assert 0.05 < tg.last_gp_loss / te.last_gp_loss < 20, (tg.last_gp_loss, te.last_gp_loss)
     moved = sum(not torch.equal(p, q) for p, q in zip(tg.GAN.G.parameters(), te.GAN.G.parameters()))
     assert moved > 10          # different random latents -> different but comparable trajectories
-    tg.steps = 2528                        # a path-length step runs eagerly inside a graphed trainer
+    tg.steps = 2528                        # a path-length step is captured too (device-side pl_mean)
+    pl0 = tg.pl_mean
     tg.train(alpha=2)
+    assert ('G', 2.0, True) in tg._graphs and tg.pl_mean != pl0 and tg.pl_mean == tg.pl_mean
+    # load() builds a new GAN -> the captured graphs of the old one must be dropped
+    tg.save(7)
+    tg.load(7)
+    assert tg._graphs == {} and tg._static is None
+    before = [p.detach().clone() for p in tg.GAN.D.parameters()]
+    tg.steps = 2501
+    tg.train(alpha=2)
+    assert sum(not torch.equal(a, b) for a, b in zip(before, tg.GAN.D.parameters())) > 10
 
 
 def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
@@ -172,26 +201,21 @@ def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
         'images': torch.rand(B, 3, S_, S_, device='cuda'),
         'hists': torch.rand(B, 3, 64, 64, device='cuda'),
         'mask': (torch.arange(L, device='cuda') < 1).float(),
-        'mask_host': torch.ones(L).pin_memory(),
+        'pl_mean': torch.zeros((), device='cuda'),
     }
     t._static['hists'] /= t._static['hists'].sum(dim=(1, 2, 3), keepdim=True)
-    fixed = {"randn": [torch.randn(B, 512, device='cuda') for _ in range(2)],
-             "rand": torch.rand(B, S_, S_, 1, device='cuda')}
-    calls = {"n": 0}
-
-    def fake_randn(*a, **k):
-        calls["n"] += 1
-        return fixed["randn"][(calls["n"] - 1) % 2]
-
-    monkeypatch.setattr(T.torch, "randn", fake_randn)
-    monkeypatch.setattr(T.torch, "rand", lambda *a, **k: fixed["rand"])
+    draws = {'z1': torch.randn(B, 512, device='cuda'), 'z2': torch.randn(B, 512, device='cuda'),
+             'inoise': torch.rand(B, S_, S_, 1, device='cuda'),
+             'pl_noise': torch.randn(B, L, 512, device='cuda')}
+    t._static['fixed'] = {'d': draws, 'g': draws}
 
     def grads(params):
         return [p.grad.detach().clone() for p in params if p.grad is not None]
 
     for key, fn, params in ((('D', True), lambda: t._phase_d(True), list(t.GAN.D.parameters())),
                             (('D', False), lambda: t._phase_d(False), list(t.GAN.D.parameters())),
-                            (('G', 2.0), lambda: t._phase_g(2.0), list(t.GAN.G.parameters()))):
+                            (('G', 2.0, False), lambda: t._phase_g(2.0), list(t.GAN.G.parameters())),
+                            (('G', 2.0, True), lambda: t._phase_g(2.0, True), list(t.GAN.G.parameters()))):
         out_e = [o.clone() for o in fn() if o is not None]
         g_e = grads(params)
         out_g = [o.clone() for o in t._graphed(key, fn, params) if o is not None]     # capture + replay
@@ -216,3 +240,118 @@ def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
     assert all(a is not b for a, b in zip(with_gp, [p.grad for p in d_params]))
     t._graphed(('D', True), None, d_params)
     assert all(a is b for a, b in zip(with_gp, [p.grad for p in d_params]))
+
+
+# ------------------------------------------------ parity of the step itself -------------
+# tests/golden/train_step_64.npz = ONE call of the UNMODIFIED reference Trainer.train
+# (histoGAN/histoGAN.py:853-1020) on the CPU: losses + every parameter gradient of both
+# phases (oracle/make_golden_step.py).  TF32 tolerances: activations-level quantities 2e-3;
+# per-tensor gradients: norm within 3 %, cosine >= 0.999 on the stored entries.
+
+LOSS_TOL, GRAD_NORM_TOL, GRAD_COS = 2e-3, 3e-2, 0.999
+
+
+def _golden_trainer(tmp_path, **kw):
+    from histogan_b200.trainer import Trainer
+    from oracle import make_golden_step as mgs
+    t = Trainer("s", str(tmp_path / "results"), str(tmp_path / "models"), image_size=mgs.IMAGE_SIZE,
+                network_capacity=mgs.CAPACITY, batch_size=mgs.BATCH, hist_insz=150,
+                hist_resizing="interpolation", save_every=10 ** 9, **kw)
+    t.init_GAN()
+    t.GAN.load_state_dict({k: v.cuda() for k, v in mgs.seeded_gan_state(t.GAN).items()}, strict=False)
+    t.GAN.reset_parameter_averaging()
+    g_params = [p for grp in t.GAN.G_opt.param_groups for p in grp['params']]
+    t.GAN.D_opt = mgs.RecordingOptimizer(t.GAN.D.parameters())
+    t.GAN.G_opt = mgs.RecordingOptimizer(g_params)
+    return t
+
+
+def _check_grads(tag, grads, names, g, case, which):
+    from tests import step_checks as sc
+    tab = sc.compare_grads(grads, names, g[f"c{case}_{which}_norms"], g[f"c{case}_{which}_samples"])
+    w = sc.worst(tab)
+    print(f"{tag} steps={case} {which}-grads worst:", w)
+    from tests import parity
+    parity.record(f"train_step[{tag},steps={case},{which}-grads]", {k: v[1] for k, v in w.items()})
+    bad = {k: v for k, v in tab.items() if v[0] > GRAD_NORM_TOL or v[1] < GRAD_COS}
+    assert not bad, bad
+    return w
+
+
+@pytest.mark.parametrize("case", [1, 4, 32])
+def test_train_step_matches_reference_trainer(case, tmp_path, cuda_device):
+    """eager Trainer.train (CPU-side random draws in the reference's order) vs the reference"""
+    from oracle import make_golden_step as mgs
+    from tests import step_checks as sc
+    g = sc.load_golden()
+    ref = g[f"c{case}_scalars"]
+    t = _golden_trainer(tmp_path)
+    images, hists = mgs.step_inputs(case)
+    t.loader = iter([{"images": images, "histograms": hists[0]}, {"images": images, "histograms": hists[1]}])
+    t.steps, t.pl_mean = case, 0
+    mgs.seed_step(case)
+    t.train(alpha=mgs.ALPHA)
+    got = {"d_loss": t.d_loss, "g_loss": t.g_loss, "h_loss": t.h_loss, "gp": t.last_gp_loss,
+           "pl_mean": float(t.pl_mean)}
+    print(f"steps={case} ours {got}\n          reference {ref}")
+    from tests import parity
+    parity.record(f"train_step[eager,steps={case},losses]",
+                  {k: sc.rel(got[k], ref[k]) for k in got if ref[k] == ref[k] and ref[k] != 0})
+    assert sc.rel(t.d_loss, ref["d_loss"]) < LOSS_TOL
+    assert sc.rel(t.g_loss, ref["g_loss"]) < LOSS_TOL
+    assert sc.rel(t.h_loss, ref["h_loss"]) < 1e-3
+    if case % 4 == 0:
+        assert sc.rel(t.last_gp_loss, ref["gp"]) < 5e-3
+    if case % 32 == 0:
+        assert sc.rel(t.pl_mean, ref["pl_mean"]) < 5e-3
+    _check_grads("eager", t.GAN.D_opt.recorded, g["names_d"], g, case, "d")
+    _check_grads("eager", t.GAN.G_opt.recorded, g["names_g"], g, case, "g")
+
+
+@pytest.mark.parametrize("case", [1, 4, 32])
+def test_graphed_phases_match_reference_trainer(case, tmp_path, cuda_device):
+    """the CUDA-graph path (_phase_d / _phase_g as captured and replayed by _train_graphed),
+    fed the reference's random draws, vs the reference Trainer.train golden"""
+    import math
+    from oracle import make_golden_step as mgs
+    from oracle import train_oracle as to
+    from tests import step_checks as sc
+    g = sc.load_golden()
+    ref = g[f"c{case}_scalars"]
+    t = _golden_trainer(tmp_path, cuda_graphs=True, fast_rng=True)
+    t.GAN.train()
+    images, hists = mgs.step_inputs(case)
+    L = int(math.log2(mgs.IMAGE_SIZE) - 1) - 2
+    mgs.seed_step(case)
+    dr = to.draw_step_inputs(mgs.BATCH, L, 512, mgs.IMAGE_SIZE, path_penalty=case % 32 == 0)
+
+    def as_fixed(style, noise, pl=None):
+        z1, n1 = style[0]
+        z2 = style[1][0] if len(style) > 1 else z1
+        out = {'z1': z1.cuda(), 'z2': z2.cuda(), 'inoise': noise.cuda(),
+               'mask': (torch.arange(L) < n1).float().cuda()}
+        if pl is not None:
+            out['pl_noise'] = pl.cuda()
+        return out
+
+    fd, fg = as_fixed(dr["d_style"], dr["d_noise"]), as_fixed(dr["g_style"], dr["g_noise"], dr["pl_noise"])
+    t._static = {'images': images.cuda(), 'hists': hists[0].cuda().clone(), 'mask': fd['mask'].clone(),
+                 'pl_mean': torch.zeros((), device='cuda'), 'fixed': {'d': fd, 'g': fg}}
+    d_params = list(t.GAN.D.parameters())
+    g_params = [p for grp in t.GAN.G_opt.param_groups for p in grp['params']]
+    gp_on, pl_on = case % 4 == 0, case % 32 == 0
+    for _ in range(2):                                   # capture + replay, then a second replay
+        div, gp = t._graphed(('D', gp_on), lambda: t._phase_d(gp_on), d_params)
+    assert sc.rel(div.item(), ref["d_loss"]) < LOSS_TOL
+    if gp_on:
+        assert sc.rel(gp.item(), ref["gp"]) < 5e-3
+    _check_grads("graph", [p.grad for p in d_params], g["names_d"], g, case, "d")
+    t._static['hists'].copy_(hists[1].cuda())
+    t._static['mask'].copy_(fg['mask'])
+    for _ in range(2):
+        loss, hl, avg_pl = t._graphed(('G', mgs.ALPHA, pl_on), lambda: t._phase_g(mgs.ALPHA, pl_on), g_params)
+    assert sc.rel(loss.item(), ref["g_loss"]) < LOSS_TOL
+    assert sc.rel(hl.item(), ref["h_loss"]) < 1e-3
+    if pl_on:
+        assert sc.rel(0.01 * avg_pl.item(), ref["pl_mean"]) < 5e-3
+    _check_grads("graph", [p.grad for p in g_params], g["names_g"], g, case, "g")
