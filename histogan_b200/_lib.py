@@ -14,7 +14,7 @@ import torch
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "lib" / "libhistogan_b200.so"
 
-HG_ABI_VERSION = 3
+HG_ABI_VERSION = 4
 
 RESIZE_IDS = {"interpolation": 0, "sampling": 1}
 METHOD_IDS = {"thresholding": 0, "RBF": 1, "inverse-quadratic": 2}
@@ -77,7 +77,9 @@ _SIGNATURES = {
     "hg_upsample_modulate_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
     "hg_torgb_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
     "hg_torgb_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
-    "hg_diffgrad_step": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_float] * 5 + [C.c_void_p]),
+    "hg_upsample2x_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_void_p]),
+    "hg_diffgrad_step": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_float] * 5 + [C.c_void_p]),
     "hg_bias_act_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_float, C.c_void_p]),
     "hg_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),

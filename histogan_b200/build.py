@@ -56,8 +56,19 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     OBJDIR.mkdir(exist_ok=True)
     LIBDIR.mkdir(exist_ok=True)
 
+    # headers every translation unit depends on; an object is rebuilt only when its own source,
+    # a header or the flags changed
+    hdr = hashlib.sha256()
+    for f in sorted(list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "histogan_b200.h"]):
+        hdr.update(f.read_bytes())
+    hdr.update(" ".join(ARCH_FLAGS + NVCC_FLAGS).encode())
+
     def compile_one(src: Path) -> Path:
         obj = OBJDIR / (src.stem + ".o")
+        ostamp = OBJDIR / (src.stem + ".sha")
+        key = hashlib.sha256(hdr.digest() + src.read_bytes()).hexdigest()
+        if not force and obj.exists() and ostamp.exists() and ostamp.read_text() == key:
+            return obj
         cmd = [nvcc, *ARCH_FLAGS, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         (OBJDIR / (src.stem + ".ptxas.log")).write_text(r.stderr)
@@ -65,6 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(r.stderr)
+        ostamp.write_text(key)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:

@@ -41,10 +41,17 @@ def is_ohwi(w: torch.Tensor) -> bool:
     return w.dim() == 4 and w.is_contiguous(memory_format=torch.channels_last)
 
 
-def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
+def pack_is_plain_copy(w: torch.Tensor) -> bool:
+    """is the forward (mode 0) packed operand of `w` just its memory, TF32-rounded?  (channels_last
+    parameter, both channel counts multiples of 32: nothing to transpose or pad)"""
+    return is_ohwi(w) and w.shape[0] % 32 == 0 and w.shape[1] % 32 == 0
+
+
+def pack_weight(w_oihw: torch.Tensor, mode: int = 0, out: torch.Tensor = None) -> torch.Tensor:
     """hg_pack_conv_weight: (Cout,Cin,kh,kw) -> [Np][KH][KW][Kp] K-major TF32, N/K zero-padded
     to multiples of 32.  mode 1 = dgrad (N = Cin, K = Cout, taps flipped).  The weight may be
-    stored channels_last (what this package's modules do) or plain contiguous."""
+    stored channels_last (what this package's modules do) or plain contiguous.  `out`: write
+    into this existing packed tensor (same shape) instead of allocating."""
     lib = _lib.load()
     _lib.require_cuda(w_oihw, "pack_weight")
     w = w_oihw.detach().float()
@@ -53,7 +60,11 @@ def pack_weight(w_oihw: torch.Tensor, mode: int = 0) -> torch.Tensor:
         w = w.contiguous()
     co, ci, kh, kw = w.shape
     n, k = (ci, co) if mode else (co, ci)
-    out = torch.empty((_up32(n), kh, kw, _up32(k)), dtype=torch.float32, device=w.device)
+    shape = (_up32(n), kh, kw, _up32(k))
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float32, device=w.device)
+    else:
+        assert tuple(out.shape) == shape and out.is_contiguous() and out.device == w.device
     if ohwi and mode == 0 and co % 32 == 0 and ci % 32 == 0:
         # channels_last parameter, nothing to pad: the packed forward operand IS the parameter's
         # memory, TF32-rounded -- one vectorised copy (hg_modulate_round without a modulation)

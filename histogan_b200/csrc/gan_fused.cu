@@ -432,6 +432,61 @@ upsample_modulate_bwd_kernel(const float* __restrict__ dxm, const float* __restr
   if (pl == 0 && cvalid) atomic_add4(gmod + (long long)b * C + c, acc[0]);
 }
 
+// ---------------------------------------------------------------------------
+// nn.Upsample(scale_factor=2, bilinear, align_corners=False) of the PLANAR rgb skip tensor
+// (RGBBlock, histoGAN/histoGAN.py:377-378,388-389): `planes` = B*3 images of H x W -> 2H x 2W.
+// Same taps / evaluation order as torch's upsample_bilinear2d.  HBM-bound (<= 33 MB per pass).
+__global__ void __launch_bounds__(256)
+upsample2x_planar_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int H, int W,
+                             long long total) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int OW = 2 * W, OH = 2 * H;
+  const int ow = (int)(i % OW);
+  const int oh = (int)((i / OW) % OH);
+  const long long pl = i / ((long long)OW * OH);
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  up2_taps(oh, H, y0, y1, ly0, ly1);
+  up2_taps(ow, W, x0, x1, lx0, lx1);
+  const float* xp = x + pl * H * W;
+  y[i] = ly0 * (lx0 * xp[y0 * W + x0] + lx1 * xp[y0 * W + x1]) +
+         ly1 * (lx0 * xp[y1 * W + x0] + lx1 * xp[y1 * W + x1]);
+}
+
+// adjoint as a gather (deterministic): low-res pixel (h, w) collects from output rows 2h-1..2h+2
+__global__ void __launch_bounds__(256)
+upsample2x_planar_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int H, int W,
+                             long long total) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int w = (int)(i % W);
+  const int h = (int)((i / W) % H);
+  const long long pl = i / ((long long)W * H);
+  const int OW = 2 * W, OH = 2 * H;
+  const float* gp = dy + pl * OH * OW;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = -1; a <= 2; ++a) {
+    const int oh = 2 * h + a;
+    if (oh < 0 || oh >= OH) continue;
+    int y0, y1; float ly0, ly1;
+    up2_taps(oh, H, y0, y1, ly0, ly1);
+    const float wy = (y0 == h ? ly0 : 0.f) + (y1 == h ? ly1 : 0.f);
+    if (wy == 0.f) continue;
+#pragma unroll
+    for (int c = -1; c <= 2; ++c) {
+      const int ow = 2 * w + c;
+      if (ow < 0 || ow >= OW) continue;
+      int x0, x1; float lx0, lx1;
+      up2_taps(ow, W, x0, x1, lx0, lx1);
+      const float wx = (x0 == w ? lx0 : 0.f) + (x1 == w ? lx1 : 0.f);
+      acc = fmaf(wy * wx, gp[(long long)oh * OW + ow], acc);
+    }
+  }
+  dx[i] = acc;
+}
+
 }  // namespace hg
 
 using namespace hg;
@@ -556,5 +611,21 @@ extern "C" int hg_upsample_modulate_bwd(const float* dxm, const float* x, const 
   upsample_modulate_bwd_kernel<<<grid, kFusedThreads, 0, stream>>>(dxm, x, mod, dx, gmod, H, W, C,
                                                                    tiles_w, n_tiles, (int)per);
   HG_LAUNCH_OK("upsample_modulate_bwd_kernel");
+  return 0;
+}
+
+extern "C" int hg_upsample2x_planar(const float* x, float* y, int32_t planes, int32_t H, int32_t W,
+                                    int32_t backward, hg_stream_t stream_) {
+  if (!x || !y) return set_error(HG_EINVAL, "null tensor pointer");
+  if (planes <= 0 || H <= 0 || W <= 0) return 0;
+  // forward: x (planes,H,W) -> y (planes,2H,2W), one thread per output; backward: x = dy
+  // (planes,2H,2W) -> y = dx (planes,H,W), one thread per low-resolution pixel
+  const long long total = (long long)planes * H * W * (backward ? 1 : 4);
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (backward)
+    upsample2x_planar_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, y, H, W, total);
+  else
+    upsample2x_planar_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, y, H, W, total);
+  HG_LAUNCH_OK("upsample2x_planar_kernel");
   return 0;
 }

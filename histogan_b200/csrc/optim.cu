@@ -4,8 +4,11 @@
 // a per-parameter Python loop of ~10 element-wise launches.  One pass here:
 //   m = b1 m + (1-b1) g ;  v = b2 v + (1-b2) g^2 ;  xi = sigmoid(|g_prev - g|)
 //   p -= step_size * (m * xi) / (sqrt(v) + eps) ;   g_prev = g
-// for up to kMaxTensors tensors per launch (pointers in kernel-parameter space).
+// for up to kMaxTensors tensors per launch (pointers in kernel-parameter space).  For conv weights
+// whose tensor-core operand is a plain TF32-rounded copy of the parameter the kernel also writes
+// that copy (`packed`), so no separate packing pass reads the weights again.
 #include "hg_common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace hg {
 
@@ -18,11 +21,27 @@ struct DiffGradBatch {
   float* m[kMaxTensors];
   float* v[kMaxTensors];
   float* prev[kMaxTensors];
+  float* packed[kMaxTensors];              // optional TF32-rounded copy of the NEW parameter (or null)
   long long n[kMaxTensors];
   int first_block[kMaxTensors + 1];        // prefix sum of ceil(n / kChunk)
   int count;
 };
 
+__device__ __forceinline__ float diffgrad_one(float pi, float gi, float& mi, float& vi, float& pvi,
+                                              float beta1, float beta2, float eps, float step_size,
+                                              float weight_decay) {
+  if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+  mi = fmaf(beta1, mi, (1.f - beta1) * gi);
+  vi = fmaf(beta2, vi, (1.f - beta2) * gi * gi);
+  const float diff = fabsf(pvi - gi);
+  const float xi = 1.f / (1.f + expf(-diff));
+  pvi = gi;
+  return pi - step_size * (mi * xi) / (sqrtf(vi) + eps);
+}
+
+// HBM-bound: 5 reads + 4 writes (+1 for the packed copy) of 4 B per element; 128-bit accesses
+// (VEC: every pointer of the batch is 16-byte aligned -- torch allocations always are).
+template <bool VEC>
 __global__ void __launch_bounds__(256)
 diffgrad_kernel(const DiffGradBatch t, float beta1, float beta2, float eps, float step_size,
                 float weight_decay) {
@@ -35,17 +54,44 @@ diffgrad_kernel(const DiffGradBatch t, float beta1, float beta2, float eps, floa
   float* __restrict__ m = t.m[ti];
   float* __restrict__ v = t.v[ti];
   float* __restrict__ pv = t.prev[ti];
+  float* __restrict__ pk = t.packed[ti];
   const long long end = min(n, base + kChunk);
-  for (long long i = base + threadIdx.x; i < end; i += 256) {
-    float gi = g[i];
-    const float pi = p[i];
-    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
-    const float mi = fmaf(beta1, m[i], (1.f - beta1) * gi);
-    const float vi = fmaf(beta2, v[i], (1.f - beta2) * gi * gi);
-    const float diff = fabsf(pv[i] - gi);
-    const float xi = 1.f / (1.f + expf(-diff));
-    m[i] = mi; v[i] = vi; pv[i] = gi;
-    p[i] = pi - step_size * (mi * xi) / (sqrtf(vi) + eps);
+  long long i = base + (VEC ? threadIdx.x * 4 : threadIdx.x);
+  if (VEC) {
+    for (; i + 3 < end; i += 256 * 4) {
+      const float4 g4 = *reinterpret_cast<const float4*>(g + i);
+      float4 p4 = *reinterpret_cast<const float4*>(p + i);
+      float4 m4 = *reinterpret_cast<const float4*>(m + i);
+      float4 v4 = *reinterpret_cast<const float4*>(v + i);
+      float4 q4 = *reinterpret_cast<const float4*>(pv + i);
+      p4.x = diffgrad_one(p4.x, g4.x, m4.x, v4.x, q4.x, beta1, beta2, eps, step_size, weight_decay);
+      p4.y = diffgrad_one(p4.y, g4.y, m4.y, v4.y, q4.y, beta1, beta2, eps, step_size, weight_decay);
+      p4.z = diffgrad_one(p4.z, g4.z, m4.z, v4.z, q4.z, beta1, beta2, eps, step_size, weight_decay);
+      p4.w = diffgrad_one(p4.w, g4.w, m4.w, v4.w, q4.w, beta1, beta2, eps, step_size, weight_decay);
+      *reinterpret_cast<float4*>(m + i) = m4;
+      *reinterpret_cast<float4*>(v + i) = v4;
+      *reinterpret_cast<float4*>(pv + i) = q4;
+      *reinterpret_cast<float4*>(p + i) = p4;
+      if (pk)
+        *reinterpret_cast<float4*>(pk + i) =
+            make_float4(tf32_round(p4.x), tf32_round(p4.y), tf32_round(p4.z), tf32_round(p4.w));
+    }
+    // tail of the chunk (n % 4 elements of the last chunk): the thread whose group is cut finishes it
+    if (i < end) {
+      for (long long j = i; j < end; ++j) {
+        float mi = m[j], vi = v[j], qi = pv[j];
+        const float pn = diffgrad_one(p[j], g[j], mi, vi, qi, beta1, beta2, eps, step_size, weight_decay);
+        m[j] = mi; v[j] = vi; pv[j] = qi; p[j] = pn;
+        if (pk) pk[j] = tf32_round(pn);
+      }
+    }
+  } else {
+    for (; i < end; i += 256) {
+      float mi = m[i], vi = v[i], qi = pv[i];
+      const float pn = diffgrad_one(p[i], g[i], mi, vi, qi, beta1, beta2, eps, step_size, weight_decay);
+      m[i] = mi; v[i] = vi; pv[i] = qi; p[i] = pn;
+      if (pk) pk[i] = tf32_round(pn);
+    }
   }
 }
 
@@ -55,8 +101,8 @@ using namespace hg;
 
 extern "C" int hg_diffgrad_step(int32_t count, float* const* p, const float* const* g,
                                 float* const* m, float* const* v, float* const* prev,
-                                const int64_t* numel, float beta1, float beta2, float eps,
-                                float step_size, float weight_decay, hg_stream_t stream_) {
+                                float* const* packed, const int64_t* numel, float beta1, float beta2,
+                                float eps, float step_size, float weight_decay, hg_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (count < 0 || (count > 0 && (!p || !g || !m || !v || !prev || !numel)))
     return set_error(HG_EINVAL, "null pointer table");
@@ -65,10 +111,14 @@ extern "C" int hg_diffgrad_step(int32_t count, float* const* p, const float* con
     DiffGradBatch b;
     b.count = 0;
     int blocks = 0;
+    uintptr_t align = 0;
     while (i < count && b.count < kMaxTensors) {
       if (numel[i] > 0) {
         const int k = b.count++;
         b.p[k] = p[i]; b.g[k] = g[i]; b.m[k] = m[i]; b.v[k] = v[i]; b.prev[k] = prev[i];
+        b.packed[k] = packed ? packed[i] : nullptr;
+        align |= (uintptr_t)p[i] | (uintptr_t)g[i] | (uintptr_t)m[i] | (uintptr_t)v[i] |
+                 (uintptr_t)prev[i] | (uintptr_t)b.packed[k];
         b.n[k] = numel[i];
         b.first_block[k] = blocks;
         blocks += (int)((numel[i] + kChunk - 1) / kChunk);
@@ -77,7 +127,10 @@ extern "C" int hg_diffgrad_step(int32_t count, float* const* p, const float* con
     }
     b.first_block[b.count] = blocks;
     if (b.count == 0) continue;
-    diffgrad_kernel<<<blocks, 256, 0, stream>>>(b, beta1, beta2, eps, step_size, weight_decay);
+    if (align & 15)
+      diffgrad_kernel<false><<<blocks, 256, 0, stream>>>(b, beta1, beta2, eps, step_size, weight_decay);
+    else
+      diffgrad_kernel<true><<<blocks, 256, 0, stream>>>(b, beta1, beta2, eps, step_size, weight_decay);
     HG_LAUNCH_OK("diffgrad_kernel");
   }
   return 0;

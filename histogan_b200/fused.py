@@ -172,3 +172,35 @@ def to_rgb(x, style, weight, prev_rgb):
     """Conv2DMod(C -> 3, k=1, demod=False)(x, style) + prev_rgb, planar NCHW result."""
     wmod = weight[None, :, :, 0, 0] * (style[:, None, :] + 1)           # (B,3,C)
     return _ToRGB.apply(x, wmod, prev_rgb)
+
+
+class _Upsample2xPlanar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        x = x.contiguous()
+        B, Cc, H, W = x.shape
+        y = torch.empty((B, Cc, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.hg_upsample2x_planar(_lib.ptr(x), _lib.ptr(y), B * Cc, H, W, 0, _st(x.device))
+        _lib.check(rc, "hg_upsample2x_planar")
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        lib = _lib.load()
+        dy = dy.contiguous()
+        B, Cc, OH, OW = dy.shape
+        dx = torch.empty((B, Cc, OH // 2, OW // 2), dtype=torch.float32, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = lib.hg_upsample2x_planar(_lib.ptr(dy), _lib.ptr(dx), B * Cc, OH // 2, OW // 2, 1,
+                                          _st(dy.device))
+        _lib.check(rc, "hg_upsample2x_planar")
+        return dx
+
+
+def upsample2x_planar(x):
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) of a planar (NCHW)
+    float32 CUDA tensor -- RGBBlock's skip path (histoGAN.py:377-378,388-389)."""
+    return _Upsample2xPlanar.apply(x)

@@ -115,7 +115,10 @@ class RGBBlock(nn.Module):
             if prev_rgb is not None:
                 x = x + prev_rgb
         if self.upsample is not None:
-            x = self.upsample(x)
+            if USE_FUSED and x.is_cuda and x.dtype == torch.float32:
+                x = fused.upsample2x_planar(x)
+            else:
+                x = self.upsample(x)
         return x
 
 

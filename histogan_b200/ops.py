@@ -92,31 +92,30 @@ def round_pad(x: torch.Tensor) -> torch.Tensor:
 
 
 class _PackCache:
-    """Packed (K-major, TF32) copies of a weight, kept ON the weight tensor object and
-    reused until the tensor is modified in place (optimizer step / load_state_dict bump
-    ``_version``).  Nothing is keyed by address, so a freed-and-reallocated tensor can
-    never hit a stale entry."""
+    """Packed (K-major, TF32) copies of a weight, kept ON the weight tensor object: a dict
+    {mode: [version, packed]} under ``w._hg_packed``.  Nothing is keyed by address, so a
+    freed-and-reallocated tensor can never hit a stale entry.
+
+    A packed tensor is allocated ONCE per (weight, mode) and afterwards re-filled IN PLACE:
+    its address is stable for the lifetime of the parameter, so captured CUDA graphs read it
+    directly and contain no packing kernels.  Whoever modifies a parameter in place keeps the
+    packs current: the fused DiffGrad kernel writes the forward operand itself and calls
+    ``refresh`` for the other forms; any other modification (load_state_dict, a foreign
+    optimiser) bumps ``_version`` and is caught by the next ``get`` / ``refresh_stale``."""
 
     ATTR = "_hg_packed"
 
-    def __init__(self):
-        self.generation = 0
-
-    def new_generation(self):
-        """forget every cached pack (CUDA-graph capture must contain its own pack kernels)"""
-        self.generation += 1
-
-    def get(self, w: torch.Tensor, mode: int) -> torch.Tensor:
-        ver = (w._version, self.generation)
-        store = getattr(w, self.ATTR, None)
-        if store is not None:
-            hit = store.get(mode)
-            if hit is not None and hit[0] == ver:
-                return hit[1]
+    def _pack(self, w, mode, out=None):
         if isinstance(mode, tuple):         # ('s2', py, px): one parity class of a stride-2 dgrad
-            packed = _conv.pack_weight(_stride2_class_weight(w, mode[1], mode[2]), 0)
-        else:
-            packed = _conv.pack_weight(w, mode)    # zero-pads both extents to multiples of 32
+            return _conv.pack_weight(_stride2_class_weight(w, mode[1], mode[2]), 0, out)
+        return _conv.pack_weight(w, mode, out)     # zero-pads both extents to multiples of 32
+
+    def get(self, w: torch.Tensor, mode) -> torch.Tensor:
+        store = getattr(w, self.ATTR, None)
+        hit = store.get(mode) if store is not None else None
+        if hit is not None and hit[0] == w._version:
+            return hit[1]
+        packed = self._pack(w, mode, hit[1] if hit is not None else None)
         if w.is_leaf:                       # parameters persist; temporaries are not worth caching
             if store is None:
                 store = {}
@@ -124,8 +123,36 @@ class _PackCache:
                     setattr(w, self.ATTR, store)
                 except AttributeError:
                     return packed
-            store[mode] = (ver, packed)
+            store[mode] = [w._version, packed]
         return packed
+
+    def refresh(self, w: torch.Tensor, done=()):
+        """`w` was just modified in place: refill every cached form (modes in `done` were already
+        written by the caller) and stamp them with the new version."""
+        store = getattr(w, self.ATTR, None)
+        if not store:
+            return
+        for mode, hit in store.items():
+            if mode not in done and hit[0] != w._version:
+                self._pack(w, mode, hit[1])
+            hit[0] = w._version
+
+    def refresh_stale(self, weights):
+        """bring the cached forms of `weights` up to date (cheap version check per tensor); called
+        before a CUDA-graph replay, whose kernels read the packed tensors without going through get"""
+        for w in weights:
+            store = getattr(w, self.ATTR, None)
+            if store and any(hit[0] != w._version for hit in store.values()):
+                self.refresh(w)
+
+    def fused_forward_target(self, w: torch.Tensor):
+        """the cached forward operand of `w` if an optimiser kernel may write it directly
+        (a plain TF32-rounded copy in the parameter's own linear order), else None"""
+        store = getattr(w, self.ATTR, None)
+        if store and 0 in store and w.dim() == 4 and _conv.pack_is_plain_copy(w) \
+                and store[0][1].numel() == w.numel():
+            return store[0][1]
+        return None
 
 
 # below 64x64 the four launches cost more than the dilated single conv (measured, B=32:

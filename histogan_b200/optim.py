@@ -109,14 +109,21 @@ class DiffGrad(Optimizer):
                    for k in ('exp_avg', 'exp_avg_sq', 'previous_grad')), "optimizer state layout"
         numel = (C.c_int64 * n)(*[p.numel() for p in ps])
         dev = ps[0].device
+        # conv weights whose tensor-core forward operand is a plain TF32-rounded copy: the kernel
+        # writes that copy too (ops._PackCache keeps its address stable)
+        from . import ops
+        targets = [ops._packs.fused_forward_target(p) for p in ps]
+        packed = arr(*[t.data_ptr() if t is not None else None for t in targets])
         with torch.cuda.device(dev):
             rc = lib.hg_diffgrad_step(n, table(ps), table([p.grad for p in ps]),
                                       table([s['exp_avg'] for s in st]),
                                       table([s['exp_avg_sq'] for s in st]),
-                                      table([s['previous_grad'] for s in st]), numel,
+                                      table([s['previous_grad'] for s in st]), packed, numel,
                                       beta1, beta2, eps, step_size, weight_decay,
                                       _lib.current_stream_ptr(dev))
         _lib.check(rc, "hg_diffgrad_step")
         # the kernel wrote through raw pointers: tell autograd the parameters changed in place
         # (saved-tensor checks, and the packed-weight caches of ops.py key on ``_version``)
         torch.autograd.graph.increment_version(ps)
+        for p, t in zip(ps, targets):        # the remaining packed forms (dgrad transposes), in place
+            ops._packs.refresh(p, done=(0,) if t is not None else ())

@@ -621,7 +621,8 @@ class Trainer:
             with torch.cuda.stream(side):           # eager warm-up on a side stream
                 fn()
             torch.cuda.current_stream().wait_stream(side)
-            ops._packs.new_generation()             # the graph must contain its own weight packing
+            # the warm-up filled the packed-weight cache (stable addresses, refilled in place by the
+            # optimiser step): the captured graph reads those tensors and packs nothing itself
             g = torch.cuda.CUDAGraph()
             n0 = lib.hg_launch_count()
             with torch.cuda.graph(g, pool=self._graphs.get('pool')):
@@ -629,7 +630,9 @@ class Trainer:
             self._graphs.setdefault('pool', g.pool())
             # library kernels recorded in this graph (each replay launches them again)
             grads = [(p, p.grad) for p in params if p.grad is not None]
-            entry = self._graphs[key] = (g, outs, int(lib.hg_launch_count() - n0), grads)
+            packed = [p for p in self.GAN.parameters() if getattr(p, ops._PackCache.ATTR, None)]
+            entry = self._graphs[key] = (g, outs, int(lib.hg_launch_count() - n0), grads, packed)
+        ops._packs.refresh_stale(entry[4])      # no-op unless someone other than DiffGrad moved weights
         entry[0].replay()
         for p, gr in entry[3]:
             p.grad = gr

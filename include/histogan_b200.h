@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HG_ABI_VERSION 3
+#define HG_ABI_VERSION 4
 
 /* error codes (negative; positive values are cudaError_t) */
 #define HG_EINVAL   (-1)   /* bad argument (message in hg_last_error)          */
@@ -252,15 +252,26 @@ int hg_torgb_bwd(const float* drgb, const float* x, const float* wmod, float* dx
 int hg_bias_act_bwd(const float* dy, const float* y, float* dpre, float* gb, int32_t B,
                     int32_t HW, int32_t C, float slope, hg_stream_t stream);
 
+/* 2x bilinear up-sampling (align_corners = False) of the planar RGB skip tensor of RGBBlock
+ * (histoGAN/histoGAN.py:377-378,388-389).  backward == 0: x (planes,H,W) -> y (planes,2H,2W);
+ * backward != 0: the adjoint, x = dy (planes,2H,2W) -> y = dx (planes,H,W).  H, W always name
+ * the LOW-resolution extent.                                                         */
+int hg_upsample2x_planar(const float* x, float* y, int32_t planes, int32_t H, int32_t W,
+                         int32_t backward, hg_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * Fused multi-tensor DiffGrad step (torch_optimizer.DiffGrad as used at
  * histoGAN/histoGAN.py:670-671,932,989).  HOST arrays of `count` DEVICE pointers;
  * step_size = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is computed by the caller.
+ * packed (ABI v4; table may be NULL, entries may be NULL): where given, the kernel also
+ * writes the TF32-rounded copy of the UPDATED parameter there (numel floats, same linear
+ * order) -- the forward tensor-core operand of a channels_last conv weight
+ * (hg_pack_conv_weight mode 0 | HG_PACK_FROM_OHWI with Cout, Cin multiples of 32).
  * ------------------------------------------------------------------------ */
 int hg_diffgrad_step(int32_t count, float* const* p, const float* const* g, float* const* m,
-                     float* const* v, float* const* prev, const int64_t* numel, float beta1,
-                     float beta2, float eps, float step_size, float weight_decay,
-                     hg_stream_t stream);
+                     float* const* v, float* const* prev, float* const* packed,
+                     const int64_t* numel, float beta1, float beta2, float eps, float step_size,
+                     float weight_decay, hg_stream_t stream);
 
 /* ------------------------------------------------------------------------ *
  * ReHistoGAN recolouring step (ReHistoGAN/rehistoGAN.py), SURVEY 8f-1.

@@ -100,3 +100,21 @@ def test_conv_bias_act_and_double_backward(cuda_device):
         (ha,) = torch.autograd.grad(ga[0].pow(2).sum(), w)
         (hb,) = torch.autograd.grad(gb[0].pow(2).sum(), w)
         assert _rel(ha, hb) < 5e-3, _rel(ha, hb)
+
+
+def test_upsample2x_planar_matches_torch(cuda_device):
+    """RGBBlock's skip up-sampling (histoGAN.py:377-378): hand-written planar kernel == nn.Upsample,
+    forward and adjoint, incl. odd / non-square / 1-pixel extents."""
+    import torch.nn.functional as F
+    from histogan_b200 import fused
+    torch.manual_seed(0)
+    for shape in [(2, 3, 4, 4), (3, 3, 16, 16), (1, 3, 7, 5), (2, 4, 1, 1), (2, 3, 128, 128)]:
+        x = torch.randn(shape, device="cuda", requires_grad=True)
+        y = fused.upsample2x_planar(x)
+        ref = F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False)
+        assert y.shape == ref.shape
+        assert (y - ref).abs().max().item() <= 1e-6 * ref.abs().max().item() + 1e-7
+        g = torch.randn_like(ref)
+        (gx,) = torch.autograd.grad(y, x, g)
+        (gr,) = torch.autograd.grad(ref, x, g)
+        assert (gx - gr).abs().max().item() <= 1e-5 * gr.abs().max().item() + 1e-7, shape

@@ -144,6 +144,38 @@ def test_optimizer_step_invalidates_packed_weights(cuda_device):
     assert ((y1 - ref).norm() / ref.norm()).item() < 2e-3   # ... and they are the current ones
 
 
+def test_packed_weights_are_refilled_in_place_by_the_optimizer(cuda_device):
+    """ops._PackCache: one allocation per (weight, form); DiffGrad's kernel writes the forward
+    operand itself and the dgrad forms are refilled in place -> stable addresses (captured CUDA
+    graphs read them) that always hold the CURRENT weights."""
+    from histogan_b200 import conv, ops
+    from histogan_b200.optim import DiffGrad
+    torch.manual_seed(0)
+    ws = [torch.nn.Parameter((torch.randn(64, 32, 3, 3, device="cuda") / 17).contiguous(memory_format=torch.channels_last)),
+          torch.nn.Parameter(torch.randn(16, 3, 3, 3, device="cuda") / 5),                  # padded, generic pack
+          torch.nn.Parameter((torch.randn(32, 32, 3, 3, device="cuda") / 17).contiguous(memory_format=torch.channels_last))]
+    forms = {0: [0, 1], 1: [0, 1], 2: [0, 1, ('s2', 0, 1), ('s2', 1, 1)]}
+    held = {(i, m): ops._packs.get(w, m) for i, w in enumerate(ws) for m in forms[i]}
+    ptrs = {k: v.data_ptr() for k, v in held.items()}
+    assert ops._packs.fused_forward_target(ws[0]) is held[(0, 0)]
+    assert ops._packs.fused_forward_target(ws[1]) is None          # needs padding: not a plain copy
+    opt = DiffGrad(ws, lr=1e-2)
+    for _ in range(2):
+        for w in ws:
+            w.grad = torch.randn_like(w)
+        opt.step()
+        for (i, m), buf in held.items():
+            cur = ops._packs.get(ws[i], m)
+            assert cur is buf and cur.data_ptr() == ptrs[(i, m)]                   # same tensor, same address
+            fresh = ops._PackCache()._pack(ws[i].detach().clone(memory_format=torch.preserve_format), m)
+            assert torch.equal(cur, fresh), (i, m)                                  # ... holding the new weights
+    # a foreign in-place modification is caught by the version check
+    with torch.no_grad():
+        ws[0].mul_(2.0)
+    ops._packs.refresh_stale(ws)
+    assert torch.equal(held[(0, 0)], conv.tf32_round(ws[0].detach()).permute(0, 2, 3, 1).contiguous())
+
+
 def test_cuda_graph_training_path(tmp_path, cuda_device):
     """cuda_graphs=True: D phase (with / without gradient penalty) and G phase replayed as
     CUDA graphs; PL steps stay eager.  Must train like the eager path: finite losses,
