@@ -154,13 +154,23 @@ def main_256():
     D.load_state_dict(go.seeded_state_dict(dshapes, seed=2))
     images = inp["images"].clone().requires_grad_(True)
     logits, q = D(images)
+    # (i) first order only: d logits.sum() / d(parameters, images)
+    logits.sum().backward(retain_graph=True)
+    names1, norms1, samples1 = grad_fingerprints(D.named_parameters())
+    g1_images = images.grad.clone()
+    D.zero_grad()
+    images.grad = None
+    # (ii) both terms: the adversarial term + the gradient penalty (second order through every conv)
     gp = gradient_penalty(images, logits)
     (logits.sum() + gp * GP_WEIGHT_IN_TEST).backward()
     names, norms, samples = grad_fingerprints(D.named_parameters())
     dout = dict(shapes=json.dumps(dshapes), logits=logits.detach().numpy(), gp=np.float64(gp.item()),
                 g_images_norm=np.float64(images.grad.double().norm().item()),
                 g_images_samples=strided(images.grad, 65536),
-                grad_names=names, grad_norms=norms, grad_samples=samples)
+                grad_names=names, grad_norms=norms, grad_samples=samples,
+                g1_images_norm=np.float64(g1_images.double().norm().item()),
+                g1_images_samples=strided(g1_images, 65536),
+                grad1_norms=norms1, grad1_samples=samples1)
     np.savez_compressed(os.path.join(GOLDEN_DIR, "gan_discriminator_256.npz"), **dout)
     print("discriminator 256: logits", logits.detach().numpy(), "gp", gp.item())
 

@@ -141,8 +141,10 @@ def generator_errors_256(device):
 
 
 def discriminator_errors_256(device):
+    """returns (scalar errors, first-order gradient table, adversarial + gradient-penalty table)"""
     from histogan_b200.gan import Discriminator
     from histogan_b200.trainer import gradient_penalty
+    from tests import step_checks as sc
     g = load("gan_discriminator_256.npz")
     D = Discriminator(mg.IMAGE_SIZE_L, network_capacity=mg.CAPACITY)
     shapes = json.loads(str(g["shapes"]))
@@ -152,9 +154,20 @@ def discriminator_errors_256(device):
     images = mg.gan_inputs(mg.IMAGE_SIZE_L, mg.B_L, seed=5)["images"].to(device).requires_grad_(True)
     logits, _ = D(images)
     e = {"logits": rel(logits, g["logits"])}
+    names = json.loads(str(g["grad_names"]))
+    params = dict(D.named_parameters())
+    # (i) first order
+    logits.sum().backward(retain_graph=True)
+    e["g1_images_norm"] = abs(images.grad.double().norm().item() - float(g["g1_images_norm"])) / float(g["g1_images_norm"])
+    e["g1_images_samples"] = rel(mg.strided(images.grad.cpu(), 65536), g["g1_images_samples"])
+    t1 = sc.compare_grads({k: params[k].grad for k in names}, names, g["grad1_norms"], g["grad1_samples"])
+    D.zero_grad()
+    images.grad = None
+    # (ii) + gradient penalty (histoGAN.py:156-163: second order through every conv)
     gp = gradient_penalty(images, logits)
     e["gp"] = abs(gp.item() - float(g["gp"])) / float(g["gp"])
     (logits.sum() + gp * mg.GP_WEIGHT_IN_TEST).backward()
     e["g_images_norm"] = abs(images.grad.double().norm().item() - float(g["g_images_norm"])) / float(g["g_images_norm"])
     e["g_images_samples"] = rel(mg.strided(images.grad.cpu(), 65536), g["g_images_samples"])
-    return e, _fingerprint_table(D.named_parameters(), g)
+    t2 = sc.compare_grads({k: params[k].grad for k in names}, names, g["grad_norms"], g["grad_samples"])
+    return e, t1, t2
