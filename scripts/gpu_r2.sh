@@ -4,7 +4,7 @@ TAG=${1:-r2a}
 mkdir -p gpurun_out
 rm -f gpurun_out/parity_records.jsonl
 if [[ " $* " == *" tests "* ]]; then
-  timeout 1500 python -m pytest tests -m gpu -q -x --timeout 600 > gpurun_out/pytest_gpu_$TAG.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu_$TAG.log 2>&1
   tail -25 gpurun_out/pytest_gpu_$TAG.log | cut -c1-300
 fi
 if [[ " $* " == *" smoke "* ]]; then
