@@ -77,6 +77,11 @@ _SIGNATURES = {
     "hg_upsample_modulate_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
     "hg_torgb_fwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_void_p]),
     "hg_torgb_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p]),
+    "hg_grouped_linear_fwd": (C.c_int, [C.c_int32] + [C.c_void_p] * 6 + [C.c_int32, C.c_int32, C.c_float,
+                                                                       C.c_float, C.c_void_p]),
+    "hg_grouped_linear_bwd": (C.c_int, [C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_int32, C.c_void_p]),
+    "hg_weight_sqsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "hg_demod_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int32] * 4 + [C.c_void_p]),
     "hg_upsample2x_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p]),
     "hg_diffgrad_step": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_float] * 5 + [C.c_void_p]),

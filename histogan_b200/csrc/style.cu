@@ -1,0 +1,430 @@
+// style.cu -- the "style path" of the generator: every small dense op between the latent
+// vectors and the modulated convolutions, as grouped skinny GEMMs with the batch (<= 32 rows)
+// mapped onto the lanes of a warp.  One launch handles ALL layers of a generator pass.
+//
+//   grouped_linear_fwd   y_g = act(x_g W_g^T + b_g) (+1)         GeneratorBlock.to_style1/2,
+//                                                                 RGBBlock.to_style (histoGAN.py:
+//                                                                 372,451,455,461-462,381) -> mod = style + 1
+//                        d_g = rsqrt((x_g^2) Wsq_g^T + eps)       Conv2DMod demodulation (:427-429)
+//   grouped_linear_bwd   gW_g = gy_g^T x_g, gb_g = sum_b gy_g, gx_g = gy_g W_g   (their adjoints)
+//   weight_sqsum         Wsq[co][ci] = sum_taps w[co][tap][ci]^2               (:428, shared by the batch)
+//   demod_bwd            adjoint of d = rsqrt(mod^2 Wsq^T + eps) given gd: adds the mod part to gmod and
+//                        the weight part 2 w gWsq straight into the weight gradient
+//
+// The reference evaluates these with per-sample weight tensors (B x Cout x Cin x k x k, :423-429);
+// here they are O(B (Cin + Cout) + Cout Cin) per layer.  All kernels are bound by reading the weight
+// matrices once (25 MB of to_style weights, 38 MB of Wsq per generator pass).
+#include "hg_common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace hg {
+
+constexpr int kMaxGroups = 24;
+constexpr int kKC = 512;                   // K chunk staged in shared memory
+constexpr int kXS = kKC + 4;               // row stride: conflict-free 128-bit reads for lane = batch row
+constexpr int kRows = 4;                   // output rows per warp step
+constexpr int kStyleThreads = 256;
+
+struct LinearGroups {
+  const float* x[kMaxGroups];              // [B][K]
+  const float* w[kMaxGroups];              // [J][K]
+  const float* bias[kMaxGroups];           // [J] or null
+  float* y[kMaxGroups];                    // [B][J]
+  int J[kMaxGroups];
+  int K[kMaxGroups];
+  int first_block[kMaxGroups + 1];         // prefix sum of ceil(J / rows_per_cta)
+  int count;
+  int B;
+  int flags;                               // HG_LIN_*
+  float slope, eps;
+};
+
+constexpr int kRowsPerCta = (kStyleThreads / 32) * kRows * 2;     // 64 rows: two steps per warp
+
+// lane = batch row b (B <= 32 per grid.y slice), warp = 4 output rows at a time.  x chunk in smem,
+// W rows read straight from global as warp-wide broadcasts (every lane the same 16 bytes).
+__global__ void __launch_bounds__(kStyleThreads)
+grouped_linear_fwd_kernel(const LinearGroups t) {
+  extern __shared__ __align__(16) float xs[];          // [32][kXS]
+  int gi = 0;
+  while (gi + 1 < t.count && (int)blockIdx.x >= t.first_block[gi + 1]) ++gi;
+  const int J = t.J[gi], K = t.K[gi];
+  const int r0 = (blockIdx.x - t.first_block[gi]) * kRowsPerCta;
+  const int b0 = blockIdx.y * 32;
+  const int nb = min(32, t.B - b0);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* __restrict__ x = t.x[gi] + (long long)b0 * K;
+  const float* __restrict__ w = t.w[gi];
+  const bool sq = t.flags & HG_LIN_SQUARE_INPUT;
+
+  float acc[2][kRows];
+#pragma unroll
+  for (int s = 0; s < 2; ++s)
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[s][r] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += kKC) {
+    const int kc = min(kKC, K - k0);                   // multiple of 4
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * (kc / 4); e += kStyleThreads) {
+      const int b = e / (kc / 4), q = e - b * (kc / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (b < nb) v = *reinterpret_cast<const float4*>(x + (long long)b * K + k0 + q * 4);
+      if (sq) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
+      *reinterpret_cast<float4*>(xs + b * kXS + q * 4) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int j0 = r0 + (s * (kStyleThreads / 32) + warp) * kRows;
+      if (j0 >= J) continue;
+      const float* wr[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) wr[r] = w + (long long)min(j0 + r, J - 1) * K + k0;
+      const float* xl = xs + lane * kXS;
+#pragma unroll 4
+      for (int k = 0; k < kc; k += 4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xl + k);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wr[r] + k));
+          acc[s][r] = fmaf(xv.x, wv.x, acc[s][r]);
+          acc[s][r] = fmaf(xv.y, wv.y, acc[s][r]);
+          acc[s][r] = fmaf(xv.z, wv.z, acc[s][r]);
+          acc[s][r] = fmaf(xv.w, wv.w, acc[s][r]);
+        }
+      }
+    }
+  }
+  if (lane >= nb) return;
+  float* __restrict__ y = t.y[gi] + (long long)(b0 + lane) * J;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int j0 = r0 + (s * (kStyleThreads / 32) + warp) * kRows;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int j = j0 + r;
+      if (j >= J) continue;
+      float v = acc[s][r];
+      if (t.bias[gi]) v += t.bias[gi][j];
+      if (t.flags & HG_LIN_RSQRT_EPS) v = rsqrtf(v + t.eps);
+      if (t.flags & HG_LIN_LRELU) v = v > 0.f ? v : v * t.slope;
+      if (t.flags & HG_LIN_ADD_ONE) v += 1.f;
+      y[j] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward --
+struct LinearBwdGroups {
+  const float* x[kMaxGroups];              // [B][K]
+  const float* w[kMaxGroups];              // [J][K]
+  const float* gy[kMaxGroups];             // [B][J]
+  float* gw[kMaxGroups];                   // [J][K]   (or null)
+  float* gb[kMaxGroups];                   // [J]      (or null)
+  float* gx[kMaxGroups];                   // [B][K]   (or null); accumulate: see flags
+  int J[kMaxGroups];
+  int K[kMaxGroups];
+  int first_block[kMaxGroups + 1];
+  int count;
+  int B;                                   // <= 32
+  int flags;
+};
+
+// gW[j][k..k+3] = sum_b gy[b][j] x[b][k..k+3];  gb[j] = sum_b gy[b][j].
+// CTA = 8 rows j x one 512-wide K chunk; thread = (row, float4 of k).  Write-bound.
+__global__ void __launch_bounds__(kStyleThreads)
+grouped_linear_wgrad_kernel(const LinearBwdGroups t) {
+  __shared__ float gys[8][32];
+  int gi = 0;
+  while (gi + 1 < t.count && (int)blockIdx.x >= t.first_block[gi + 1]) ++gi;
+  const int J = t.J[gi], K = t.K[gi];
+  const int kchunks = (K + kKC - 1) / kKC;
+  const int blk = blockIdx.x - t.first_block[gi];
+  const int j0 = (blk / kchunks) * 8, k0 = (blk % kchunks) * kKC;
+  const int B = t.B;
+  {
+    const int r = threadIdx.x >> 5, b = threadIdx.x & 31;
+    gys[r][b] = (b < B && j0 + r < J) ? t.gy[gi][(long long)b * J + j0 + r] : 0.f;
+  }
+  __syncthreads();
+  const float* __restrict__ x = t.x[gi];
+  const bool sq = t.flags & HG_LIN_SQUARE_INPUT;
+  const int q = threadIdx.x & 127, rh = threadIdx.x >> 7;          // 128 float4 columns x 2 row halves
+  const int k = k0 + q * 4;
+  if (k < K) {
+    float4 acc[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) acc[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+      float4 xv = __ldg(reinterpret_cast<const float4*>(x + (long long)b * K + k));
+      if (sq) { xv.x *= xv.x; xv.y *= xv.y; xv.z *= xv.z; xv.w *= xv.w; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const float g = gys[rh * 4 + r][b];
+        acc[r].x = fmaf(g, xv.x, acc[r].x); acc[r].y = fmaf(g, xv.y, acc[r].y);
+        acc[r].z = fmaf(g, xv.z, acc[r].z); acc[r].w = fmaf(g, xv.w, acc[r].w);
+      }
+    }
+    if (t.gw[gi]) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int j = j0 + rh * 4 + r;
+        if (j < J) *reinterpret_cast<float4*>(t.gw[gi] + (long long)j * K + k) = acc[r];
+      }
+    }
+  }
+  if (t.gb[gi] && k0 == 0 && threadIdx.x < 8 && j0 + threadIdx.x < J) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += gys[threadIdx.x][b];
+    t.gb[gi][j0 + threadIdx.x] = s;
+  }
+}
+
+// gx[b][k] (+)= post[b][k] * sum_j gy[b][j] W[j][k]:  CTA = one 32-wide K slab of one group, lanes = k,
+// the 8 warps split the J rows and are reduced in shared memory in a fixed order (deterministic).
+// post (HG_LIN_POST_2X): multiply by 2 x[b][k] (the demodulation's  d(mod^2)/d mod).
+__global__ void __launch_bounds__(kStyleThreads)
+grouped_linear_dgrad_kernel(const LinearBwdGroups t) {
+  extern __shared__ __align__(16) float sm[];          // gy tile [32 b][kJT + 1] then reduction [8][32 b][32 k]
+  constexpr int kJT = 256;
+  float* gys = sm;
+  float* red = sm + 32 * (kJT + 1);
+  int gi = 0;
+  while (gi + 1 < t.count && (int)blockIdx.x >= t.first_block[gi + 1]) ++gi;
+  const int J = t.J[gi], K = t.K[gi], B = t.B;
+  const int k = (blockIdx.x - t.first_block[gi]) * 32 + (threadIdx.x & 31);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ w = t.w[gi];
+  float acc[32];
+#pragma unroll
+  for (int b = 0; b < 32; ++b) acc[b] = 0.f;
+  for (int jt = 0; jt < J; jt += kJT) {
+    const int jn = min(kJT, J - jt);
+    __syncthreads();
+    for (int e = threadIdx.x; e < 32 * jn; e += kStyleThreads) {
+      const int b = e / jn, j = e - b * jn;
+      gys[b * (kJT + 1) + j] = b < B ? t.gy[gi][(long long)b * J + jt + j] : 0.f;
+    }
+    __syncthreads();
+    if (k < K) {
+      for (int j = warp; j < jn; j += 8) {
+        const float wv = __ldg(w + (long long)(jt + j) * K + k);
+#pragma unroll
+        for (int b = 0; b < 32; ++b) acc[b] = fmaf(gys[b * (kJT + 1) + j], wv, acc[b]);
+      }
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < 32; ++b) red[(warp * 32 + b) * 32 + lane] = acc[b];
+  __syncthreads();
+  // thread (b8 = warp, lane = k): rows b = warp, warp + 8, ...
+  if (k < K && t.gx[gi]) {
+    for (int b = warp; b < B; b += 8) {
+      float s = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) s += red[(wq * 32 + b) * 32 + lane];
+      const long long o = (long long)b * K + k;
+      if (t.flags & HG_LIN_POST_2X) s *= 2.f * t.x[gi][o];
+      if (t.flags & HG_LIN_ACCUMULATE) s += t.gx[gi][o];
+      t.gx[gi][o] = s;
+    }
+  }
+}
+
+// ------------------------------------------------------------ weight helpers --
+// Wsq[co][ci] = sum_tap w[co][tap][ci]^2  (w channels_last: [Cout][T][Cin]).  One pass over the weight.
+__global__ void __launch_bounds__(256)
+weight_sqsum_kernel(const float* __restrict__ w, float* __restrict__ wsq, int T, int Cin, long long n4) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;       // (co, ci4)
+  if (i >= n4) return;
+  const int q = Cin / 4;
+  const long long co = i / q;
+  const int ci = (int)(i - co * q) * 4;
+  const float* p = w + (co * T) * Cin + ci;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int tp = 0; tp < T; ++tp) {
+    const float4 v = *reinterpret_cast<const float4*>(p + (long long)tp * Cin);
+    s.x = fmaf(v.x, v.x, s.x); s.y = fmaf(v.y, v.y, s.y); s.z = fmaf(v.z, v.z, s.z); s.w = fmaf(v.w, v.w, s.w);
+  }
+  *reinterpret_cast<float4*>(wsq + co * Cin + ci) = s;
+}
+
+// dW[co][tap][ci] += 2 w[co][tap][ci] * sum_b t[b][co] mod[b][ci]^2    (t = -1/2 gd d^3)
+// thread = (co, ci4): the batch sum once, then the T taps.  CTA = 64 ci4 x 4 co.
+__global__ void __launch_bounds__(256)
+demod_weight_grad_kernel(float* __restrict__ dw, const float* __restrict__ w, const float* __restrict__ gd,
+                         const float* __restrict__ d, const float* __restrict__ mod, int B, int Cout,
+                         int T, int Cin) {
+  __shared__ float ts[4][64];
+  const int q = threadIdx.x & 63, r = threadIdx.x >> 6;
+  const int co = blockIdx.y * 4 + r;
+  const int ci = (blockIdx.x * 64 + q) * 4;
+  for (int e = threadIdx.x; e < 4 * B; e += 256) {
+    const int rr = e / B, b = e - rr * B;
+    const int c = blockIdx.y * 4 + rr;
+    float v = 0.f;
+    if (c < Cout) {
+      const float dv = d[(long long)b * Cout + c];
+      v = -0.5f * gd[(long long)b * Cout + c] * dv * dv * dv;
+    }
+    ts[rr][b] = v;
+  }
+  __syncthreads();
+  if (co >= Cout || ci >= Cin) return;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < B; ++b) {
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mod + (long long)b * Cin + ci));
+    const float tv = ts[r][b];
+    s.x = fmaf(tv, m.x * m.x, s.x); s.y = fmaf(tv, m.y * m.y, s.y);
+    s.z = fmaf(tv, m.z * m.z, s.z); s.w = fmaf(tv, m.w * m.w, s.w);
+  }
+  s.x *= 2.f; s.y *= 2.f; s.z *= 2.f; s.w *= 2.f;
+  const long long base = ((long long)co * T) * Cin + ci;
+  for (int tp = 0; tp < T; ++tp) {
+    const long long o = base + (long long)tp * Cin;
+    const float4 wv = *reinterpret_cast<const float4*>(w + o);
+    float4 g = *reinterpret_cast<const float4*>(dw + o);
+    g.x = fmaf(wv.x, s.x, g.x); g.y = fmaf(wv.y, s.y, g.y); g.z = fmaf(wv.z, s.z, g.z); g.w = fmaf(wv.w, s.w, g.w);
+    *reinterpret_cast<float4*>(dw + o) = g;
+  }
+}
+
+// t[b][co] = -1/2 gd d^3  (so that the demod adjoint w.r.t. mod is a grouped_linear_dgrad with W = Wsq)
+__global__ void demod_t_kernel(const float* __restrict__ gd, const float* __restrict__ d, float* __restrict__ t,
+                               int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) {
+    const float dv = d[i];
+    t[i] = -0.5f * gd[i] * dv * dv * dv;
+  }
+}
+
+static int check_groups(int count, int B, const int32_t* J, const int32_t* K) {
+  if (count < 0 || count > kMaxGroups) return set_error(HG_EINVAL, "group count %d not in [0, %d]", count, kMaxGroups);
+  if (B < 0) return set_error(HG_EINVAL, "negative batch");
+  for (int i = 0; i < count; ++i)
+    if (J[i] <= 0 || K[i] <= 0 || K[i] % 4) return set_error(HG_ENOSUP, "group %d: J=%d, K=%d (K %% 4 == 0 required)", i, J[i], K[i]);
+  return 0;
+}
+
+}  // namespace hg
+
+using namespace hg;
+
+extern "C" int hg_grouped_linear_fwd(int32_t count, const float* const* x, const float* const* w,
+                                     const float* const* bias, float* const* y, const int32_t* J,
+                                     const int32_t* K, int32_t B, int32_t flags, float slope, float eps,
+                                     hg_stream_t stream_) {
+  int rc = check_groups(count, B, J, K);
+  if (rc) return rc;
+  if (count == 0 || B == 0) return 0;
+  LinearGroups t{};
+  int blocks = 0;
+  for (int i = 0; i < count; ++i) {
+    if (!x[i] || !w[i] || !y[i]) return set_error(HG_EINVAL, "null pointer in group %d", i);
+    if (((uintptr_t)x[i] | (uintptr_t)w[i]) & 15) return set_error(HG_EINVAL, "group %d: x / W must be 16-byte aligned", i);
+    t.x[i] = x[i]; t.w[i] = w[i]; t.bias[i] = bias ? bias[i] : nullptr; t.y[i] = y[i];
+    t.J[i] = J[i]; t.K[i] = K[i];
+    t.first_block[i] = blocks;
+    blocks += (J[i] + kRowsPerCta - 1) / kRowsPerCta;
+  }
+  t.first_block[count] = blocks;
+  t.count = count; t.B = B; t.flags = flags; t.slope = slope; t.eps = eps;
+  const size_t smem = sizeof(float) * 32 * kXS;
+  static PerDeviceOnce once;
+  if (once.need()) {
+    HG_CUDA_OK(cudaFuncSetAttribute(grouped_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    once.mark();
+  }
+  grouped_linear_fwd_kernel<<<dim3(blocks, (B + 31) / 32), kStyleThreads, smem, (cudaStream_t)stream_>>>(t);
+  HG_LAUNCH_OK("grouped_linear_fwd_kernel");
+  return 0;
+}
+
+extern "C" int hg_grouped_linear_bwd(int32_t count, const float* const* x, const float* const* w,
+                                     const float* const* gy, float* const* gw, float* const* gb,
+                                     float* const* gx, const int32_t* J, const int32_t* K, int32_t B,
+                                     int32_t flags, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = check_groups(count, B, J, K);
+  if (rc) return rc;
+  if (count == 0 || B == 0) return 0;
+  if (B > 32) return set_error(HG_ENOSUP, "grouped_linear_bwd: batch %d > 32", B);
+  LinearBwdGroups t{};
+  bool any_w = false, any_x = false;
+  for (int i = 0; i < count; ++i) {
+    if (!x[i] || !w[i] || !gy[i]) return set_error(HG_EINVAL, "null pointer in group %d", i);
+    t.x[i] = x[i]; t.w[i] = w[i]; t.gy[i] = gy[i];
+    t.gw[i] = gw ? gw[i] : nullptr; t.gb[i] = gb ? gb[i] : nullptr; t.gx[i] = gx ? gx[i] : nullptr;
+    t.J[i] = J[i]; t.K[i] = K[i];
+    any_w |= t.gw[i] || t.gb[i];
+    any_x |= t.gx[i] != nullptr;
+  }
+  t.count = count; t.B = B; t.flags = flags;
+  if (any_w) {
+    int blocks = 0;
+    for (int i = 0; i < count; ++i) {
+      t.first_block[i] = blocks;
+      blocks += ((J[i] + 7) / 8) * ((K[i] + kKC - 1) / kKC);
+    }
+    t.first_block[count] = blocks;
+    grouped_linear_wgrad_kernel<<<blocks, kStyleThreads, 0, stream>>>(t);
+    HG_LAUNCH_OK("grouped_linear_wgrad_kernel");
+  }
+  if (any_x) {
+    int blocks = 0;
+    for (int i = 0; i < count; ++i) {
+      t.first_block[i] = blocks;
+      blocks += (K[i] + 31) / 32;
+    }
+    t.first_block[count] = blocks;
+    const size_t smem = sizeof(float) * (32 * (256 + 1) + 8 * 32 * 32);
+    static PerDeviceOnce once;
+    if (once.need()) {
+      HG_CUDA_OK(cudaFuncSetAttribute(grouped_linear_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      once.mark();
+    }
+    grouped_linear_dgrad_kernel<<<blocks, kStyleThreads, smem, stream>>>(t);
+    HG_LAUNCH_OK("grouped_linear_dgrad_kernel");
+  }
+  return 0;
+}
+
+extern "C" int hg_weight_sqsum(const float* w, float* wsq, int32_t Cout, int32_t T, int32_t Cin,
+                               hg_stream_t stream_) {
+  if (!w || !wsq) return set_error(HG_EINVAL, "null tensor pointer");
+  if (Cin % 4) return set_error(HG_ENOSUP, "Cin=%d must be a multiple of 4", Cin);
+  const long long n4 = (long long)Cout * (Cin / 4);
+  if (n4 <= 0) return 0;
+  weight_sqsum_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(w, wsq, T, Cin, n4);
+  HG_LAUNCH_OK("weight_sqsum_kernel");
+  return 0;
+}
+
+extern "C" int hg_demod_bwd(const float* gd, const float* d, const float* mod, const float* wsq,
+                            const float* w, float* gmod_accum, float* dw_accum, float* t_ws, int32_t B,
+                            int32_t Cout, int32_t T, int32_t Cin, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!gd || !d || !mod || !wsq || !t_ws) return set_error(HG_EINVAL, "null tensor pointer");
+  if (Cin % 4) return set_error(HG_ENOSUP, "Cin=%d must be a multiple of 4", Cin);
+  if (B <= 0) return 0;
+  if (B > 32) return set_error(HG_ENOSUP, "demod_bwd: batch %d > 32", B);
+  if (gmod_accum) {       // gmod[b][ci] += 2 mod[b][ci] sum_co t[b][co] Wsq[co][ci]
+    demod_t_kernel<<<(B * Cout + 255) / 256, 256, 0, stream>>>(gd, d, t_ws, B * Cout);
+    HG_LAUNCH_OK("demod_t_kernel");
+    const float* xs[1] = {mod};  const float* ws[1] = {wsq};  const float* gys[1] = {t_ws};
+    float* gxs[1] = {gmod_accum};
+    const int32_t Js[1] = {Cout}, Ks[1] = {Cin};
+    int rc = hg_grouped_linear_bwd(1, xs, ws, gys, nullptr, nullptr, gxs, Js, Ks, B,
+                                   HG_LIN_POST_2X | HG_LIN_ACCUMULATE, stream_);
+    if (rc) return rc;
+  }
+  if (dw_accum) {
+    if (!w) return set_error(HG_EINVAL, "dw_accum without w");
+    dim3 grid((Cin / 4 + 63) / 64, (Cout + 3) / 4);
+    demod_weight_grad_kernel<<<grid, 256, 0, stream>>>(dw_accum, w, gd, d, mod, B, Cout, T, Cin);
+    HG_LAUNCH_OK("demod_weight_grad_kernel");
+  }
+  return 0;
+}

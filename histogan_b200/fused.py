@@ -55,8 +55,13 @@ def _upsample_modulate_round(x, mod):
 
 
 class _ModConvLayer(torch.autograd.Function):
+    """wsq is None: `d` is a differentiable input (its gradient is returned).  wsq given:
+    d = rsqrt(mod^2 wsq^T + eps) was computed outside autograd (demod_all) and its dependence on
+    (mod, w) is differentiated here analytically: hg_demod_bwd adds d loss/d d * d d/d mod to the
+    modulation gradient and 2 w (sum_b t mod^2) to the weight gradient, in place."""
+
     @staticmethod
-    def forward(ctx, x, mod, w, d, inoise, nw, nb, slope, upsample, act=True):
+    def forward(ctx, x, mod, w, d, inoise, nw, nb, slope, upsample, act=True, wsq=None):
         k = w.shape[2]
         pad = (k - 1) // 2
         mod = mod.contiguous()
@@ -64,14 +69,14 @@ class _ModConvLayer(torch.autograd.Function):
         ctx.upsample = upsample
         y = _conv.conv2d_nhwc(xm, ops._packs.get(w, 0), 1, pad, cout=w.shape[0], scale=d,
                               noise=inoise, noise_w=nw, noise_b=nb, lrelu=act, slope=slope)
-        ctx.save_for_backward(x, xm, mod, w, d, inoise, nw, nb, y)
+        ctx.save_for_backward(x, xm, mod, w, d, inoise, nw, nb, y, wsq)
         ctx.slope = slope if act else 1.0       # no activation == LeakyReLU with slope 1
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, xm, mod, w, d, inoise, nw, nb, y = ctx.saved_tensors
+        x, xm, mod, w, d, inoise, nw, nb, y, wsq = ctx.saved_tensors
         lib = _lib.load()
         B, Cout, H, W = y.shape
         Cin, k = w.shape[1], w.shape[2]
@@ -107,7 +112,18 @@ class _ModConvLayer(torch.autograd.Function):
                 _lib.check(rc, "hg_modulate_bwd")
         if ctx.needs_input_grad[2]:
             dw = _conv.conv2d_wgrad_nhwc(dz, xm, k, 1, (k - 1) // 2)
-        return dx, gmod, dw, gd, None, gnw, gnb, None, None, None
+        if wsq is not None and d is not None:
+            analytic = dw is None or (dw.is_contiguous(memory_format=torch.channels_last) and
+                                      w.is_contiguous(memory_format=torch.channels_last))
+            assert analytic, "analytic demodulation needs channels_last weights"
+            t_ws = torch.empty_like(gd)
+            with torch.cuda.device(dev):
+                rc = lib.hg_demod_bwd(_lib.ptr(gd), _lib.ptr(d), _lib.ptr(mod), _lib.ptr(wsq), _lib.ptr(w),
+                                      _lib.ptr(gmod), _lib.ptr(dw), _lib.ptr(t_ws), B, Cout, k * k, Cin,
+                                      _st(dev))
+            _lib.check(rc, "hg_demod_bwd")
+            gd = None
+        return dx, gmod, dw, gd, None, gnw, gnb, None, None, None, None
 
 
 def fusable(x, w):
@@ -204,3 +220,140 @@ def upsample2x_planar(x):
     """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) of a planar (NCHW)
     float32 CUDA tensor -- RGBBlock's skip path (histoGAN.py:377-378,388-389)."""
     return _Upsample2xPlanar.apply(x)
+
+
+# ------------------------------------------------------------ style path (style.cu) ------
+LIN_ADD_ONE, LIN_LRELU, LIN_SQUARE_INPUT, LIN_RSQRT_EPS, LIN_POST_2X, LIN_ACCUMULATE = 1, 2, 4, 8, 16, 32
+
+
+def _ptr_table(ts):
+    return (C.c_void_p * len(ts))(*[t.data_ptr() if t is not None else None for t in ts])
+
+
+def _int_table(vs):
+    return (C.c_int32 * len(vs))(*[int(v) for v in vs])
+
+
+def grouped_linear(xs, ws, bs, flags=0, slope=0.2, eps=1e-8):
+    """raw hg_grouped_linear_fwd: y_g = f(x_g W_g^T + b_g) for every group in ONE launch.
+    xs[g] (B,K_g), ws[g] (J_g,K_g), bs[g] (J_g) or None -> list of (B,J_g)."""
+    lib = _lib.load()
+    B, dev = xs[0].shape[0], xs[0].device
+    ys = [torch.empty((B, w.shape[0]), dtype=torch.float32, device=dev) for w in ws]
+    with torch.cuda.device(dev):
+        rc = lib.hg_grouped_linear_fwd(len(xs), _ptr_table(xs), _ptr_table(ws), _ptr_table(bs), _ptr_table(ys),
+                                       _int_table([w.shape[0] for w in ws]), _int_table([w.shape[1] for w in ws]),
+                                       B, flags, float(slope), float(eps), _st(dev))
+    _lib.check(rc, "hg_grouped_linear_fwd")
+    return ys
+
+
+def grouped_linear_bwd(xs, ws, gys, gws, gbs, gxs, flags=0):
+    """raw hg_grouped_linear_bwd into the given output tensors (entries may be None)"""
+    lib = _lib.load()
+    B, dev = xs[0].shape[0], xs[0].device
+    with torch.cuda.device(dev):
+        rc = lib.hg_grouped_linear_bwd(len(xs), _ptr_table(xs), _ptr_table(ws), _ptr_table(gys),
+                                       _ptr_table(gws), _ptr_table(gbs), _ptr_table(gxs),
+                                       _int_table([w.shape[0] for w in ws]), _int_table([w.shape[1] for w in ws]),
+                                       B, flags, _st(dev))
+    _lib.check(rc, "hg_grouped_linear_bwd")
+
+
+MAX_GROUPS = 24          # style.cu kMaxGroups (a multiple of 3: a chunk holds whole blocks)
+
+
+class _GroupedStyleLinear(torch.autograd.Function):
+    """mods = [to_style_g(istyle[block_g]) + 1 for g]: the 3 Linears (to_style1, to_style2,
+    to_rgb.to_style; histoGAN.py:451,455,372) of EVERY generator block and the `y + 1` of
+    Conv2DMod (:423-425) in one launch; backward = one weight/bias-gradient launch + one
+    input-gradient launch."""
+
+    @staticmethod
+    def forward(ctx, per_block, block_of, *wb):
+        ws, bs = list(wb[0::2]), list(wb[1::2])
+        xs = [per_block[i] for i in block_of]
+        ctx.save_for_backward(per_block, *ws)
+        ctx.block_of = block_of
+        return tuple(grouped_linear(xs, ws, bs, LIN_ADD_ONE))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gys):
+        per_block, *ws = ctx.saved_tensors
+        block_of = ctx.block_of
+        xs = [per_block[i] for i in block_of]
+        B = per_block.shape[1]
+        gys = [g.contiguous() if g is not None else torch.zeros((B, w.shape[0]), device=w.device)
+               for g, w in zip(gys, ws)]
+        gws = [torch.empty_like(w) for w in ws]
+        gbs = [torch.empty((w.shape[0],), dtype=torch.float32, device=w.device) for w in ws]
+        gx = torch.empty((len(ws),) + tuple(per_block.shape[1:]), dtype=torch.float32, device=per_block.device)
+        grouped_linear_bwd(xs, ws, gys, gws, gbs, list(gx.unbind(0)), 0)
+        # the groups come as consecutive triples per block (style_mods): sum each triple, zero-pad
+        # the blocks this call did not touch (no index tensors: this runs under graph capture)
+        n = len(block_of) // 3
+        assert block_of == tuple(block_of[0] + i // 3 for i in range(3 * n)), block_of
+        g = gx.view(n, 3, *per_block.shape[1:]).sum(dim=1)
+        if n != per_block.shape[0]:
+            lo, hi = block_of[0], per_block.shape[0] - block_of[0] - n
+            g = torch.cat([g.new_zeros((lo,) + tuple(g.shape[1:])), g, g.new_zeros((hi,) + tuple(g.shape[1:]))])
+        out = [g, None]
+        for gw, gb in zip(gws, gbs):
+            out += [gw, gb]
+        return tuple(out)
+
+
+def style_mods(per_block, linears):
+    """per_block (L,B,latent); linears = [(block index, nn.Linear)]; returns [Linear(istyle)+1]."""
+    per_block = per_block.contiguous().float()
+    mods = []
+    for i in range(0, len(linears), MAX_GROUPS):
+        chunk = linears[i:i + MAX_GROUPS]
+        wb = []
+        for _, lin in chunk:
+            wb += [lin.weight, lin.bias]
+        mods += list(_GroupedStyleLinear.apply(per_block, tuple(b for b, _ in chunk), *wb))
+    return mods
+
+
+def weight_sqsum(w, out=None):
+    """Wsq (Cout,Cin) = sum_taps w^2 of a channels_last (Cout,Cin,k,k) weight (hg_weight_sqsum)"""
+    lib = _lib.load()
+    co, ci, kh, kw = w.shape
+    assert w.is_contiguous(memory_format=torch.channels_last) and ci % 4 == 0
+    if out is None:
+        out = torch.empty((co, ci), dtype=torch.float32, device=w.device)
+    with torch.cuda.device(w.device):
+        rc = lib.hg_weight_sqsum(_lib.ptr(w.detach()), _lib.ptr(out), co, kh * kw, ci, _st(w.device))
+    _lib.check(rc, "hg_weight_sqsum")
+    return out
+
+
+@torch.no_grad()
+def demod_all(mods, wsqs, eps=1e-8):
+    """d_g = rsqrt(mod_g^2 Wsq_g^T + eps) (histoGAN.py:427-429) for every conv layer of a generator
+    pass in one launch.  NOT differentiated by autograd: _ModConvLayer's backward carries the
+    dependence on (mod, w) analytically."""
+    out = []
+    for i in range(0, len(mods), MAX_GROUPS):
+        out += grouped_linear([m.detach() for m in mods[i:i + MAX_GROUPS]], wsqs[i:i + MAX_GROUPS],
+                              [None] * len(mods[i:i + MAX_GROUPS]), LIN_SQUARE_INPUT | LIN_RSQRT_EPS, eps=eps)
+    return out
+
+
+def mod_conv_layer_pre(x, mod, weight, d, wsq, inoise, noise_lin, slope=0.2, upsample=False, act=True):
+    """mod_conv_layer with the modulation (style + 1), the demodulation factor d and Wsq already
+    computed by style_mods / demod_all (one launch each for the whole generator)."""
+    nz = nw = nb = None
+    if inoise is not None:
+        nz = inoise.reshape(inoise.shape[0], inoise.shape[1], inoise.shape[2])
+        nw = noise_lin.weight.reshape(-1)
+        nb = noise_lin.bias
+    return _ModConvLayer.apply(x, mod, weight, d, nz, nw, nb, slope, bool(upsample), bool(act), wsq)
+
+
+def to_rgb_mod(x, mod, weight, prev_rgb):
+    """to_rgb with the modulation (style + 1) already formed"""
+    wmod = weight[None, :, :, 0, 0] * mod[:, None, :]                    # (B,3,C)
+    return _ToRGB.apply(x, wmod, prev_rgb)

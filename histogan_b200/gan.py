@@ -188,6 +188,29 @@ class GeneratorBlock(nn.Module):
             rgb = self.to_rgb.forward_(x, prev_rgb, to_rgb_style)
         return x, rgb
 
+    def style_path_ok(self, x_shape, inoise):
+        """can this block run on precomputed modulations (Generator.forward's fused path)?"""
+        up = 2 if self.upsample is not None else 1
+        w1, w2 = self.conv1.weight, self.conv2.weight
+        return (w1.is_cuda and all(c % 4 == 0 for c in (w1.shape[0], w1.shape[1], w2.shape[0]))
+                and w1.is_contiguous(memory_format=torch.channels_last)
+                and w2.is_contiguous(memory_format=torch.channels_last)
+                and self.to_rgb.conv.filters == 3 and x_shape[1] == w1.shape[1]
+                and x_shape[2] == x_shape[3] and inoise.shape[1] >= x_shape[2] * up
+                and inoise.shape[2] >= x_shape[3] * up)
+
+    def forward_mods(self, x, prev_rgb, mod1, d1, mod2, d2, mod_rgb, inoise):
+        """forward on precomputed modulations (style + 1) and demodulation factors"""
+        nz = inoise if inoise.is_contiguous() else inoise.contiguous()
+        wsq1, wsq2 = ops._packs.get(self.conv1.weight, 'wsq'), ops._packs.get(self.conv2.weight, 'wsq')
+        x = fused.mod_conv_layer_pre(x, mod1, self.conv1.weight, d1, wsq1, nz, self.to_noise1,
+                                     upsample=self.upsample is not None)
+        x = fused.mod_conv_layer_pre(x, mod2, self.conv2.weight, d2, wsq2, nz, self.to_noise2)
+        rgb = fused.to_rgb_mod(x, mod_rgb, self.to_rgb.conv.weight, prev_rgb)
+        if self.to_rgb.upsample is not None:
+            rgb = fused.upsample2x_planar(rgb)
+        return x, rgb
+
 
 class DiscriminatorBlock(nn.Module):
     """1x1 residual + 2 x [3x3 conv + LeakyReLU], sum, stride-2 3x3
@@ -292,9 +315,32 @@ class Generator(nn.Module):
         # blocks 0..L-3 take the mapped latent, the last two the histogram latent (:561-563)
         per_block = torch.cat((styles.transpose(0, 1), hists.transpose(0, 1)), dim=0)
         rgb = None
+        if USE_FUSED and x.is_cuda and self._style_path_ok(x.shape, input_noise):
+            # the 21 to_style Linears (+1) of all blocks in one launch, the 14 demodulation factors
+            # in a second one (fused.style_mods / demod_all); the blocks then run on those
+            linears = []
+            for i, b in enumerate(self.blocks):
+                linears += [(i, b.to_style1), (i, b.to_style2), (i, b.to_rgb.to_style)]
+            mods = fused.style_mods(per_block, linears)
+            conv_mods = [m for i in range(len(self.blocks)) for m in mods[3 * i:3 * i + 2]]
+            wsqs = [ops._packs.get(c.weight, 'wsq') for b in self.blocks for c in (b.conv1, b.conv2)]
+            ds = fused.demod_all(conv_mods, wsqs, EPS)
+            for i, block in enumerate(self.blocks):
+                x, rgb = block.forward_mods(x, rgb, mods[3 * i], ds[2 * i], mods[3 * i + 1], ds[2 * i + 1],
+                                            mods[3 * i + 2], input_noise)
+            return rgb
         for style, block in zip(per_block, self.blocks):
             x, rgb = block(x, rgb, style, input_noise)
         return rgb
+
+    def _style_path_ok(self, x_shape, inoise):
+        shape = list(x_shape)
+        for b in self.blocks:
+            if not b.style_path_ok(shape, inoise):
+                return False
+            up = 2 if b.upsample is not None else 1
+            shape = [shape[0], b.conv2.weight.shape[0], shape[2] * up, shape[3] * up]
+        return True
 
 
 class Discriminator(nn.Module):

@@ -106,6 +106,9 @@ class _PackCache:
     ATTR = "_hg_packed"
 
     def _pack(self, w, mode, out=None):
+        if mode == 'wsq':                   # (Cout,Cin) sum of squares over the taps: demodulation
+            from . import fused
+            return fused.weight_sqsum(w, out)
         if isinstance(mode, tuple):         # ('s2', py, px): one parity class of a stride-2 dgrad
             return _conv.pack_weight(_stride2_class_weight(w, mode[1], mode[2]), 0, out)
         return _conv.pack_weight(w, mode, out)     # zero-pads both extents to multiples of 32

@@ -252,6 +252,41 @@ int hg_torgb_bwd(const float* drgb, const float* x, const float* wmod, float* dx
 int hg_bias_act_bwd(const float* dy, const float* y, float* dpre, float* gb, int32_t B,
                     int32_t HW, int32_t C, float slope, hg_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * The generator's "style path" (csrc/style.cu): every small dense op between the latents
+ * and the modulated convolutions as GROUPED skinny GEMMs (batch <= 32 on the lanes of a warp),
+ * one launch for all layers of a generator pass.  HOST arrays of `count` (<= 24) DEVICE
+ * pointers / extents.  x_g (B,K_g), W_g (J_g,K_g) row-major, y_g (B,J_g); K_g % 4 == 0.
+ *   fwd:  y_g = f(x_g' W_g^T + bias_g),  x' = x or x^2 (HG_LIN_SQUARE_INPUT),
+ *         f = [rsqrt(. + eps)] -> [LeakyReLU(slope)] -> [+ 1]   in that order, as flagged:
+ *         to_style Linear + 1  (GeneratorBlock.to_style1/2, RGBBlock.to_style, histoGAN.py:372,451,455
+ *         and the `y + 1` of Conv2DMod :423-425):            HG_LIN_ADD_ONE
+ *         demodulation d = rsqrt(mod^2 Wsq^T + 1e-8) (:427-429): HG_LIN_SQUARE_INPUT | HG_LIN_RSQRT_EPS
+ *   bwd (B <= 32): gw_g = gy_g^T x_g', gb_g = sum_b gy_g, gx_g = gy_g W_g [* 2 x_g: HG_LIN_POST_2X]
+ *         [added to gx_g: HG_LIN_ACCUMULATE]; any of the three output tables / entries may be NULL.
+ *         Deterministic (no atomics).
+ * ------------------------------------------------------------------------ */
+enum { HG_LIN_ADD_ONE = 1, HG_LIN_LRELU = 2, HG_LIN_SQUARE_INPUT = 4, HG_LIN_RSQRT_EPS = 8,
+       HG_LIN_POST_2X = 16, HG_LIN_ACCUMULATE = 32 };
+int hg_grouped_linear_fwd(int32_t count, const float* const* x, const float* const* w,
+                          const float* const* bias, float* const* y, const int32_t* J,
+                          const int32_t* K, int32_t B, int32_t flags, float slope, float eps,
+                          hg_stream_t stream);
+int hg_grouped_linear_bwd(int32_t count, const float* const* x, const float* const* w,
+                          const float* const* gy, float* const* gw, float* const* gb,
+                          float* const* gx, const int32_t* J, const int32_t* K, int32_t B,
+                          int32_t flags, hg_stream_t stream);
+/* Wsq (Cout,Cin) = sum over the T = KH*KW taps of w^2, w stored channels_last [Cout][T][Cin]
+ * (the batch-independent part of the demodulation, histoGAN.py:428).                       */
+int hg_weight_sqsum(const float* w, float* wsq, int32_t Cout, int32_t T, int32_t Cin,
+                    hg_stream_t stream);
+/* adjoint of d = rsqrt(mod^2 Wsq^T + eps) given gd (B,Cout):  gmod_accum (B,Cin) += d d/d mod,
+ * dw_accum [Cout][T][Cin] += 2 w * (sum_b t mod^2), t = -1/2 gd d^3.  Either accumulator may be
+ * NULL.  t_ws: B*Cout floats of scratch.  B <= 32.                                          */
+int hg_demod_bwd(const float* gd, const float* d, const float* mod, const float* wsq,
+                 const float* w, float* gmod_accum, float* dw_accum, float* t_ws, int32_t B,
+                 int32_t Cout, int32_t T, int32_t Cin, hg_stream_t stream);
+
 /* 2x bilinear up-sampling (align_corners = False) of the planar RGB skip tensor of RGBBlock
  * (histoGAN/histoGAN.py:377-378,388-389).  backward == 0: x (planes,H,W) -> y (planes,2H,2W);
  * backward != 0: the adjoint, x = dy (planes,2H,2W) -> y = dx (planes,H,W).  H, W always name

@@ -118,3 +118,78 @@ def test_upsample2x_planar_matches_torch(cuda_device):
         (gx,) = torch.autograd.grad(y, x, g)
         (gr,) = torch.autograd.grad(ref, x, g)
         assert (gx - gr).abs().max().item() <= 1e-5 * gr.abs().max().item() + 1e-7, shape
+
+
+# ------------------------------------------------------------- style path (style.cu) -----
+
+def test_grouped_linear_forward_and_backward(cuda_device):
+    """hg_grouped_linear_fwd/bwd against torch: ragged groups, K over several shared-memory chunks,
+    J not a multiple of the CTA row count, every epilogue flag."""
+    import torch.nn.functional as F
+    from histogan_b200 import fused as fz
+    torch.manual_seed(0)
+    for B in (32, 5):
+        shapes = [(64, 512), (2048, 512), (100, 512), (3, 512), (130, 2048), (17, 36)]
+        xs = [torch.randn(B, k, device="cuda") for _, k in shapes]
+        ws = [torch.randn(j, k, device="cuda") / k ** 0.5 for j, k in shapes]
+        bs = [torch.randn(j, device="cuda") if i % 2 == 0 else None for i, (j, _) in enumerate(shapes)]
+        ys = fz.grouped_linear(xs, ws, bs, fz.LIN_ADD_ONE)
+        for x, w, b, y in zip(xs, ws, bs, ys):
+            ref = F.linear(x.double(), w.double(), b.double() if b is not None else None) + 1
+            assert (y.double() - ref).abs().max().item() < 2e-5, (B, tuple(w.shape))
+        ys = fz.grouped_linear(xs, ws, bs, fz.LIN_LRELU, slope=0.2)
+        for x, w, b, y in zip(xs, ws, bs, ys):
+            ref = F.leaky_relu(F.linear(x.double(), w.double(), b.double() if b is not None else None), 0.2)
+            assert (y.double() - ref).abs().max().item() < 2e-5
+        wp = [w.abs() for w in ws]
+        ys = fz.grouped_linear(xs, wp, [None] * len(xs), fz.LIN_SQUARE_INPUT | fz.LIN_RSQRT_EPS, eps=1e-8)
+        for x, w, y in zip(xs, wp, ys):
+            ref = torch.rsqrt(x.double().pow(2) @ w.double().t() + 1e-8)
+            assert ((y.double() - ref).abs() / ref).max().item() < 2e-5
+        # backward: gW, gb, gx (+ accumulate, + 2x post-factor)
+        gys = [torch.randn(B, j, device="cuda") for j, _ in shapes]
+        gws = [torch.empty_like(w) for w in ws]
+        gbs = [torch.empty(j, device="cuda") for j, _ in shapes]
+        gxs = [torch.empty_like(x) for x in xs]
+        fz.grouped_linear_bwd(xs, ws, gys, gws, gbs, gxs, 0)
+        for x, w, gy, gw, gb, gx in zip(xs, ws, gys, gws, gbs, gxs):
+            assert (gw.double() - gy.double().t() @ x.double()).abs().max().item() < 1e-4
+            assert (gb.double() - gy.double().sum(0)).abs().max().item() < 1e-4
+            assert (gx.double() - gy.double() @ w.double()).abs().max().item() < 1e-4
+        acc = [torch.randn_like(x) for x in xs]
+        acc0 = [a.clone() for a in acc]
+        fz.grouped_linear_bwd(xs, ws, gys, [None] * 6, [None] * 6, acc, fz.LIN_POST_2X | fz.LIN_ACCUMULATE)
+        for x, w, gy, a, a0 in zip(xs, ws, gys, acc, acc0):
+            ref = a0.double() + 2 * x.double() * (gy.double() @ w.double())
+            assert (a.double() - ref).abs().max().item() < 2e-4
+
+
+def test_analytic_demodulation_matches_autograd(cuda_device):
+    """_ModConvLayer with the demodulation differentiated analytically (hg_demod_bwd: style_mods /
+    demod_all path of Generator.forward) == the same layer with torch ops + autograd for
+    d = rsqrt((style+1)^2 Wsq^T + eps) (histoGAN.py:423-429)."""
+    from histogan_b200 import fused as fz, ops
+    torch.manual_seed(0)
+    for B, cin, cout, s, up in [(3, 64, 128, 8, False), (2, 32, 32, 16, True), (4, 128, 64, 4, False)]:
+        x = torch.randn(B, cin, s, s, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        style = (torch.randn(B, cin, device="cuda") * 0.5).requires_grad_(True)
+        w = torch.nn.Parameter((torch.randn(cout, cin, 3, 3, device="cuda") / (cin * 9) ** 0.5)
+                               .contiguous(memory_format=torch.channels_last))
+        lin = torch.nn.Linear(1, cout).cuda()
+        so = s * (2 if up else 1)
+        nz = torch.rand(B, so, so, 1, device="cuda")
+        gy = torch.randn(B, cout, so, so, device="cuda")
+
+        y0 = fz.mod_conv_layer(x, style, w, True, nz, lin, upsample=up)
+        g0 = torch.autograd.grad(y0, (x, style, w, lin.weight, lin.bias), gy)
+
+        mod = style + 1
+        wsq = ops._packs.get(w, 'wsq')
+        assert (wsq - w.detach().pow(2).sum(dim=(2, 3))).abs().max().item() < 1e-6
+        (d,) = fz.demod_all([mod], [wsq])
+        y1 = fz.mod_conv_layer_pre(x, mod, w, d, wsq, nz, lin, upsample=up)
+        g1 = torch.autograd.grad(y1, (x, style, w, lin.weight, lin.bias), gy)
+        assert (y1 - y0).abs().max().item() <= 2e-5 * y0.abs().max().item()
+        for name, a, b in zip(("x", "style", "w", "noise_w", "noise_b"), g1, g0):
+            err = ((a - b).norm() / b.norm()).item()
+            assert err < 2e-4, (name, err, (B, cin, cout, s, up))
