@@ -50,3 +50,88 @@ def worst(table):
 
 def rel(a, b):
     return abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
+
+
+def emulated_step_tables(case, golden=None):
+    """TF32 noise floor of ONE train step: the histogan_b200 modules (same algorithm as the CUDA path:
+    activation-side modulation, shared weights) evaluated on the CPU with torch stand-ins for the
+    conv primitives and TF32-rounded operands (tests/emulation.py), the histogram block replaced by
+    the CPU oracle; same weights / inputs / random draws as the reference golden.  Returns
+    (scalars, D-gradient table, G-gradient table) against that golden."""
+    import math
+    import torch.nn.functional as F
+    from histogan_b200 import gan
+    from histogan_b200.trainer import gradient_penalty, styles_def_to_tensor, EPS
+    from oracle import hist_oracle as ho
+    from oracle import train_oracle as to
+    from tests.emulation import emulated_conv
+    g = golden or load_golden()
+    S = mgs.IMAGE_SIZE
+    with torch.device("cpu"):
+        mods = {"G": gan.Generator(S, 512, mgs.CAPACITY), "D": gan.Discriminator(S, mgs.CAPACITY),
+                "S": gan.StyleVectorizer(512, 8), "H": gan.HistVectorizer(64, 512, 8)}
+
+    class _Box:
+        pass
+    box = _Box()
+    for k, m in mods.items():
+        setattr(box, k, m)
+    sd = mgs.seeded_gan_state(box)
+    for k, m in mods.items():
+        m.load_state_dict({n[len(k) + 1:]: v for n, v in sd.items() if n.startswith(k + ".")})
+    images, hists = mgs.step_inputs(case)
+    L = int(math.log2(S) - 1) - 2
+    mgs.seed_step(case)
+    dr = to.draw_step_inputs(mgs.BATCH, L, 512, S, path_penalty=case % 32 == 0)
+    Gm, Dm, Sm, Hm = mods["G"], mods["D"], mods["S"], mods["H"]
+
+    def w_of(style):
+        return styles_def_to_tensor([(Sm(z), n) for z, n in style])
+
+    def hw_of(h):
+        v = Hm(h).unsqueeze(1)
+        return torch.cat((v, v), dim=1)
+
+    with emulated_conv(round_operands=True):
+        with torch.no_grad():
+            fake = Gm(w_of(dr["d_style"]), hw_of(hists[0]), dr["d_noise"])
+        img = images.clone().requires_grad_(True)
+        fo, _ = Dm(fake)
+        ro, _ = Dm(img)
+        div = (F.relu(1 + ro) + F.relu(1 - fo)).mean()
+        loss, gp = div, None
+        if case % 4 == 0:
+            gp = gradient_penalty(img, ro)
+            loss = loss + gp
+        dgr = torch.autograd.grad(loss, list(Dm.parameters()))
+        w_styles, hw = w_of(dr["g_style"]), hw_of(hists[1])
+        fake = Gm(w_styles, hw, dr["g_noise"])
+        fo, _ = Dm(fake)
+        hl = ho.hellinger_loss(hists[1], ho.rgb_uv_hist(F.relu(fake), insz=150), mgs.ALPHA)
+        gl = fo.mean()
+        gen = gl + hl
+        pl = None
+        if case % 32 == 0:
+            std = 0.1 / (w_styles.std(dim=0, keepdim=True) + EPS)
+            pli = Gm(w_styles + dr["pl_noise"] / (std + EPS), hw, dr["g_noise"])
+            pll = ((pli - fake) ** 2).mean(dim=(1, 2, 3))
+            pl = pll.detach().mean().item()
+            gen = gen + (pll ** 2).mean()
+        gparams = list(Gm.parameters()) + list(Sm.parameters()) + list(Hm.parameters())
+        ggr = torch.autograd.grad(gen, gparams)
+    ref = g[f"c{case}_scalars"]
+    scal = {"d_loss": rel(div, ref["d_loss"]), "g_loss_abs_over_dscale": abs(gl.item() - ref["g_loss"]) / abs(ref["d_loss"]),
+            "h_loss": rel(hl, ref["h_loss"])}
+    if gp is not None:
+        scal["gp"] = rel(gp, ref["gp"])
+    if pl is not None:
+        scal["pl_mean"] = rel(0.01 * pl, ref["pl_mean"])
+    td = compare_grads(list(dgr), g["names_d"], g[f"c{case}_d_norms"], g[f"c{case}_d_samples"])
+    tg = compare_grads(list(ggr), g["names_g"], g[f"c{case}_g_norms"], g[f"c{case}_g_samples"])
+    return scal, td, tg
+
+
+def within_floor(tab, tab_emu, norm_margin=2e-2, cos_margin=1e-3):
+    """{tensor: (measured, floor)} for every tensor further from the golden than 2x the TF32 floor"""
+    return {k: (v, tab_emu[k]) for k, v in tab.items()
+            if v[0] > 2 * tab_emu[k][0] + norm_margin or (1 - v[1]) > 2 * (1 - tab_emu[k][1]) + cos_margin}

@@ -280,7 +280,36 @@ def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
 # phases (oracle/make_golden_step.py).  TF32 tolerances: activations-level quantities 2e-3;
 # per-tensor gradients: norm within 3 %, cosine >= 0.999 on the stored entries.
 
-LOSS_TOL, GRAD_NORM_TOL, GRAD_COS = 2e-3, 3e-2, 0.999
+import functools
+
+GRAD_COS = 0.999
+
+
+@functools.lru_cache(maxsize=None)
+def _floor(case):
+    """TF32 noise floor of the step on the CPU (tests/step_checks.emulated_step_tables)"""
+    from tests import step_checks as sc
+    scal, td, tg = sc.emulated_step_tables(case)
+    print(f"steps={case} CPU TF32 emulation vs reference: {scal}\n  D worst {sc.worst(td)}\n  G worst {sc.worst(tg)}")
+    return scal, td, tg
+
+
+def _check_scalars(case, got, ref):
+    """losses vs the reference Trainer: within 2x the TF32 floor (+1e-3).  g_loss = mean of B=2 D
+    logits of opposite sign: measured against the logit scale (|d_loss|), not its own value."""
+    from tests import step_checks as sc
+    from tests import parity
+    fl = _floor(case)[0]
+    err = {"d_loss": sc.rel(got["d_loss"], ref["d_loss"]),
+           "g_loss_abs_over_dscale": abs(got["g_loss"] - ref["g_loss"]) / abs(ref["d_loss"]),
+           "h_loss": sc.rel(got["h_loss"], ref["h_loss"])}
+    if case % 4 == 0:
+        err["gp"] = sc.rel(got["gp"], ref["gp"])
+    if case % 32 == 0:
+        err["pl_mean"] = sc.rel(got["pl_mean"], ref["pl_mean"])
+    parity.record(f"train_step[steps={case},losses]", {**err, **{"floor_" + k: v for k, v in fl.items()}})
+    bad = {k: (v, fl[k]) for k, v in err.items() if v > 2 * fl[k] + 1e-3}
+    assert not bad, bad
 
 
 def _golden_trainer(tmp_path, **kw):
@@ -304,8 +333,15 @@ def _check_grads(tag, grads, names, g, case, which):
     w = sc.worst(tab)
     print(f"{tag} steps={case} {which}-grads worst:", w)
     from tests import parity
-    parity.record(f"train_step[{tag},steps={case},{which}-grads]", {k: v[1] for k, v in w.items()})
-    bad = {k: v for k, v in tab.items() if v[0] > GRAD_NORM_TOL or v[1] < GRAD_COS}
+    floor = _floor(case)[1 if which == "d" else 2]
+    wf = sc.worst(floor)
+    parity.record(f"train_step[{tag},steps={case},{which}-grads]",
+                  {**{k: v[1] for k, v in w.items()}, **{"floor_" + k: v[1] for k, v in wf.items()}})
+    # per-tensor direction: cosine >= 0.999 wherever the TF32 arithmetic itself allows it ...
+    below = {k: (v[1], floor[k][1]) for k, v in tab.items() if v[1] < GRAD_COS}
+    assert all(f < GRAD_COS + 5e-4 for _, f in below.values()), below
+    # ... and everywhere no further from the reference than 2x the floor of the same algorithm
+    bad = sc.within_floor(tab, floor)
     assert not bad, bad
     return w
 
@@ -326,16 +362,7 @@ def test_train_step_matches_reference_trainer(case, tmp_path, cuda_device):
     got = {"d_loss": t.d_loss, "g_loss": t.g_loss, "h_loss": t.h_loss, "gp": t.last_gp_loss,
            "pl_mean": float(t.pl_mean)}
     print(f"steps={case} ours {got}\n          reference {ref}")
-    from tests import parity
-    parity.record(f"train_step[eager,steps={case},losses]",
-                  {k: sc.rel(got[k], ref[k]) for k in got if ref[k] == ref[k] and ref[k] != 0})
-    assert sc.rel(t.d_loss, ref["d_loss"]) < LOSS_TOL
-    assert sc.rel(t.g_loss, ref["g_loss"]) < LOSS_TOL
-    assert sc.rel(t.h_loss, ref["h_loss"]) < 1e-3
-    if case % 4 == 0:
-        assert sc.rel(t.last_gp_loss, ref["gp"]) < 5e-3
-    if case % 32 == 0:
-        assert sc.rel(t.pl_mean, ref["pl_mean"]) < 5e-3
+    _check_scalars(case, got, ref)
     _check_grads("eager", t.GAN.D_opt.recorded, g["names_d"], g, case, "d")
     _check_grads("eager", t.GAN.G_opt.recorded, g["names_g"], g, case, "g")
 
@@ -374,16 +401,12 @@ def test_graphed_phases_match_reference_trainer(case, tmp_path, cuda_device):
     gp_on, pl_on = case % 4 == 0, case % 32 == 0
     for _ in range(2):                                   # capture + replay, then a second replay
         div, gp = t._graphed(('D', gp_on), lambda: t._phase_d(gp_on), d_params)
-    assert sc.rel(div.item(), ref["d_loss"]) < LOSS_TOL
-    if gp_on:
-        assert sc.rel(gp.item(), ref["gp"]) < 5e-3
     _check_grads("graph", [p.grad for p in d_params], g["names_d"], g, case, "d")
     t._static['hists'].copy_(hists[1].cuda())
     t._static['mask'].copy_(fg['mask'])
     for _ in range(2):
         loss, hl, avg_pl = t._graphed(('G', mgs.ALPHA, pl_on), lambda: t._phase_g(mgs.ALPHA, pl_on), g_params)
-    assert sc.rel(loss.item(), ref["g_loss"]) < LOSS_TOL
-    assert sc.rel(hl.item(), ref["h_loss"]) < 1e-3
-    if pl_on:
-        assert sc.rel(0.01 * avg_pl.item(), ref["pl_mean"]) < 5e-3
+    _check_scalars(case, {"d_loss": div.item(), "g_loss": loss.item(), "h_loss": hl.item(),
+                          "gp": gp.item() if gp_on else 0.0,
+                          "pl_mean": 0.01 * avg_pl.item() if pl_on else 0.0}, ref)
     _check_grads("graph", [p.grad for p in g_params], g["names_g"], g, case, "g")
