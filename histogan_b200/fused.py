@@ -357,3 +357,39 @@ def to_rgb_mod(x, mod, weight, prev_rgb):
     """to_rgb with the modulation (style + 1) already formed"""
     wmod = weight[None, :, :, 0, 0] * mod[:, None, :]                    # (B,3,C)
     return _ToRGB.apply(x, wmod, prev_rgb)
+
+
+class _LinearLReLU(torch.autograd.Function):
+    """LeakyReLU(Linear(x)) of a skinny batch (<= 32 rows): StyleVectorizer / HistVectorizer layers
+    (histoGAN.py:335-365) on the grouped-linear kernels (weights read once, batch on the lanes)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, slope):
+        x = x.contiguous().float()
+        (y,) = grouped_linear([x], [w], [b], LIN_LRELU, slope=slope)
+        ctx.save_for_backward(x, w, y)
+        ctx.slope = slope
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, w, y = ctx.saved_tensors
+        gpre = torch.where(y > 0, gy, gy * ctx.slope).contiguous()
+        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        gb = torch.empty((w.shape[0],), dtype=torch.float32, device=w.device) if ctx.needs_input_grad[2] else None
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        grouped_linear_bwd([x], [w], [gpre], [gw], [gb], [gx], 0)
+        return gx, gw, gb, None
+
+
+def mlp_lrelu(x, linears, slope=0.2):
+    """[Linear -> LeakyReLU(slope)] x n on the grouped-linear kernels; x (B <= 32, K), K % 4 == 0"""
+    for lin in linears:
+        x = _LinearLReLU.apply(x, lin.weight, lin.bias, slope)
+    return x
+
+
+def mlp_ok(x, linears):
+    return (x.is_cuda and x.dim() == 2 and x.shape[0] <= 32 and x.dtype == torch.float32
+            and all(l.weight.shape[1] % 4 == 0 and l.weight.is_contiguous() for l in linears))

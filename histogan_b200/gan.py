@@ -275,7 +275,11 @@ class HistVectorizer(nn.Module):
         self.fcs = nn.Sequential(*layers)
 
     def forward(self, x):
-        return self.fcs(self.flatten(x))
+        x = self.flatten(x)
+        linears = [m for m in self.fcs if isinstance(m, nn.Linear)]
+        if USE_FUSED and fused.mlp_ok(x, linears):
+            return fused.mlp_lrelu(x, linears, 0.2)
+        return self.fcs(x)
 
 
 class StyleVectorizer(nn.Module):
@@ -289,6 +293,9 @@ class StyleVectorizer(nn.Module):
         self.net = nn.Sequential(*layers)
 
     def forward(self, x):
+        linears = [m for m in self.net if isinstance(m, nn.Linear)]
+        if USE_FUSED and fused.mlp_ok(x, linears):
+            return fused.mlp_lrelu(x, linears, 0.2)
         return self.net(x)
 
 

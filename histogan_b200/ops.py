@@ -37,7 +37,9 @@ from . import conv as _conv
 # 16-channel 256^2 conv takes exactly as long as the 32-channel one (the kernel is bound by the
 # number of TMA boxes / MMAs per tile, not by bytes) and the 4-channel image path is slower, so
 # D's 3/16-channel tensors are carried zero-padded to 32 channels.
-_CH = 32
+import os as _os
+
+_CH = int(_os.environ.get("HG_CH_PAD", "32"))      # 16 / 32 (experiment knob)
 
 
 def _round_up(n, m=_CH):
@@ -59,9 +61,15 @@ def round_tf32_nhwc(x: torch.Tensor, already_rounded: bool = False) -> torch.Ten
     if x.dtype != torch.float32:
         x = x.float()
     if Cp != Cc:
-        src = torch.zeros((B, Cp, H, W), dtype=torch.float32, device=x.device).contiguous(
-            memory_format=torch.channels_last)
-        src[:, :Cc] = x
+        # one pass: strided read of the Cc real channels, zero padding, rounding, NHWC write
+        out = torch.empty((B, Cp, H, W), dtype=torch.float32, device=x.device,
+                          memory_format=torch.channels_last)
+        if out.numel():
+            with torch.cuda.device(x.device):
+                rc = lib.hg_pad_round_nhwc(_lib.ptr(x), _lib.ptr(out), B, Cc, H, W, Cp, *x.stride(),
+                                           _lib.current_stream_ptr(x.device))
+            _lib.check(rc, "hg_pad_round_nhwc")
+        return out
     else:
         src = x if _is_nhwc(x) else x.contiguous(memory_format=torch.channels_last)
     out = torch.empty_like(src, memory_format=torch.channels_last)

@@ -287,6 +287,12 @@ int hg_demod_bwd(const float* gd, const float* d, const float* mod, const float*
                  const float* w, float* gmod_accum, float* dw_accum, float* t_ws, int32_t B,
                  int32_t Cout, int32_t T, int32_t Cin, hg_stream_t stream);
 
+/* Discriminator input staging (histoGAN/histoGAN.py:613-617): x (B,C,H,W) float32 with element
+ * strides sb,sc,sh,sw -> out NHWC (B,H,W,Cp), channels zero-padded to Cp (multiple of 4),
+ * TF32-rounded (round to nearest even), in one pass.                                   */
+int hg_pad_round_nhwc(const float* x, float* out, int32_t B, int32_t C, int32_t H, int32_t W,
+                      int32_t Cp, int64_t sb, int64_t sc, int64_t sh, int64_t sw, hg_stream_t stream);
+
 /* 2x bilinear up-sampling (align_corners = False) of the planar RGB skip tensor of RGBBlock
  * (histoGAN/histoGAN.py:377-378,388-389).  backward == 0: x (planes,H,W) -> y (planes,2H,2W);
  * backward != 0: the adjoint, x = dy (planes,2H,2W) -> y = dx (planes,H,W).  H, W always name

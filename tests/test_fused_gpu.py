@@ -193,3 +193,23 @@ def test_analytic_demodulation_matches_autograd(cuda_device):
         for name, a, b in zip(("x", "style", "w", "noise_w", "noise_b"), g1, g0):
             err = ((a - b).norm() / b.norm()).item()
             assert err < 2e-4, (name, err, (B, cin, cout, s, up))
+
+
+def test_style_and_hist_vectorizers_match_torch(cuda_device, monkeypatch):
+    """StyleVectorizer / HistVectorizer (histoGAN.py:335-365) on the grouped-linear kernels ==
+    the nn.Sequential of nn.Linear + LeakyReLU they wrap, values and every gradient."""
+    from histogan_b200 import gan
+    torch.manual_seed(0)
+    for mod, x in ((gan.StyleVectorizer(512, 8).cuda(), torch.randn(32, 512, device="cuda")),
+                   (gan.HistVectorizer(64, 512, 8).cuda(), torch.rand(7, 3, 64, 64, device="cuda"))):
+        x.requires_grad_(True)
+        y = mod(x)
+        g = torch.randn_like(y)
+        grads = torch.autograd.grad(y, [x] + list(mod.parameters()), g)
+        monkeypatch.setattr(gan, "USE_FUSED", False)
+        y0 = mod(x)
+        grads0 = torch.autograd.grad(y0, [x] + list(mod.parameters()), g)
+        monkeypatch.setattr(gan, "USE_FUSED", True)
+        assert ((y - y0).norm() / y0.norm()).item() < 1e-5
+        for a, b in zip(grads, grads0):
+            assert ((a - b).norm() / b.norm().clamp_min(1e-20)).item() < 1e-4
