@@ -54,6 +54,7 @@ struct ConvArgs {
   const float* residual;          // NHWC like y, added after the activation (or null)
   int noise_size;
   long long y_img, y_row, y_pix;  // output strides in floats (dense NHWC unless the caller says otherwise)
+  int desc_base_offset;           // HALO == 2: put (start >> 7) & 7 into the descriptor's base-offset field
   int ksplit;                     // > 1: the K loop (taps x 32-channel chunks) is split over ksplit work
                                   // items per output tile; each writes its raw partial sums to its own
                                   // slice of `partial`, conv_finish_kernel adds the slices in a fixed
@@ -76,10 +77,22 @@ constexpr int kHaloABytes = (8 + 2) * 16 * kBlockK * 4;   // 20 KB
 // re-fetch was 36 of 96 KB.
 constexpr int kResWBytes = 72 * 1024;
 
-template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
+// HALO == 2 (resident filter only; 8-wide x 16-tall pixel tiles): ONE activation box with a one-pixel
+// halo on every side -- {32 ch, 8+2, 16+2, 1} = 180 pixel rows = 22.5 KB -- serves all NINE taps.  The
+// 128 MMA rows are 16 groups of 8 consecutive pixels (one tile row each); inside the box consecutive
+// tile rows are 10 pixels = 1280 B apart, which is the descriptor's stride between 8-row groups (SBO),
+// and tap (kh, kw) is the same matrix started (kh*10 + kw) rows = (kh*10 + kw)*128 B further on.  TMA
+// and the tensor core both derive the 128B-swizzle phase from the shared-memory ADDRESS, so a start
+// that is not a multiple of the 1024 B swizzle atom addresses exactly the rows TMA wrote.  The
+// activation is fetched ONCE per tile (22.5 KB per 128 pixels instead of 3 x 20 KB): the 32/64-channel
+// 256^2 / 128^2 layers were bound by the bytes TMA moves into shared memory.
+constexpr int kHalo2ABytes = (16 + 2) * (8 + 2) * kBlockK * 4;     // 23040
+constexpr int kHalo2Stage = (kHalo2ABytes + 1023) / 1024 * 1024;   // ring slots stay 1024 B aligned
+
+template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false>
 struct ConvSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
-  static constexpr int kAStage = HALO ? kHaloABytes : kABytes;
+  static constexpr int kAStage = HALO == 2 ? kHalo2Stage : (HALO ? kHaloABytes : kABytes);
   static constexpr int kStageBytes = kAStage + (RESW ? 0 : (HALO ? 3 : 1) * kBBytes);
   static constexpr int kRing = STAGES * kStageBytes;
   static constexpr int kTotal = kRing + (RESW ? kResWBytes : 0) + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -89,11 +102,12 @@ struct ConvSmem {
 // together share A tiles through L2).  Two TMEM accumulator stages let the epilogue of
 // tile t overlap the main loop of tile t+1; the smem ring (STAGES deep) runs straight
 // through tile boundaries.
-template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
+template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
                  const ConvArgs a) {
-  static_assert(!RESW || HALO, "resident weights: halo variant only");
+  static_assert(!RESW || HALO, "resident weights: halo variants only");
+  static_assert(HALO != 2 || RESW, "single-box halo: resident weights only");
   using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW>;
   constexpr uint32_t kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
@@ -163,7 +177,15 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         const int tb_i = mt / (a.tiles_w * a.tiles_h);
         const int iw0 = tw_i * a.TW * a.stride - a.pad, ih0 = th_i * a.TH * a.stride - a.pad;
         const int b0 = tb_i * a.TB;
-        if (HALO) {
+        if (HALO == 2) {
+          for (int kc = 0; kc < a.kc_per_tap; ++kc) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sA = base + stage * SM::kStageBytes;
+            ptx::mbar_expect_tx(&full_bar[stage], kHalo2ABytes);
+            ptx::tma_load_4d(sA, &tmx, &full_bar[stage], kc * kBlockK, iw0, ih0, b0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+          }
+        } else if (HALO) {
           for (int kw = 0; kw < 3; ++kw) {
             for (int kc = 0; kc < a.kc_per_tap; ++kc) {
               ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -211,13 +233,33 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * kAccCols;
         const int ks = item % ksplit;
-        const int iters = HALO ? 3 * a.kc_per_tap
+        const int iters = HALO == 2 ? a.kc_per_tap : HALO ? 3 * a.kc_per_tap
                                : (int)((long long)(ks + 1) * total_kb / ksplit) -
                                      (int)((long long)ks * total_kb / ksplit);
         for (int kb = 0; kb < iters; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sA = ptx::smem_u32(base + stage * SM::kStageBytes);
+          if (HALO == 2) {
+            // kb = kc; all nine taps read the one box: start (kh*10 + kw) pixel rows in, 8-row
+            // groups 10 rows (1280 B) apart
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t a_addr = sA + (uint32_t)(((tap / 3) * 10 + tap % 3) * 128);
+              const uint64_t a_desc = ptx::make_smem_desc(a_addr, 16, 1280, ptx::kLayoutSW128) |
+                                      ((uint64_t)(a.desc_base_offset ? ((a_addr >> 7) & 7u) : 0u) << 49);
+              const uint64_t b_desc = ptx::make_smem_desc(
+                  ptx::smem_u32(wres) + (uint32_t)((tap * a.kc_per_tap + kb) * SM::kBBytes), 16, 1024,
+                  ptx::kLayoutSW128);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 8; ++k)
+                ptx::mma_tf32_ss(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc,
+                                 (uint32_t)((kb | tap | k) != 0));
+            }
+            ptx::tc_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
 #pragma unroll
           for (int kh = 0; kh < (HALO ? 3 : 1); ++kh) {
             // HALO: vertical tap kh = the same box 16 pixel rows (2 swizzle atoms) further down
@@ -500,7 +542,7 @@ static float* splitk_workspace(size_t bytes, cudaStream_t stream) {
   return p;
 }
 
-template <int BLOCK_N, int STAGES, bool HALO = false, bool RESW = false>
+template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false>
 static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
                        int m_tiles, cudaStream_t stream) {
   using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW>;
@@ -577,6 +619,20 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
   int TW = 1; while (TW < 16 && TW < OW) TW <<= 1;
   int TH = 1; while (TW * TH < kBlockM && TH < OH) TH <<= 1;
   int TB = kBlockM / (TW * TH);
+  // single-box halo (HALO == 2): 3x3 / stride 1, one n-tile, the whole filter resident (<= 72 KB, one
+  // 32-channel chunk per tap or two), enough tiles per CTA -- the 32/64-channel 256^2 / 128^2 layers
+  static const int halo2_mode = [] {
+    const char* e = getenv("HG_CONV_HALO2");        // 0 = off, 1 = on, 2 = on with the base-offset field
+    return e ? atoi(e) : 1;
+  }();
+  const int Kp_ = (p->Cin + 31) / 32 * 32, Np_ = (p->Cout + 31) / 32 * 32;
+  const int BN_ = (Np_ % 128 == 0) ? 128 : (Np_ % 64 == 0 ? 64 : 32);
+  const bool halo2 = halo2_mode > 0 && p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1 &&
+                     OW >= 8 && OH >= 16 && Np_ == BN_ && BN_ <= 64 &&
+                     9 * (Kp_ / kBlockK) * BN_ * kBlockK * 4 <= kResWBytes &&
+                     (long long)((OW + 7) / 8) * ((OH + 15) / 16) * p->B >= 4 * 148;
+  if (halo2) { TW = 8; TH = 16; TB = 1; }
+  a.desc_base_offset = halo2_mode == 2;
   a.TW = TW; a.TH = TH; a.TB = TB;
   a.tiles_w = (OW + TW - 1) / TW;
   a.tiles_h = (OH + TH - 1) / TH;
@@ -608,7 +664,7 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
 
   // 3x3 / stride 1 / 16x8 tiles within one image: fetch each activation box once per filter
   // COLUMN (with a one-row halo) instead of once per tap
-  const bool halo = p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1 && TW == 16 &&
+  const bool halo = !halo2 && p->KH == 3 && p->KW == 3 && p->stride == 1 && p->pad == 1 && TW == 16 &&
                     TH == 8 && TB == 1;
   // x: NHWC as a 4-D tensor {C, W, H, B}; strided boxes implement stride-2 convs
   alignas(64) CUtensorMap tmx, tmw;
@@ -616,8 +672,8 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     cuuint64_t dims[4] = {(cuuint64_t)p->Cin, (cuuint64_t)p->W, (cuuint64_t)p->H, (cuuint64_t)p->B};
     cuuint64_t strides[3] = {(cuuint64_t)p->Cin * 4, (cuuint64_t)p->W * p->Cin * 4,
                              (cuuint64_t)p->H * p->W * p->Cin * 4};
-    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(TW * p->stride),
-                         (cuuint32_t)(halo ? TH + 2 : TH * p->stride), (cuuint32_t)TB};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(halo2 ? TW + 2 : TW * p->stride),
+                         (cuuint32_t)(halo || halo2 ? TH + 2 : TH * p->stride), (cuuint32_t)TB};
     cuuint32_t estr[4] = {1, (cuuint32_t)p->stride, (cuuint32_t)p->stride, 1};
     int rc = encode_map(&tmx, x, 4, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
@@ -637,7 +693,7 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
       const char* e = getenv("HG_CONV_SPLITK");
       return e ? e[0] != '0' : kSplitKDefault;
     }();
-    if (enabled && !halo && dense_out && 2 * base <= sms && iters >= 32) {
+    if (enabled && !halo && !halo2 && dense_out && 2 * base <= sms && iters >= 32) {
       int ks = sms / base;
       if (ks > iters / 8) ks = iters / 8;
       if (ks >= 2) {
@@ -654,6 +710,11 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     int rc = encode_map(&tmw, w_packed, 2, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
   }
+  if (halo2) {
+    a.ksplit = 1;
+    if (BN == 64) return launch_conv<64, 5, 2, true>(tmx, tmw, a, m_tiles, stream);
+    return launch_conv<32, 5, 2, true>(tmx, tmw, a, m_tiles, stream);
+  }
   if (halo) {
     static const bool resw_enabled = [] {
       const char* e = getenv("HG_CONV_RESIDENT_W");
@@ -665,12 +726,12 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     // loss -- 242 -> 255 us -- so one chunk per tap only)
     if (resw_enabled && a.n_tiles == 1 && a.kc_per_tap == 1 &&
         9 * a.kc_per_tap * BN * kBlockK * 4 <= kResWBytes && m_tiles >= 4 * 148) {
-      if (BN == 64) return launch_conv<64, 6, true, true>(tmx, tmw, a, m_tiles, stream);
-      if (BN == 32) return launch_conv<32, 7, true, true>(tmx, tmw, a, m_tiles, stream);
+      if (BN == 64) return launch_conv<64, 6, 1, true>(tmx, tmw, a, m_tiles, stream);
+      if (BN == 32) return launch_conv<32, 7, 1, true>(tmx, tmw, a, m_tiles, stream);
     }
-    if (BN == 128) return launch_conv<128, 3, true>(tmx, tmw, a, m_tiles, stream);
-    if (BN == 64) return launch_conv<64, 4, true>(tmx, tmw, a, m_tiles, stream);
-    return launch_conv<32, 6, true>(tmx, tmw, a, m_tiles, stream);
+    if (BN == 128) return launch_conv<128, 3, 1>(tmx, tmw, a, m_tiles, stream);
+    if (BN == 64) return launch_conv<64, 4, 1>(tmx, tmw, a, m_tiles, stream);
+    return launch_conv<32, 6, 1>(tmx, tmw, a, m_tiles, stream);
   }
   if (BN == 128) return launch_conv<128, 6>(tmx, tmw, a, m_tiles, stream);
   if (BN == 64) return launch_conv<64, 8>(tmx, tmw, a, m_tiles, stream);

@@ -39,13 +39,31 @@ struct LinearGroups {
   float slope, eps;
 };
 
-constexpr int kRowsPerCta = (kStyleThreads / 32) * kRows * 2;     // 64 rows: two steps per warp
+constexpr int kRowsPerCta = 64;            // 8 warps x 4 row pairs
 
-// lane = batch row b (B <= 32 per grid.y slice), warp = 4 output rows at a time.  x chunk in smem,
-// W rows read straight from global as warp-wide broadcasts (every lane the same 16 bytes).
-__global__ void __launch_bounds__(kStyleThreads)
+// lane <- sum over the 32 lanes of acc[lane] (a 31-shuffle reduce-scatter instead of 32 x 5)
+__device__ __forceinline__ float warp_reduce_scatter(float (&acc)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? acc[i] : acc[i + s];
+      const float keep = up ? acc[i + s] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return acc[0];
+}
+
+// CTA = 64 output rows x (up to) 32 batch rows.  The x chunk (32 x 512) sits in shared memory; a
+// warp takes a PAIR of W rows at a time with the lanes across K (coalesced 512 B per load, all the
+// loads of the pair issued before the math), accumulates the 32 batch rows in registers and
+// finishes each row with a reduce-scatter so that lane b ends up holding y[b][row].
+__global__ void __launch_bounds__(kStyleThreads, 2)
 grouped_linear_fwd_kernel(const LinearGroups t) {
-  extern __shared__ __align__(16) float xs[];          // [32][kXS]
+  extern __shared__ __align__(16) float xs[];          // [32][kXS] then partial sums [64][32]
+  float* part = xs + 32 * kXS;
   int gi = 0;
   while (gi + 1 < t.count && (int)blockIdx.x >= t.first_block[gi + 1]) ++gi;
   const int J = t.J[gi], K = t.K[gi];
@@ -56,61 +74,66 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
   const float* __restrict__ x = t.x[gi] + (long long)b0 * K;
   const float* __restrict__ w = t.w[gi];
   const bool sq = t.flags & HG_LIN_SQUARE_INPUT;
-
-  float acc[2][kRows];
-#pragma unroll
-  for (int s = 0; s < 2; ++s)
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) acc[s][r] = 0.f;
+  const bool multi = K > kKC;                          // several K chunks: partial sums go through smem
 
   for (int k0 = 0; k0 < K; k0 += kKC) {
     const int kc = min(kKC, K - k0);                   // multiple of 4
     __syncthreads();
-    for (int e = threadIdx.x; e < 32 * (kc / 4); e += kStyleThreads) {
-      const int b = e / (kc / 4), q = e - b * (kc / 4);
+    for (int e = threadIdx.x; e < 32 * (kKC / 4); e += kStyleThreads) {
+      const int b = e / (kKC / 4), q = e - b * (kKC / 4);
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (b < nb) v = *reinterpret_cast<const float4*>(x + (long long)b * K + k0 + q * 4);
+      if (b < nb && q * 4 < kc) v = *reinterpret_cast<const float4*>(x + (long long)b * K + k0 + q * 4);
       if (sq) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
       *reinterpret_cast<float4*>(xs + b * kXS + q * 4) = v;
     }
     __syncthreads();
+#pragma unroll 1
+    for (int pr = 0; pr < 4; ++pr) {
+      const int j0 = r0 + (warp * 4 + pr) * 2;         // rows j0, j0 + 1
+      if (j0 >= J) break;
+      const float* w0 = w + (long long)j0 * K + k0;
+      const float* w1 = w + (long long)min(j0 + 1, J - 1) * K + k0;
+      float4 wa[4], wb[4];
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      const int j0 = r0 + (s * (kStyleThreads / 32) + warp) * kRows;
-      if (j0 >= J) continue;
-      const float* wr[kRows];
-#pragma unroll
-      for (int r = 0; r < kRows; ++r) wr[r] = w + (long long)min(j0 + r, J - 1) * K + k0;
-      const float* xl = xs + lane * kXS;
-#pragma unroll 4
-      for (int k = 0; k < kc; k += 4) {
-        const float4 xv = *reinterpret_cast<const float4*>(xl + k);
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) {
-          const float4 wv = __ldg(reinterpret_cast<const float4*>(wr[r] + k));
-          acc[s][r] = fmaf(xv.x, wv.x, acc[s][r]);
-          acc[s][r] = fmaf(xv.y, wv.y, acc[s][r]);
-          acc[s][r] = fmaf(xv.z, wv.z, acc[s][r]);
-          acc[s][r] = fmaf(xv.w, wv.w, acc[s][r]);
-        }
+      for (int i = 0; i < 4; ++i) {
+        const int k = i * 128 + lane * 4;
+        const bool ok = k < kc;
+        wa[i] = ok ? __ldg(reinterpret_cast<const float4*>(w0 + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wb[i] = ok ? __ldg(reinterpret_cast<const float4*>(w1 + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-    }
-  }
-  if (lane >= nb) return;
-  float* __restrict__ y = t.y[gi] + (long long)(b0 + lane) * J;
+      float a0[32], a1[32];
 #pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int j0 = r0 + (s * (kStyleThreads / 32) + warp) * kRows;
+      for (int b = 0; b < 32; ++b) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) {
-      const int j = j0 + r;
-      if (j >= J) continue;
-      float v = acc[s][r];
-      if (t.bias[gi]) v += t.bias[gi][j];
-      if (t.flags & HG_LIN_RSQRT_EPS) v = rsqrtf(v + t.eps);
-      if (t.flags & HG_LIN_LRELU) v = v > 0.f ? v : v * t.slope;
-      if (t.flags & HG_LIN_ADD_ONE) v += 1.f;
-      y[j] = v;
+        for (int i = 0; i < 4; ++i) {
+          const float4 xv = *reinterpret_cast<const float4*>(xs + b * kXS + i * 128 + lane * 4);
+          s0 = fmaf(xv.x, wa[i].x, s0); s0 = fmaf(xv.y, wa[i].y, s0);
+          s0 = fmaf(xv.z, wa[i].z, s0); s0 = fmaf(xv.w, wa[i].w, s0);
+          s1 = fmaf(xv.x, wb[i].x, s1); s1 = fmaf(xv.y, wb[i].y, s1);
+          s1 = fmaf(xv.z, wb[i].z, s1); s1 = fmaf(xv.w, wb[i].w, s1);
+        }
+        a0[b] = s0; a1[b] = s1;
+      }
+      float v0 = warp_reduce_scatter(a0, lane);        // lane b: row j0
+      float v1 = warp_reduce_scatter(a1, lane);        //         row j0 + 1
+      float* pp = part + ((warp * 4 + pr) * 2) * 32 + lane;
+      if (multi) {
+        if (k0 > 0) { v0 += pp[0]; v1 += pp[32]; }
+        if (k0 + kKC < K) { pp[0] = v0; pp[32] = v1; continue; }
+      }
+      if (lane >= nb) continue;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int j = j0 + r;
+        if (j >= J) break;
+        float v = r ? v1 : v0;
+        if (t.bias[gi]) v += t.bias[gi][j];
+        if (t.flags & HG_LIN_RSQRT_EPS) v = rsqrtf(v + t.eps);
+        if (t.flags & HG_LIN_LRELU) v = v > 0.f ? v : v * t.slope;
+        if (t.flags & HG_LIN_ADD_ONE) v += 1.f;
+        t.y[gi][(long long)(b0 + lane) * J + j] = v;
+      }
     }
   }
 }
@@ -208,10 +231,18 @@ grouped_linear_dgrad_kernel(const LinearBwdGroups t) {
     }
     __syncthreads();
     if (k < K) {
-      for (int j = warp; j < jn; j += 8) {
-        const float wv = __ldg(w + (long long)(jt + j) * K + k);
+      // 8 rows per step, their loads issued together (one 128 B line per row and warp)
+      for (int j = warp; j < jn; j += 64) {
+        float wv[8];
 #pragma unroll
-        for (int b = 0; b < 32; ++b) acc[b] = fmaf(gys[b * (kJT + 1) + j], wv, acc[b]);
+        for (int u = 0; u < 8; ++u)
+          wv[u] = j + 8 * u < jn ? __ldg(w + (long long)(jt + j + 8 * u) * K + k) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int jj = min(j + 8 * u, jn - 1);
+#pragma unroll
+          for (int b = 0; b < 32; ++b) acc[b] = fmaf(gys[b * (kJT + 1) + jj], wv[u], acc[b]);
+        }
       }
     }
   }
@@ -331,7 +362,7 @@ extern "C" int hg_grouped_linear_fwd(int32_t count, const float* const* x, const
   }
   t.first_block[count] = blocks;
   t.count = count; t.B = B; t.flags = flags; t.slope = slope; t.eps = eps;
-  const size_t smem = sizeof(float) * 32 * kXS;
+  const size_t smem = sizeof(float) * (32 * kXS + kRowsPerCta * 32);
   static PerDeviceOnce once;
   if (once.need()) {
     HG_CUDA_OK(cudaFuncSetAttribute(grouped_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -559,8 +559,16 @@ class Trainer:
             fake = GAN.G(self._mixed_styles(z1, z2, st['mask']), torch.cat((h_w, h_w), dim=1), inoise)
         # a fresh leaf over the static buffer: its .grad is a graph-local temporary
         images = st['images'].detach().requires_grad_(True) if apply_gp else st['images']
-        fake_out, _ = GAN.D(fake)
-        real_out, _ = GAN.D(images)
+        if apply_gp:
+            fake_out, _ = GAN.D(fake)
+            real_out, _ = GAN.D(images)
+        else:
+            # one discriminator pass over [fake; real] (the same per-sample arithmetic, histoGAN.py
+            # :904-911): half the launches, and D's small-resolution layers run 2x fuller tiles.
+            # Steps with the gradient penalty keep two passes: its d D(real)/d real backward would
+            # otherwise drag the fake half along.
+            both, _ = GAN.D(torch.cat((fake, images), dim=0))
+            fake_out, real_out = both[:fake.shape[0]], both[fake.shape[0]:]
         divergence = (F.relu(1 + real_out) + F.relu(1 - fake_out)).mean()
         loss, gp = divergence, None
         if apply_gp:

@@ -27,6 +27,10 @@ CASES = [
     (4, 64, 128, 160, 32, 3, 1),   # resident filter, two k-chunks per tap
     (4, 32, 128, 160, 64, 3, 1),   # resident filter, BLOCK_N = 64
     (5, 20, 120, 136, 24, 3, 1),   # resident filter with channel tails and ragged tiles
+    (5, 32, 128, 128, 32, 3, 1),   # single-box halo (8x16 tiles, all nine taps from one TMA box)
+    (3, 64, 160, 152, 32, 3, 1),   # ... two k-chunks per tap, ragged tiles in both directions
+    (6, 32, 96, 104, 64, 3, 1),    # ... BLOCK_N = 64
+    (32, 16, 64, 64, 16, 3, 1),    # ... channel tails (D block 0 shape family)
 ]
 
 
