@@ -86,6 +86,7 @@ _SIGNATURES = {
     "hg_upsample2x_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p]),
     "hg_diffgrad_step": (C.c_int, [C.c_int32] + [C.c_void_p] * 7 + [C.c_float] * 5 + [C.c_void_p]),
+    "hg_ema_update": (C.c_int, [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "hg_bias_act_bwd": (C.c_int, [C.c_void_p] * 4 + [C.c_int32] * 3 + [C.c_float, C.c_void_p]),
     "hg_pack_conv_weight": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_void_p]),

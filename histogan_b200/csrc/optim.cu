@@ -95,6 +95,46 @@ diffgrad_kernel(const DiffGradBatch t, float beta1, float beta2, float eps, floa
   }
 }
 
+// ---------------------------------------------------------------------------
+// Exponential moving average of the generator-side weights (HistoGAN.EMA, histoGAN/histoGAN.py
+// :698-707, every 10th step after step 20 000):  ma = beta * ma + (1 - beta) * cur  for up to
+// kMaxTensors tensors per launch.  The reference loops over ~150 parameters with 3 element-wise
+// launches each; this is one pass (2 reads + 1 write per element).
+struct EmaBatch {
+  float* ma[kMaxTensors];
+  const float* cur[kMaxTensors];
+  long long n[kMaxTensors];
+  int first_block[kMaxTensors + 1];
+  int count;
+};
+
+__global__ void __launch_bounds__(256)
+ema_kernel(const EmaBatch t, float beta) {
+  int ti = 0;
+  while (ti + 1 < t.count && (int)blockIdx.x >= t.first_block[ti + 1]) ++ti;
+  const long long base = (long long)(blockIdx.x - t.first_block[ti]) * kChunk;
+  const long long end = min(t.n[ti], base + kChunk);
+  float* __restrict__ ma = t.ma[ti];
+  const float* __restrict__ cur = t.cur[ti];
+  const float omb = 1.f - beta;
+  const bool vec = (((uintptr_t)ma | (uintptr_t)cur) & 15) == 0;
+  long long i = base + (vec ? threadIdx.x * 4 : threadIdx.x);
+  if (vec) {
+    for (; i + 3 < end; i += 256 * 4) {
+      float4 m = *reinterpret_cast<const float4*>(ma + i);
+      const float4 c = *reinterpret_cast<const float4*>(cur + i);
+      // same expression as EMA.update_average (:69): old * beta + (1 - beta) * new
+      m.x = m.x * beta + omb * c.x; m.y = m.y * beta + omb * c.y;
+      m.z = m.z * beta + omb * c.z; m.w = m.w * beta + omb * c.w;
+      *reinterpret_cast<float4*>(ma + i) = m;
+    }
+    if (i < end)
+      for (long long j = i; j < end; ++j) ma[j] = ma[j] * beta + omb * cur[j];
+  } else {
+    for (; i < end; i += 256) ma[i] = ma[i] * beta + omb * cur[i];
+  }
+}
+
 }  // namespace hg
 
 using namespace hg;
@@ -132,6 +172,32 @@ extern "C" int hg_diffgrad_step(int32_t count, float* const* p, const float* con
     else
       diffgrad_kernel<true><<<blocks, 256, 0, stream>>>(b, beta1, beta2, eps, step_size, weight_decay);
     HG_LAUNCH_OK("diffgrad_kernel");
+  }
+  return 0;
+}
+
+extern "C" int hg_ema_update(int32_t count, float* const* ma, const float* const* cur,
+                             const int64_t* numel, float beta, hg_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (count < 0 || (count > 0 && (!ma || !cur || !numel))) return set_error(HG_EINVAL, "null pointer table");
+  int i = 0;
+  while (i < count) {
+    EmaBatch b;
+    b.count = 0;
+    int blocks = 0;
+    while (i < count && b.count < kMaxTensors) {
+      if (numel[i] > 0) {
+        const int k = b.count++;
+        b.ma[k] = ma[i]; b.cur[k] = cur[i]; b.n[k] = numel[i];
+        b.first_block[k] = blocks;
+        blocks += (int)((numel[i] + kChunk - 1) / kChunk);
+      }
+      ++i;
+    }
+    b.first_block[b.count] = blocks;
+    if (b.count == 0) continue;
+    ema_kernel<<<blocks, 256, 0, stream>>>(b, beta);
+    HG_LAUNCH_OK("ema_kernel");
   }
   return 0;
 }

@@ -172,11 +172,32 @@ class HistoGAN(nn.Module):
 
     @torch.no_grad()
     def EMA(self):
+        """SE/HE/GE <- beta * (SE/HE/GE) + (1 - beta) * (S/H/G)  (histoGAN.py:698-707) as ONE fused
+        multi-tensor kernel (hg_ema_update): a single pass over the 100 M generator-side weights."""
+        import ctypes as C
+        from . import _lib
         beta = self.ema_updater.beta
+        ma_p, cur_p = [], []
         for ma, cur in ((self.SE, self.S), (self.HE, self.H), (self.GE, self.G)):
-            ma_p, cur_p = list(ma.parameters()), list(cur.parameters())
-            torch._foreach_mul_(ma_p, beta)
-            torch._foreach_add_(ma_p, cur_p, alpha=1 - beta)
+            for a, c in zip(ma.parameters(), cur.parameters()):
+                same = a.shape == c.shape and (a.stride() == c.stride()) and a.is_cuda and \
+                    a.dtype == c.dtype == torch.float32 and a.is_non_overlapping_and_dense()
+                if same:
+                    ma_p.append(a); cur_p.append(c)
+                else:               # layouts differ (e.g. a state_dict loaded into another format)
+                    a.mul_(beta).add_(c, alpha=1 - beta)
+        if not ma_p:
+            return
+        n = len(ma_p)
+        arr = C.c_void_p * n
+        dev = ma_p[0].device
+        with torch.cuda.device(dev):
+            rc = _lib.load().hg_ema_update(n, arr(*[t.data_ptr() for t in ma_p]),
+                                           arr(*[t.data_ptr() for t in cur_p]),
+                                           (C.c_int64 * n)(*[t.numel() for t in ma_p]), float(beta),
+                                           _lib.current_stream_ptr(dev))
+        _lib.check(rc, "hg_ema_update")
+        torch.autograd.graph.increment_version(ma_p)
 
     def reset_parameter_averaging(self):
         self.SE.load_state_dict(self.S.state_dict())

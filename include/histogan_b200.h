@@ -314,6 +314,12 @@ int hg_diffgrad_step(int32_t count, float* const* p, const float* const* g, floa
                      const int64_t* numel, float beta1, float beta2, float eps, float step_size,
                      float weight_decay, hg_stream_t stream);
 
+/* Fused multi-tensor exponential moving average (HistoGAN.EMA, histoGAN/histoGAN.py:62-69,
+ * 698-707): ma_i = beta * ma_i + (1 - beta) * cur_i for `count` tensors (HOST arrays of DEVICE
+ * pointers), one pass.                                                                     */
+int hg_ema_update(int32_t count, float* const* ma, const float* const* cur, const int64_t* numel,
+                  float beta, hg_stream_t stream);
+
 /* ------------------------------------------------------------------------ *
  * ReHistoGAN recolouring step (ReHistoGAN/rehistoGAN.py), SURVEY 8f-1.
  * ------------------------------------------------------------------------ */

@@ -129,6 +129,28 @@ def test_fused_diffgrad_matches_scalar_oracle(cuda_device):
     assert err < 5e-7          # fp32 state vs float64 oracle after 6 steps of |dp| <= 2e-4
 
 
+def test_fused_ema_matches_reference_formula(cuda_device):
+    """HistoGAN.EMA (hg_ema_update) == EMA.update_average applied per parameter as the reference
+    does (histoGAN.py:62-69,698-707), including channels_last conv weights and odd sizes."""
+    from histogan_b200.trainer import HistoGAN
+    torch.manual_seed(0)
+    gan = HistoGAN(image_size=32, network_capacity=16)
+    with torch.no_grad():
+        for p in list(gan.G.parameters()) + list(gan.S.parameters()) + list(gan.H.parameters()):
+            p.add_(torch.randn_like(p) * 0.1)
+    want = {}
+    for ma, cur in ((gan.SE, gan.S), (gan.HE, gan.H), (gan.GE, gan.G)):
+        for (k, a), c in zip(ma.named_parameters(), cur.parameters()):
+            want[id(a)] = (k, a.detach().clone() * 0.995 + (1 - 0.995) * c.detach())
+    gan.EMA()
+    for ma in (gan.SE, gan.HE, gan.GE):
+        for a in ma.parameters():
+            k, ref = want[id(a)]
+            assert torch.allclose(a.detach(), ref, rtol=1e-6, atol=1e-8), k
+    # the optimised weights themselves are untouched
+    assert not torch.equal(gan.GE.initial_block, gan.G.initial_block)
+
+
 def test_optimizer_step_invalidates_packed_weights(cuda_device):
     from histogan_b200 import ops
     from histogan_b200.optim import DiffGrad
