@@ -139,7 +139,7 @@ def conv2d_nhwc(x: torch.Tensor, w_packed: torch.Tensor, stride: int = 1, pad: i
 
 
 def conv2d_wgrad_nhwc(dy: torch.Tensor, x: torch.Tensor, ksize: int, stride: int = 1,
-                      pad: int = 1) -> torch.Tensor:
+                      pad: int = 1, out: torch.Tensor = None) -> torch.Tensor:
     """dW (Cout,Cin,k,k) from dy (B,Cout,OH,OW) and x (B,Cin,H,W), both channels_last float32
     (hg_conv2d_wgrad).  The result is stored channels_last -- the kernel's own
     [Cout][k][k][Cin] output viewed as (Cout,Cin,k,k) -- which is also how the modules store
@@ -150,7 +150,14 @@ def conv2d_wgrad_nhwc(dy: torch.Tensor, x: torch.Tensor, ksize: int, stride: int
     B, Cin, H, W = x.shape
     _, Cout, OH, OW = dy.shape
     p = _lib.ConvParams(B, H, W, Cin, Cout, ksize, ksize, stride, pad, OH, OW)
-    dwp = torch.empty((Cout, ksize, ksize, _up32(Cin)), dtype=torch.float32, device=x.device)
+    # `out`: a (Cout,Cin,k,k) channels_last tensor to write into (a slot of the trainer's flat
+    # gradient arena); usable when the kernel's [Cout][k][k][Cin_p] output has no channel padding
+    dwp = None
+    if out is not None and _up32(Cin) == Cin and tuple(out.shape) == (Cout, Cin, ksize, ksize) \
+            and out.is_contiguous(memory_format=torch.channels_last) and out.dtype == torch.float32:
+        dwp = out.permute(0, 2, 3, 1)
+    if dwp is None:
+        dwp = torch.empty((Cout, ksize, ksize, _up32(Cin)), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
         st = _lib.current_stream_ptr(x.device)
         _lib.check(lib.hg_conv2d_wgrad(_lib.ptr(dy), _lib.ptr(x), _lib.ptr(dwp), C.byref(p), st),

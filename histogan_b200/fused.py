@@ -111,7 +111,7 @@ class _ModConvLayer(torch.autograd.Function):
                                              B, H * W, Cin, _st(dev))
                 _lib.check(rc, "hg_modulate_bwd")
         if ctx.needs_input_grad[2]:
-            dw = _conv.conv2d_wgrad_nhwc(dz, xm, k, 1, (k - 1) // 2)
+            dw = _conv.conv2d_wgrad_nhwc(dz, xm, k, 1, (k - 1) // 2, out=ops.grad_slot(w))
         if wsq is not None and d is not None:
             analytic = dw is None or (dw.is_contiguous(memory_format=torch.channels_last) and
                                       w.is_contiguous(memory_format=torch.channels_last))

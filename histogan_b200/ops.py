@@ -229,10 +229,32 @@ def _raw_grad_input(dy, w, stride, pad, in_hw, dy_rounded=False, padded_io=False
     return dx if padded_io else _match_channels(dx, w.shape[1])
 
 
-def _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False):
+GRAD_SLOT = "_hg_grad_slot"      # trainer.GradArena: where this parameter's gradient should be written
+
+
+_slot_epoch = [0]
+
+
+def new_backward():
+    """a new backward pass begins (the gradients were reset to None): slots may be handed out again"""
+    _slot_epoch[0] += 1
+
+
+def grad_slot(w):
+    """the flat-arena view a weight's gradient should be produced in, or None (outside DDP, or when
+    this backward already produced a gradient for `w` there: a second use of the weight must come in
+    its own tensor and be ADDED by autograd)"""
+    slot = getattr(w, GRAD_SLOT, None)
+    if slot is None or getattr(w, "_hg_grad_slot_epoch", -1) == _slot_epoch[0]:
+        return None
+    w._hg_grad_slot_epoch = _slot_epoch[0]
+    return slot
+
+
+def _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False, out=None):
     k = wshape[2]
     dw = _conv.conv2d_wgrad_nhwc(round_tf32_nhwc(dy, dy_rounded), round_tf32_nhwc(x, x_rounded), k,
-                                 stride, pad)
+                                 stride, pad, out=out)
     if tuple(dw.shape[:2]) != tuple(wshape[:2]):
         dw = dw[:wshape[0], :wshape[1]].contiguous(memory_format=torch.channels_last)
     return dw
@@ -253,7 +275,8 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = _Conv2dGradInput.apply(dy, w, stride, pad, tuple(x.shape[2:]), False, padded_io)
         if ctx.needs_input_grad[1]:
-            dw = _Conv2dGradWeight.apply(dy, x, tuple(w.shape), stride, pad, False, x_rounded)
+            dw = _Conv2dGradWeight.apply(dy, x, tuple(w.shape), stride, pad, False, x_rounded,
+                                         None if torch.is_grad_enabled() else grad_slot(w))
         return dx, dw, None, None, None, None
 
 
@@ -278,9 +301,11 @@ class _Conv2dGradInput(torch.autograd.Function):
 
 class _Conv2dGradWeight(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False):
+    def forward(ctx, dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False, out=None):
         ctx.save_for_backward(dy, x)
         ctx.cfg = (wshape, stride, pad, dy_rounded, x_rounded)
+        if out is not None:
+            return _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded, x_rounded, out=out)
         return _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded, x_rounded)
 
     @staticmethod
@@ -294,7 +319,7 @@ class _Conv2dGradWeight(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g_x = _Conv2dGradInput.apply(dy, ddw, stride, pad, tuple(x.shape[2:]), dy_rounded,
                                          padded_io)
-        return g_dy, g_x, None, None, None, None, None
+        return g_dy, g_x, None, None, None, None, None, None
 
 
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias=None, stride: int = 1,
@@ -379,8 +404,9 @@ class _ConvBiasAct(torch.autograd.Function):
                 dx = _Conv2dGradInput.apply(dpre, w, stride, pad, tuple(xr.shape[2:]), True, True)
                 if dx.shape[1] != xshape[1]:
                     dx = dx[:, :xshape[1]]
-            if need_w:
-                dw = _Conv2dGradWeight.apply(dpre, xr, tuple(w.shape), stride, pad, True, True)
+            if need_w:      # (under create_graph the result is part of a graph: never an arena slot)
+                dw = _Conv2dGradWeight.apply(dpre, xr, tuple(w.shape), stride, pad, True, True,
+                                             None if torch.is_grad_enabled() else grad_slot(w))
         dres = dy if (has_res and ctx.needs_input_grad[3]) else None
         return dx, dw, db, dres, None, None, None, None, None, None
 

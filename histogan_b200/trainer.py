@@ -208,6 +208,74 @@ class HistoGAN(nn.Module):
         return x
 
 
+class GradArena:
+    """ONE contiguous float32 buffer holding the gradients of a parameter group (D, or G+S+H), so that
+    the data-parallel exchange is a single all-reduce instead of ~100-200 small ones.
+
+    Every parameter owns a slot (a view with the parameter's own memory layout).  The weight-gradient
+    kernels write conv gradients straight into their slots (ops.grad_slot), autograd adopts those
+    tensors as `.grad`; whatever arrived elsewhere (small tensors produced by torch ops) is copied
+    into its slot by finalize(), which also re-points `.grad` at the slot -- the optimiser then reads
+    the arena.  All of it is capturable in a CUDA graph (fixed addresses)."""
+
+    ALIGN = 128          # floats: 512-byte slots keep every view 16-byte aligned for the vector kernels
+
+    def __init__(self, params):
+        from . import ops
+        self.params = [p for p in params]
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.slots = []
+        for p, o in zip(self.params, offs):
+            flat = self.flat[o:o + p.numel()]
+            if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+                co, ci, kh, kw = p.shape
+                v = flat.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            else:
+                v = flat.view(p.shape) if p.is_contiguous() else None
+            self.slots.append(v)
+            if v is not None:
+                setattr(p, ops.GRAD_SLOT, v)
+
+    def begin(self):
+        from . import ops
+        ops.new_backward()
+
+    def finalize(self):
+        """after backward: every gradient lives in (and `.grad` points at) its slot"""
+        src, dst = [], []
+        for p, v in zip(self.params, self.slots):
+            if v is None:
+                continue
+            g = p.grad
+            if g is None:
+                v.zero_()               # parameter unused in this phase: contributes zeros
+            elif g.data_ptr() != v.data_ptr():
+                src.append(g); dst.append(v)
+            p.grad = v
+        if src:
+            torch._foreach_copy_(dst, src)
+
+    def all_reduce_mean(self):
+        world = dist.get_world_size()
+        if self.flat.is_cuda and dist.get_backend() == 'nccl':
+            dist.all_reduce(self.flat, op=dist.ReduceOp.AVG)       # one collective, mean inside NCCL
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(world)
+        leftovers = [p for p, v in zip(self.params, self.slots) if v is None and p.grad is not None]
+        if leftovers:
+            _allreduce_mean_grads(leftovers)
+
+
+def _ddp_active():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 def _allreduce_mean_grads(params, bucket_bytes=128 << 20):
     """bucketed NCCL all-reduce (mean) of .grad over the default process group."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -314,6 +382,9 @@ class Trainer:
         self.cuda_graphs = bool(kwargs.pop('cuda_graphs', False))
         self._graphs = {}
         self._static = None
+        self._arenas = {}
+        # flat gradient arenas (one all-reduce per phase): on under torch.distributed, or forced
+        self.use_grad_arena = kwargs.pop('grad_arena', None)
         self.graph_replayed_launches = 0      # library kernels launched through graph replays
         self.GAN_params = [args, kwargs]
         self.GAN = None
@@ -368,6 +439,7 @@ class Trainer:
         # load() -> load_config() after a NaN) must be captured afresh
         self._graphs = {}
         self._static = None
+        self._arenas = {}
         self.GAN = HistoGAN(lr=self.lr, image_size=self.image_size,
                             network_capacity=self.network_capacity, transparent=self.transparent,
                             fq_layers=self.fq_layers, fq_dict_size=self.fq_dict_size,
@@ -403,6 +475,30 @@ class Trainer:
 
     def _is_main(self):
         return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
+
+    def _arena(self, kind):
+        """the flat gradient arena of the D ('d') or G+S+H ('g') parameters, or None when off"""
+        on = self.use_grad_arena
+        if on is None:
+            on = _ddp_active() or os.environ.get('HG_GRAD_ARENA', '0') != '0'
+        if not on:
+            return None
+        if kind not in self._arenas:
+            GAN = self.GAN
+            params = list(GAN.D.parameters()) if kind == 'd' else \
+                [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+            self._arenas[kind] = GradArena(params)
+        return self._arenas[kind]
+
+    def _exchange(self, kind, params):
+        """average the gradients of one parameter group over the ranks (no-op on one GPU)"""
+        arena = self._arenas.get(kind)
+        if not _ddp_active():
+            return
+        if arena is not None:
+            arena.all_reduce_mean()
+        else:
+            _allreduce_mean_grads(params)
 
     # --------------------------------------------------------------- train --
     def _sample_latents(self, get_latents_fn, batch_size, num_layers, latent_dim, image_size):
@@ -443,6 +539,9 @@ class Trainer:
 
         # ---------------------------------------------------- discriminator --
         GAN.D_opt.zero_grad()
+        arena_d = self._arena('d')
+        if arena_d is not None:
+            arena_d.begin()
         for _ in range(accum):
             get_latents_fn = mixed_list if random() < self.mixed_prob else noise_list
             style, inoise = self._sample_latents(get_latents_fn, batch_size, num_layers,
@@ -468,12 +567,17 @@ class Trainer:
             disc_loss.backward()
             total_disc_loss += divergence.detach().item() / accum
         self.d_loss = float(total_disc_loss)
-        _allreduce_mean_grads(list(GAN.D.parameters()))
+        if arena_d is not None:
+            arena_d.finalize()
+        self._exchange('d', list(GAN.D.parameters()))
         GAN.D_opt.step()
 
         # -------------------------------------------------------- generator --
         GAN.G_opt.zero_grad()
         g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        arena_g = self._arena('g')
+        if arena_g is not None:
+            arena_g.begin()
         # the reference lets this phase's backward fill D's parameter gradients too, only to
         # zero them at the next D_opt.zero_grad() (:886): skip that dead wgrad work
         set_requires_grad(GAN.D, False)
@@ -509,7 +613,9 @@ class Trainer:
         set_requires_grad(GAN.D, True)
         self.g_loss = float(total_gen_loss)
         self.h_loss = float(total_hist_loss)
-        _allreduce_mean_grads(g_params)
+        if arena_g is not None:
+            arena_g.finalize()
+        self._exchange('g', g_params)
         GAN.G_opt.step()
 
         return self._finish_step(total_disc_loss, total_gen_loss, total_hist_loss,
@@ -573,6 +679,9 @@ class Trainer:
         # the backward allocates this graph's own gradient tensors (kept alive by _graphed and
         # re-attached to the parameters after every replay): no zero-fill / accumulate kernels
         GAN.D_opt.zero_grad(set_to_none=True)
+        arena = self._arena('d')
+        if arena is not None:
+            arena.begin()
         dr = self._device_draws('d')
         z1, z2, inoise = dr['z1'], dr['z2'], dr['inoise']
         with torch.no_grad():
@@ -598,6 +707,8 @@ class Trainer:
         with _GradOverlap(GAN.D.parameters()) as ov:
             loss.backward()
         ov.finish()
+        if arena is not None:
+            arena.finalize()
         return divergence.detach(), (gp.detach() if gp is not None else None)
 
     def _phase_g(self, alpha, apply_pl=False):
@@ -606,6 +717,9 @@ class Trainer:
         reference's host-side `if not isnan(pl_loss)` becomes a select on the device."""
         GAN, st = self.GAN, self._static
         GAN.G_opt.zero_grad(set_to_none=True)
+        arena = self._arena('g')
+        if arena is not None:
+            arena.begin()
         dr = self._device_draws('g', apply_pl)
         z1, z2, inoise = dr['z1'], dr['z2'], dr['inoise']
         hists = st['hists']      # the reference's hist_batch.requires_grad_() (:940) is never used
@@ -630,6 +744,8 @@ class Trainer:
             with _GradOverlap([p for grp in GAN.G_opt.param_groups for p in grp['params']]) as ov:
                 gen_loss.backward()
             ov.finish()
+            if arena is not None:
+                arena.finalize()
         finally:
             set_requires_grad(GAN.D, True)
         return loss.detach(), hist_loss.detach(), avg_pl
@@ -710,7 +826,7 @@ class Trainer:
         overlapped = _GradOverlap([]).enabled       # the collectives then live inside the graphs
         divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp), d_params)
         if not overlapped:
-            _allreduce_mean_grads(d_params)
+            self._exchange('d', d_params)
         GAN.D_opt.step()
         stage(next(self.loader), 1)
         if apply_pl:
@@ -718,7 +834,7 @@ class Trainer:
         g_loss, h_loss, avg_pl = self._graphed(('G', float(alpha), bool(apply_pl)),
                                                lambda: self._phase_g(alpha, apply_pl), g_params)
         if not overlapped:
-            _allreduce_mean_grads(g_params)
+            self._exchange('g', g_params)
         GAN.G_opt.step()
         # host reads once, after everything has been queued
         self.q_loss = 0.0

@@ -61,6 +61,30 @@ def _worker(rank, world, port, q):
     ov.finish()
     ok = ok and ov.enabled and all(torch.allclose(q_.grad, wnt, atol=1e-6)
                                    for q_, wnt in zip(net.parameters(), want))
+    # flat gradient arena: slots alias one buffer, finalize() gathers gradients that were produced
+    # elsewhere, ONE all-reduce averages everything (Trainer._exchange)
+    from histogan_b200.trainer import GradArena
+    from histogan_b200 import ops
+    aps = [torch.nn.Parameter(torch.zeros(s)) for s in shapes]
+    aps[2].data = aps[2].data.contiguous(memory_format=torch.channels_last)        # a conv weight as stored
+    arena = GradArena(aps)
+    arena.begin()
+    ga = torch.Generator().manual_seed(100 + rank)
+    for i, p in enumerate(aps):
+        gsrc = torch.randn(p.shape, generator=ga)
+        if i == 2:                          # "the kernel wrote into the slot": adopt the slot as .grad
+            slot = ops.grad_slot(p)
+            assert slot is not None and ops.grad_slot(p) is None        # handed out once per backward
+            slot.copy_(gsrc)
+            p.grad = slot
+        elif i != 3:
+            p.grad = gsrc                   # produced by a torch op: gathered by finalize()
+    arena.finalize()                        # parameter 3 had no gradient: zeros
+    ok = ok and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(aps, arena.slots))
+    arena.all_reduce_mean()
+    for i, (p, e) in enumerate(zip(aps, expected)):
+        want_i = torch.zeros_like(e) if i == 3 else e
+        ok = ok and torch.allclose(p.grad, want_i, atol=1e-6)
     # NaN flag agreement (Trainer.train): MAX-reduce of a per-rank flag
     f = torch.tensor([1.0 if rank == 1 else 0.0])
     dist.all_reduce(f, op=dist.ReduceOp.MAX)

@@ -390,8 +390,9 @@ def test_train_step_matches_reference_trainer(case, tmp_path, cuda_device):
     _check_grads("eager", t.GAN.G_opt.recorded, g["names_g"], g, case, "g")
 
 
+@pytest.mark.parametrize("arena", [False, True], ids=["", "arena"])
 @pytest.mark.parametrize("case", [1, 4, 32])
-def test_graphed_phases_match_reference_trainer(case, tmp_path, cuda_device):
+def test_graphed_phases_match_reference_trainer(case, arena, tmp_path, cuda_device):
     """the CUDA-graph path (_phase_d / _phase_g as captured and replayed by _train_graphed),
     fed the reference's random draws, vs the reference Trainer.train golden"""
     import math
@@ -400,7 +401,7 @@ def test_graphed_phases_match_reference_trainer(case, tmp_path, cuda_device):
     from tests import step_checks as sc
     g = sc.load_golden()
     ref = g[f"c{case}_scalars"]
-    t = _golden_trainer(tmp_path, cuda_graphs=True, fast_rng=True)
+    t = _golden_trainer(tmp_path, cuda_graphs=True, fast_rng=True, grad_arena=arena)
     t.GAN.train()
     images, hists = mgs.step_inputs(case)
     L = int(math.log2(mgs.IMAGE_SIZE) - 1) - 2
@@ -425,6 +426,11 @@ def test_graphed_phases_match_reference_trainer(case, tmp_path, cuda_device):
     for _ in range(2):                                   # capture + replay, then a second replay
         div, gp = t._graphed(('D', gp_on), lambda: t._phase_d(gp_on), d_params)
     _check_grads("graph", [p.grad for p in d_params], g["names_d"], g, case, "d")
+    if arena:       # every D gradient lives in the flat arena (the DDP exchange is one all-reduce)
+        ar = t._arenas['d']
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(ar.params, ar.slots))
+        lo, hi = ar.flat.data_ptr(), ar.flat.data_ptr() + 4 * ar.flat.numel()
+        assert all(lo <= p.grad.data_ptr() < hi for p in d_params)
     t._static['hists'].copy_(hists[1].cuda())
     t._static['mask'].copy_(fg['mask'])
     for _ in range(2):
