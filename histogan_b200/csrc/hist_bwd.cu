@@ -178,12 +178,17 @@ hist_bwd_fast_kernel(const float* __restrict__ x, const HistGeom g, const HistTa
       for (int c = 0; c < 4; ++c) {
         const int o = og * 4 + c;
         const float chi = t.c_hi[o], clo = t.c_lo[o];
-        const float4 e04 = *reinterpret_cast<const float4*>(&s.E[0][o][pg * 4]);
-        const float4 e14 = *reinterpret_cast<const float4*>(&s.E[1][o][pg * 4]);
-        const float4 e24 = *reinterpret_cast<const float4*>(&s.E[2][o][pg * 4]);
-        const float e0[4] = {e04.x, e04.y, e04.z, e04.w};
-        const float e1[4] = {e14.x, e14.y, e14.z, e14.w};
-        const float e2[4] = {e24.x, e24.y, e24.z, e24.w};
+        // the kernel values are RECOMPUTED here (48 evaluations per thread and tile, against the 6144
+        // FMAs of the loop above) instead of re-read from s.E: rows o = og*4+c of the 16 lanes of a
+        // half-warp are 512 B apart -> the same banks, a 16-way conflict on every one of those loads
+        // (ncu, round 1: 89.9 M conflicts per launch)
+        float e0[4], e1[4], e2[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          e0[a] = kernel_f32<METHOD>(u0[a], chi, clo, inv_s2);
+          e1[a] = kernel_f32<METHOD>(u1[a], chi, clo, inv_s2);
+          e2[a] = kernel_f32<METHOD>(u2[a], chi, clo, inv_s2);
+        }
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
           const float w = wv[a];
