@@ -14,6 +14,8 @@
 //            outside the image == padding), element stride s for stride-2 convs.
 // One CTA owns one (tap, 128-co tile, BN-ci tile) accumulator in TMEM and a slice
 // of the pixel range (split-K); partial results are combined with fp32 atomics.
+#include <cstdlib>
+#include <mutex>
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -29,9 +31,11 @@ struct WgradArgs {
   int PB, PH, PW;
   int tiles_w, tiles_h, tiles_b;
   int co_tiles, ci_tiles, splits;
-  int atomic;
+  int atomic;                           // splits > 1 and no scratch: fp32 atomics into a zeroed dw (fallback)
   float* dw;                            // packed [Cout][KH*KW][Kp], Kp = round_up(Cin, 32)
   int Kp;
+  float* partial;                       // splits > 1: split s writes its partial dW to partial + s*slice;
+  long long slice;                      //   wgrad_finish_kernel adds the slices in index order (deterministic)
 };
 
 template <int BN, int STAGES, int TAPS = 1>
@@ -175,7 +179,8 @@ conv_wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tmdy,
         const int c0 = TAPS == 1 ? cc : 0;
         const int tap_o = TAPS == 1 ? tap : cc / 32;
         if (co < a.Cout) {
-          float* o = a.dw + ((long long)co * taps + tap_o) * a.Kp + ci0 + c0;
+          float* o = (a.partial ? a.partial + (long long)blockIdx.y * a.slice : a.dw) +
+                     ((long long)co * taps + tap_o) * a.Kp + ci0 + c0;
           if (a.atomic) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) atomicAdd(o + j, __uint_as_float(v[j]));
@@ -325,11 +330,18 @@ conv_wgrad_col_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_con
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kw * N + cc), v);
             ptx::tmem_ld_wait();
-            float* o = a.dw + ((long long)(co0 + cc) * 9 + q * 3 + kw) * a.Kp + ci;
+            float* o = (a.partial ? a.partial + (long long)blockIdx.y * a.slice : a.dw) +
+                       ((long long)(co0 + cc) * 9 + q * 3 + kw) * a.Kp + ci;
             const int ncols = min(32, a.Cout - (co0 + cc));
+            if (a.partial) {             // lanes = consecutive ci: coalesced 128 B rows
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) atomicAdd(o + (long long)j * 9 * a.Kp, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) o[(long long)j * 9 * a.Kp] = __uint_as_float(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols) atomicAdd(o + (long long)j * 9 * a.Kp, __uint_as_float(v[j]));
+            }
           }
         }
       }
@@ -338,6 +350,69 @@ conv_wgrad_col_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_con
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// dW = sum over the split-K slices, in index order: bit-reproducible (fp32 atomics are not, and the
+// randomly initialised networks amplify a 1e-7 reordering to percents in later gradients)
+__global__ void __launch_bounds__(256)
+wgrad_finish_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long n4, long long slice,
+                    int splits) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = *reinterpret_cast<const float4*>(partial + i * 4);
+  for (int k = 1; k < splits; ++k) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + k * slice + i * 4);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  *reinterpret_cast<float4*>(dw + i * 4) = s;
+}
+
+// Per-device scratch for the split-K slices: one fixed allocation made on first use (never inside a
+// stream capture, never moved: captured graphs keep its address).  CONTRACT as for the forward
+// split-K scratch: weight-gradient launches of one device are issued on one stream.
+constexpr size_t kWgradWsBytes = 96u << 20;
+
+static float* wgrad_workspace(size_t bytes, cudaStream_t stream) {
+  static float* ws[64] = {};
+  static std::mutex mu;
+  if (bytes > kWgradWsBytes) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (ws[dev]) return ws[dev];
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+  float* p = nullptr;
+  if (cudaMalloc(&p, kWgradWsBytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ws[dev] = p;
+  return p;
+}
+
+// splits > 1: route the partial sums through the scratch (deterministic); without scratch (request too
+// large, or first use inside a capture) fall back to atomics into a zeroed dw.  Returns 0 / error.
+static int setup_split(WgradArgs& a, float* dw_packed, size_t out_bytes, cudaStream_t stream) {
+  a.partial = nullptr; a.slice = 0; a.atomic = 0; a.dw = dw_packed;
+  if (a.splits <= 1) return 0;
+  static const bool deterministic = [] {
+    const char* e = getenv("HG_WGRAD_ATOMIC");
+    return !(e && e[0] == '1');
+  }();
+  float* ws = deterministic ? wgrad_workspace(out_bytes * (size_t)a.splits, stream) : nullptr;
+  if (ws) {
+    a.partial = ws; a.slice = (long long)(out_bytes / sizeof(float));
+  } else {
+    a.atomic = 1;
+    HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream));
+  }
+  return 0;
+}
+
+static int finish_split(const WgradArgs& a, size_t out_bytes, cudaStream_t stream) {
+  if (!a.partial) return 0;
+  const long long n4 = (long long)(out_bytes / 16);
+  wgrad_finish_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a.partial, a.dw, n4, a.slice, a.splits);
+  HG_LAUNCH_OK("wgrad_finish_kernel");
+  return 0;
 }
 
 // packed [Cout][KH][KW][Cin] gradient -> OIHW parameter gradient (optionally +=)
@@ -448,16 +523,19 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
     int splits = (2 * sms + a.ci_tiles - 1) / a.ci_tiles;
     if (splits > kb_total / 2) splits = kb_total / 2;
     if (splits < 1) splits = 1;
-    a.splits = splits; a.atomic = 1; a.dw = dw_packed;
-    HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream));
+    a.splits = splits;
+    int rc = setup_split(a, dw_packed, out_bytes, stream);
+    if (rc) return rc;
+    if (splits == 1) { a.atomic = 1; HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream)); }
     alignas(64) CUtensorMap tmdy, tmx;
-    int rc = encode_nhwc_map(&tmdy, dy, p->Cout, OW, OH, p->B, 16, 4, 1, 1);
+    rc = encode_nhwc_map(&tmdy, dy, p->Cout, OW, OH, p->B, 16, 4, 1, 1);
     if (rc) return rc;
     rc = encode_nhwc_map(&tmx, x, p->Cin, p->W, p->H, p->B, 16, 6, 1, 1);
     if (rc) return rc;
-    if (NC == 1) return launch_wgrad_col<1, 4>(tmdy, tmx, a, 1, stream);
-    if (NC == 2) return launch_wgrad_col<2, 4>(tmdy, tmx, a, 1, stream);
-    return launch_wgrad_col<4, 3>(tmdy, tmx, a, 1, stream);
+    if (NC == 1) rc = launch_wgrad_col<1, 4>(tmdy, tmx, a, 1, stream);
+    else if (NC == 2) rc = launch_wgrad_col<2, 4>(tmdy, tmx, a, 1, stream);
+    else rc = launch_wgrad_col<4, 3>(tmdy, tmx, a, 1, stream);
+    return rc ? rc : finish_split(a, out_bytes, stream);
   }
   int PW = 1; while (PW < 16 && PW < OW) PW <<= 1;
   int PH = 1; while (PW * PH < kWgPix && PH < OH) PH <<= 1;
@@ -476,19 +554,19 @@ extern "C" int hg_conv2d_wgrad(const float* dy, const float* x, float* dw_packed
   if (splits > kb_total / 2) splits = kb_total / 2;
   if (splits < 1) splits = 1;
   a.splits = splits;
-  a.atomic = splits > 1;
-  a.dw = dw_packed;
-  if (a.atomic) HG_CUDA_OK(cudaMemsetAsync(dw_packed, 0, out_bytes, stream));
+  int rc = setup_split(a, dw_packed, out_bytes, stream);
+  if (rc) return rc;
 
   alignas(64) CUtensorMap tmdy, tmx;
-  int rc = encode_nhwc_map(&tmdy, dy, p->Cout, OW, OH, p->B, PW, PH, PB, 1);
+  rc = encode_nhwc_map(&tmdy, dy, p->Cout, OW, OH, p->B, PW, PH, PB, 1);
   if (rc) return rc;
   rc = encode_nhwc_map(&tmx, x, p->Cin, p->W, p->H, p->B, PW, PH, PB, p->stride);
   if (rc) return rc;
-  if (all_taps) return launch_wgrad<32, 2, 9>(tmdy, tmx, a, stream);
-  if (BN == 128) return launch_wgrad<128, 3>(tmdy, tmx, a, stream);
-  if (BN == 64) return launch_wgrad<64, 4>(tmdy, tmx, a, stream);
-  return launch_wgrad<32, 4>(tmdy, tmx, a, stream);
+  if (all_taps) rc = launch_wgrad<32, 2, 9>(tmdy, tmx, a, stream);
+  else if (BN == 128) rc = launch_wgrad<128, 3>(tmdy, tmx, a, stream);
+  else if (BN == 64) rc = launch_wgrad<64, 4>(tmdy, tmx, a, stream);
+  else rc = launch_wgrad<32, 4>(tmdy, tmx, a, stream);
+  return rc ? rc : finish_split(a, out_bytes, stream);
 }
 
 extern "C" int hg_unpack_conv_wgrad(const float* dw_packed, float* dw_oihw, int32_t Cout, int32_t Cin,
