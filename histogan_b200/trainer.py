@@ -385,6 +385,9 @@ class Trainer:
         self._arenas = {}
         # flat gradient arenas (one all-reduce per phase): on under torch.distributed, or forced
         self.use_grad_arena = kwargs.pop('grad_arena', None)
+        # split the captured G phase into a D-independent part and the rest (overlaps the D-side
+        # all-reduce); None = only under torch.distributed
+        self.split_g_phase = kwargs.pop('split_g_phase', None)
         self.graph_replayed_launches = 0      # library kernels launched through graph replays
         self.GAN_params = [args, kwargs]
         self.GAN = None
@@ -489,6 +492,19 @@ class Trainer:
                 [p for grp in GAN.G_opt.param_groups for p in grp['params']]
             self._arenas[kind] = GradArena(params)
         return self._arenas[kind]
+
+    def _exchange_async(self, kind, params):
+        """start averaging one parameter group's gradients over the ranks; returns a callable that
+        makes the current stream wait for the result (None on one GPU)."""
+        if not _ddp_active():
+            return None
+        arena = self._arenas.get(kind)
+        if arena is None or not (arena.flat.is_cuda and dist.get_backend() == 'nccl') or \
+                any(v is None for v in arena.slots):
+            self._exchange(kind, params)
+            return None
+        w = dist.all_reduce(arena.flat, op=dist.ReduceOp.AVG, async_op=True)   # on NCCL's own stream
+        return w.wait
 
     def _exchange(self, kind, params):
         """average the gradients of one parameter group over the ranks (no-op on one GPU)"""
@@ -714,7 +730,15 @@ class Trainer:
     def _phase_g(self, alpha, apply_pl=False):
         """G phase (histoGAN.py:934-989).  apply_pl: + the path-length regulariser (:965-975)
         with `pl_mean` read from a device scalar, so that PL steps are capturable too; the
-        reference's host-side `if not isnan(pl_loss)` becomes a select on the device."""
+        reference's host-side `if not isnan(pl_loss)` becomes a select on the device.
+        = _phase_g1 (everything that does not depend on D) followed by _phase_g2."""
+        self._phase_g1(apply_pl)
+        return self._phase_g2(alpha, apply_pl)
+
+    def _phase_g1(self, apply_pl=False):
+        """generator side of the G phase: latents -> S / H -> G forward (twice on path-length steps).
+        Independent of the discriminator's weights, so under DDP it runs WHILE the D-side gradient
+        all-reduce of the same step is in flight (see _train_graphed)."""
         GAN, st = self.GAN, self._static
         GAN.G_opt.zero_grad(set_to_none=True)
         arena = self._arena('g')
@@ -727,6 +751,19 @@ class Trainer:
         h_w = torch.cat((h_w, h_w), dim=1)
         w_styles = self._mixed_styles(z1, z2, st['mask'])
         fake = GAN.G(w_styles, h_w, inoise)
+        pl_images = None
+        if apply_pl:
+            std = 0.1 / (w_styles.std(dim=0, keepdim=True) + EPS)
+            pl_images = GAN.G(w_styles + dr['pl_noise'] / (std + EPS), h_w, inoise)
+        self._g1 = (fake, pl_images, hists)
+        return ()
+
+    def _phase_g2(self, alpha, apply_pl=False):
+        """the rest of the G phase: D(fake), histogram loss, path-length loss, backward"""
+        GAN, st = self.GAN, self._static
+        fake, pl_images, hists = self._g1
+        self._g1 = None
+        arena = self._arena('g')
         set_requires_grad(GAN.D, False)          # D's parameter gradients are dead work here
         avg_pl = None
         try:
@@ -735,8 +772,6 @@ class Trainer:
             loss = fake_out.mean()
             gen_loss = loss + hist_loss
             if apply_pl:
-                std = 0.1 / (w_styles.std(dim=0, keepdim=True) + EPS)
-                pl_images = GAN.G(w_styles + dr['pl_noise'] / (std + EPS), h_w, inoise)
                 pl_lengths = ((pl_images - fake) ** 2).mean(dim=(1, 2, 3))
                 avg_pl = pl_lengths.detach().mean()
                 pl_loss = ((pl_lengths - st['pl_mean']) ** 2).mean()
@@ -750,24 +785,21 @@ class Trainer:
             set_requires_grad(GAN.D, True)
         return loss.detach(), hist_loss.detach(), avg_pl
 
-    def _graphed(self, key, fn, params):
-        """capture `fn` (one phase: zero_grad + forward + backward) once, then replay.
-
-        Each graph writes the gradients of `params` into tensors of its own memory pool; they
-        are kept alive here (stable addresses, refreshed by every replay) and attached to the
-        parameters after the replay, so the optimiser always reads what the graph just wrote
-        -- whichever variant (with / without gradient penalty) ran."""
+    def _capture(self, keys, fns, params_list):
+        """capture the functions `fns` (run in this order; later ones may consume tensors earlier ones
+        left on `self`) as one CUDA graph each: an eager warm-up of the whole sequence on a side
+        stream, then the captures, all sharing one memory pool."""
         from . import ops, _lib
         lib = _lib.load()
-        entry = self._graphs.get(key)
-        if entry is None:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):           # eager warm-up on a side stream
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):           # eager warm-up on a side stream
+            for fn in fns:
                 fn()
-            torch.cuda.current_stream().wait_stream(side)
-            # the warm-up filled the packed-weight cache (stable addresses, refilled in place by the
-            # optimiser step): the captured graph reads those tensors and packs nothing itself
+        torch.cuda.current_stream().wait_stream(side)
+        # the warm-up filled the packed-weight cache (stable addresses, refilled in place by the
+        # optimiser step): the captured graphs read those tensors and pack nothing themselves
+        for key, fn, params in zip(keys, fns, params_list):
             g = torch.cuda.CUDAGraph()
             n0 = lib.hg_launch_count()
             with torch.cuda.graph(g, pool=self._graphs.get('pool')):
@@ -776,7 +808,11 @@ class Trainer:
             # library kernels recorded in this graph (each replay launches them again)
             grads = [(p, p.grad) for p in params if p.grad is not None]
             packed = [p for p in self.GAN.parameters() if getattr(p, ops._PackCache.ATTR, None)]
-            entry = self._graphs[key] = (g, outs, int(lib.hg_launch_count() - n0), grads, packed)
+            self._graphs[key] = (g, outs, int(lib.hg_launch_count() - n0), grads, packed)
+
+    def _replay(self, key):
+        from . import ops
+        entry = self._graphs[key]
         ops._packs.refresh_stale(entry[4])      # no-op unless someone other than DiffGrad moved weights
         entry[0].replay()
         for p, gr in entry[3]:
@@ -787,6 +823,17 @@ class Trainer:
         # optimiser) before the next replay; the scalar outputs are read at the end of the step,
         # so hand out copies that live outside the pool.
         return tuple(o.clone() if o is not None else None for o in entry[1])
+
+    def _graphed(self, key, fn, params):
+        """capture `fn` (one phase: zero_grad + forward + backward) once, then replay.
+
+        Each graph writes the gradients of `params` into tensors of its own memory pool; they
+        are kept alive (stable addresses, refreshed by every replay) and attached to the
+        parameters after the replay, so the optimiser always reads what the graph just wrote
+        -- whichever variant (with / without gradient penalty) ran."""
+        if key not in self._graphs:
+            self._capture([key], [fn], [params])
+        return self._replay(key)
 
     def _train_graphed(self, alpha, apply_gp, apply_pl=False):
         GAN = self.GAN
@@ -825,14 +872,33 @@ class Trainer:
         g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
         overlapped = _GradOverlap([]).enabled       # the collectives then live inside the graphs
         divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp), d_params)
-        if not overlapped:
-            self._exchange('d', d_params)
-        GAN.D_opt.step()
-        stage(next(self.loader), 1)
-        if apply_pl:
-            st['pl_mean'].fill_(float(self.pl_mean))
-        g_loss, h_loss, avg_pl = self._graphed(('G', float(alpha), bool(apply_pl)),
-                                               lambda: self._phase_g(alpha, apply_pl), g_params)
+        split_g = self.split_g_phase if self.split_g_phase is not None else _ddp_active()
+        if split_g:
+            # the generator side of the G phase (G1) does not depend on D: it runs while the D-side
+            # gradient all-reduce is in flight; D's update and the rest of the phase (G2) follow
+            k1, k2 = ('G1', bool(apply_pl)), ('G2', float(alpha), bool(apply_pl))
+            batch_g = next(self.loader)
+            work = None if overlapped else self._exchange_async('d', d_params)
+            stage(batch_g, 1)
+            if apply_pl:
+                st['pl_mean'].fill_(float(self.pl_mean))
+            if k2 not in self._graphs:
+                self._capture([k1, k2], [lambda: self._phase_g1(apply_pl),
+                                         lambda: self._phase_g2(alpha, apply_pl)], [[], g_params])
+            self._replay(k1)
+            if work is not None:
+                work()
+            GAN.D_opt.step()
+            g_loss, h_loss, avg_pl = self._replay(k2)
+        else:
+            if not overlapped:
+                self._exchange('d', d_params)
+            GAN.D_opt.step()
+            stage(next(self.loader), 1)
+            if apply_pl:
+                st['pl_mean'].fill_(float(self.pl_mean))
+            g_loss, h_loss, avg_pl = self._graphed(('G', float(alpha), bool(apply_pl)),
+                                                   lambda: self._phase_g(alpha, apply_pl), g_params)
         if not overlapped:
             self._exchange('g', g_params)
         GAN.G_opt.step()
