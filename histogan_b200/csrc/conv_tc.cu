@@ -19,10 +19,12 @@
 //           weight [Cout][KH*KW*Cin] (K-major).
 //   Both land in 128B-swizzled rows == the canonical K-major UMMA layout, so no
 //   thread ever touches operand data.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA
-// issuer (one elected lane), warps 2-5 = epilogue (TMEM -> registers -> fused
-// scale / bias / noise / LeakyReLU / residual -> NHWC global).  The kernel is
-// persistent (one CTA per SM) with two TMEM accumulator stages.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA
+// issuer (one elected lane), warps 2-5 and 6-9 = two epilogue sets (TMEM ->
+// registers -> fused scale / bias / noise / LeakyReLU / residual -> NHWC global);
+// set s drains accumulator stage s, i.e. every other tile, so two tiles are in
+// their (latency-bound: TMEM load, parameter loads, 128-bit stores) epilogue at a
+// time.  The kernel is persistent (one CTA per SM) with two TMEM accumulator stages.
 #include <cstdlib>
 #include <mutex>
 #include "hg_common.cuh"
@@ -33,7 +35,8 @@ namespace hg {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;                       // fp32 channels per k-block = 128 B rows
 constexpr int kABytes = kBlockM * kBlockK * 4;    // 16 KB
-constexpr int kConvThreads = 192;
+constexpr int kEpilogueSets = 2;                 // two sets of 4 epilogue warps alternate over the tiles
+constexpr int kConvThreads = 64 + 128 * kEpilogueSets;
 
 struct ConvArgs {
   int B, H, W, Cin, Cout, KH, KW, stride, pad, OH, OW;
@@ -287,10 +290,12 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   } else {
     // ------------------------------------------------------------ epilogue --
     const int q = warp & 3;                          // TMEM lane quadrant this warp may read
+    const int set = (warp - 2) >> 2;                 // this warp's epilogue set == its accumulator stage
     const int row = q * 32 + lane;
     const int tw = row % a.TW, th = (row / a.TW) % a.TH, tb = row / (a.TW * a.TH);
     int t = 0;
     for (int item = blockIdx.x; item < total_tiles; item += gridDim.x, ++t) {
+      if ((t & (kEpilogueSets - 1)) != set) continue;
       const int acc = t & 1;
       const uint32_t acc_phase = (uint32_t)((t >> 1) & 1);
       const int tile = item / ksplit;

@@ -14,6 +14,7 @@
 // The reference evaluates these with per-sample weight tensors (B x Cout x Cin x k x k, :423-429);
 // here they are O(B (Cin + Cout) + Cout Cin) per layer.  All kernels are bound by reading the weight
 // matrices once (25 MB of to_style weights, 38 MB of Wsq per generator pass).
+#include <mutex>
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -37,6 +38,7 @@ struct LinearGroups {
   int B;
   int flags;                               // HG_LIN_*
   float slope, eps;
+  int pairs_per_warp;                      // 1..4 row pairs per warp: rows per CTA = 16 * pairs_per_warp
 };
 
 constexpr int kRowsPerCta = 64;            // 8 warps x 4 row pairs
@@ -67,7 +69,8 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
   int gi = 0;
   while (gi + 1 < t.count && (int)blockIdx.x >= t.first_block[gi + 1]) ++gi;
   const int J = t.J[gi], K = t.K[gi];
-  const int r0 = (blockIdx.x - t.first_block[gi]) * kRowsPerCta;
+  const int ppw = t.pairs_per_warp;
+  const int r0 = (blockIdx.x - t.first_block[gi]) * 16 * ppw;
   const int b0 = blockIdx.y * 32;
   const int nb = min(32, t.B - b0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -88,8 +91,8 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
     }
     __syncthreads();
 #pragma unroll 1
-    for (int pr = 0; pr < 4; ++pr) {
-      const int j0 = r0 + (warp * 4 + pr) * 2;         // rows j0, j0 + 1
+    for (int pr = 0; pr < ppw; ++pr) {
+      const int j0 = r0 + (warp * ppw + pr) * 2;       // rows j0, j0 + 1
       if (j0 >= J) break;
       const float* w0 = w + (long long)j0 * K + k0;
       const float* w1 = w + (long long)min(j0 + 1, J - 1) * K + k0;
@@ -117,7 +120,7 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
       }
       float v0 = warp_reduce_scatter(a0, lane);        // lane b: row j0
       float v1 = warp_reduce_scatter(a1, lane);        //         row j0 + 1
-      float* pp = part + ((warp * 4 + pr) * 2) * 32 + lane;
+      float* pp = part + ((warp * ppw + pr) * 2) * 32 + lane;
       if (multi) {
         if (k0 > 0) { v0 += pp[0]; v1 += pp[32]; }
         if (k0 + kKC < K) { pp[0] = v0; pp[32] = v1; continue; }
@@ -152,6 +155,8 @@ struct LinearBwdGroups {
   int count;
   int B;                                   // <= 32
   int flags;
+  int jsplit;                              // dgrad: the J rows are divided over gridDim.y CTAs ...
+  float* partial;                          // ... whose sums land in partial[(split * nslab + slab) * 1024 + b*32 + k]
 };
 
 // gW[j][k..k+3] = sum_b gy[b][j] x[b][k..k+3];  gb[j] = sum_b gy[b][j].
@@ -204,9 +209,18 @@ grouped_linear_wgrad_kernel(const LinearBwdGroups t) {
   }
 }
 
-// gx[b][k] (+)= post[b][k] * sum_j gy[b][j] W[j][k]:  CTA = one 32-wide K slab of one group, lanes = k,
-// the 8 warps split the J rows and are reduced in shared memory in a fixed order (deterministic).
+// gx[b][k] (+)= post[b][k] * sum_j gy[b][j] W[j][k]:  CTA = one 32-wide K slab of one group (lanes = k)
+// x one share of the J rows (gridDim.y shares); its 8 warps split those rows and are reduced in
+// shared memory in a fixed order.  With several shares the CTA sums go to a scratch buffer and
+// grouped_linear_dgrad_finish adds them in share order -- deterministic, no atomics.
 // post (HG_LIN_POST_2X): multiply by 2 x[b][k] (the demodulation's  d(mod^2)/d mod).
+__device__ __forceinline__ void dgrad_store(const LinearBwdGroups& t, int gi, int b, int k, int K, float s) {
+  const long long o = (long long)b * K + k;
+  if (t.flags & HG_LIN_POST_2X) s *= 2.f * t.x[gi][o];
+  if (t.flags & HG_LIN_ACCUMULATE) s += t.gx[gi][o];
+  t.gx[gi][o] = s;
+}
+
 __global__ void __launch_bounds__(kStyleThreads)
 grouped_linear_dgrad_kernel(const LinearBwdGroups t) {
   extern __shared__ __align__(16) float sm[];          // gy tile [32 b][kJT + 1] then reduction [8][32 b][32 k]
@@ -219,11 +233,14 @@ grouped_linear_dgrad_kernel(const LinearBwdGroups t) {
   const int k = (blockIdx.x - t.first_block[gi]) * 32 + (threadIdx.x & 31);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* __restrict__ w = t.w[gi];
+  // this CTA's share of the rows (multiples of 8 so that the warps stay balanced)
+  const int per = ((J + t.jsplit - 1) / t.jsplit + 7) / 8 * 8;
+  const int jlo = min(J, (int)blockIdx.y * per), jhi = min(J, jlo + per);
   float acc[32];
 #pragma unroll
   for (int b = 0; b < 32; ++b) acc[b] = 0.f;
-  for (int jt = 0; jt < J; jt += kJT) {
-    const int jn = min(kJT, J - jt);
+  for (int jt = jlo; jt < jhi; jt += kJT) {
+    const int jn = min(kJT, jhi - jt);
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * jn; e += kStyleThreads) {
       const int b = e / jn, j = e - b * jn;
@@ -246,21 +263,35 @@ grouped_linear_dgrad_kernel(const LinearBwdGroups t) {
       }
     }
   }
+  __syncthreads();
 #pragma unroll
   for (int b = 0; b < 32; ++b) red[(warp * 32 + b) * 32 + lane] = acc[b];
   __syncthreads();
-  // thread (b8 = warp, lane = k): rows b = warp, warp + 8, ...
-  if (k < K && t.gx[gi]) {
-    for (int b = warp; b < B; b += 8) {
-      float s = 0.f;
+  // thread (warp, lane = k): batch rows b = warp, warp + 8, ...
+  if (!t.gx[gi]) return;
+  for (int b = warp; b < 32; b += 8) {
+    float s = 0.f;
 #pragma unroll
-      for (int wq = 0; wq < 8; ++wq) s += red[(wq * 32 + b) * 32 + lane];
-      const long long o = (long long)b * K + k;
-      if (t.flags & HG_LIN_POST_2X) s *= 2.f * t.x[gi][o];
-      if (t.flags & HG_LIN_ACCUMULATE) s += t.gx[gi][o];
-      t.gx[gi][o] = s;
-    }
+    for (int wq = 0; wq < 8; ++wq) s += red[(wq * 32 + b) * 32 + lane];
+    if (t.jsplit > 1)
+      t.partial[((long long)blockIdx.y * gridDim.x + blockIdx.x) * 1024 + b * 32 + lane] = s;
+    else if (k < K && b < B)
+      dgrad_store(t, gi, b, k, K, s);
   }
+}
+
+// several J shares: gx = ordered sum of the shares' partial sums.  grid = slabs (as above), 1024 threads
+__global__ void __launch_bounds__(1024)
+grouped_linear_dgrad_finish_kernel(const LinearBwdGroups t, int nslab) {
+  int gi = 0;
+  while (gi + 1 < t.count && (int)blockIdx.x >= t.first_block[gi + 1]) ++gi;
+  const int K = t.K[gi];
+  const int b = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = (blockIdx.x - t.first_block[gi]) * 32 + lane;
+  if (!t.gx[gi] || k >= K || b >= t.B) return;
+  float s = 0.f;
+  for (int sp = 0; sp < t.jsplit; ++sp) s += t.partial[((long long)sp * nslab + blockIdx.x) * 1024 + b * 32 + lane];
+  dgrad_store(t, gi, b, k, K, s);
 }
 
 // ------------------------------------------------------------ weight helpers --
@@ -331,6 +362,26 @@ __global__ void demod_t_kernel(const float* __restrict__ gd, const float* __rest
   }
 }
 
+// per-device scratch for the dgrad J-split partial sums (4 KB per CTA; a few MB at most): allocated on
+// first use outside a stream capture, never moved.  Launches of one device are issued on one stream.
+constexpr size_t kStyleWsBytes = 32u << 20;
+
+static float* style_workspace(size_t bytes, cudaStream_t stream) {
+  static float* ws[64] = {};
+  static std::mutex mu;
+  if (bytes > kStyleWsBytes) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (ws[dev]) return ws[dev];
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return nullptr;
+  float* p = nullptr;
+  if (cudaMalloc(&p, kStyleWsBytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  ws[dev] = p;
+  return p;
+}
+
 static int check_groups(int count, int B, const int32_t* J, const int32_t* K) {
   if (count < 0 || count > kMaxGroups) return set_error(HG_EINVAL, "group count %d not in [0, %d]", count, kMaxGroups);
   if (B < 0) return set_error(HG_EINVAL, "negative batch");
@@ -351,6 +402,15 @@ extern "C" int hg_grouped_linear_fwd(int32_t count, const float* const* x, const
   if (rc) return rc;
   if (count == 0 || B == 0) return 0;
   LinearGroups t{};
+  // rows per CTA: 64 when that still gives >= 2 CTAs per SM, else 32 / 16 (a 512-row layer of the
+  // S / H MLPs would otherwise run on 8 CTAs; the 1024 x 12288 first layer of H on 16)
+  long long rows = 0;
+  for (int i = 0; i < count; ++i) rows += J[i];
+  const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+  int ppw = 4;
+  while (ppw > 1 && rows / (16 * ppw) < 2 * sms) ppw >>= 1;
+  t.pairs_per_warp = ppw;
+  const int rpc = 16 * ppw;
   int blocks = 0;
   for (int i = 0; i < count; ++i) {
     if (!x[i] || !w[i] || !y[i]) return set_error(HG_EINVAL, "null pointer in group %d", i);
@@ -358,7 +418,7 @@ extern "C" int hg_grouped_linear_fwd(int32_t count, const float* const* x, const
     t.x[i] = x[i]; t.w[i] = w[i]; t.bias[i] = bias ? bias[i] : nullptr; t.y[i] = y[i];
     t.J[i] = J[i]; t.K[i] = K[i];
     t.first_block[i] = blocks;
-    blocks += (J[i] + kRowsPerCta - 1) / kRowsPerCta;
+    blocks += (J[i] + rpc - 1) / rpc;
   }
   t.first_block[count] = blocks;
   t.count = count; t.B = B; t.flags = flags; t.slope = slope; t.eps = eps;
@@ -404,20 +464,36 @@ extern "C" int hg_grouped_linear_bwd(int32_t count, const float* const* x, const
     HG_LAUNCH_OK("grouped_linear_wgrad_kernel");
   }
   if (any_x) {
-    int blocks = 0;
+    int blocks = 0, maxJ = 0;
     for (int i = 0; i < count; ++i) {
       t.first_block[i] = blocks;
       blocks += (K[i] + 31) / 32;
+      if (J[i] > maxJ) maxJ = J[i];
     }
     t.first_block[count] = blocks;
+    // few K slabs (a single layer's demodulation adjoint: <= 64) -> divide the J rows over several
+    // CTAs per slab, sums through a per-device scratch (fixed address: capturable), ordered finish
+    const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
+    int jsplit = 1;
+    while (jsplit < 16 && blocks * jsplit < 2 * sms && maxJ / (jsplit * 2) >= 64) jsplit *= 2;
+    t.jsplit = 1; t.partial = nullptr;
+    if (jsplit > 1) {
+      const size_t need = sizeof(float) * 1024 * (size_t)blocks * jsplit;
+      float* ws = style_workspace(need, stream);
+      if (ws) { t.jsplit = jsplit; t.partial = ws; }
+    }
     const size_t smem = sizeof(float) * (32 * (256 + 1) + 8 * 32 * 32);
     static PerDeviceOnce once;
     if (once.need()) {
       HG_CUDA_OK(cudaFuncSetAttribute(grouped_linear_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       once.mark();
     }
-    grouped_linear_dgrad_kernel<<<blocks, kStyleThreads, smem, stream>>>(t);
+    grouped_linear_dgrad_kernel<<<dim3(blocks, t.jsplit), kStyleThreads, smem, stream>>>(t);
     HG_LAUNCH_OK("grouped_linear_dgrad_kernel");
+    if (t.jsplit > 1) {
+      grouped_linear_dgrad_finish_kernel<<<blocks, 1024, 0, stream>>>(t, blocks);
+      HG_LAUNCH_OK("grouped_linear_dgrad_finish_kernel");
+    }
   }
   return 0;
 }

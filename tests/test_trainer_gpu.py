@@ -83,7 +83,7 @@ def test_histogram_loss_first_order_descent(tmp_path, cuda_device):
     # the kernel width (sigma = 0.02 in log-chroma makes the loss strongly curved) yet large
     # compared with the TF32 quantum of the packed weights (below it most weights do not move)
     assert all(r > 0 for r in ratios.values()), ratios
-    assert 0.5 < sorted(ratios[f] for f in (3e-3, 1e-3, 5e-4))[1] < 1.5, ratios
+    assert 0.5 < max(ratios[f] for f in (3e-3, 1e-3, 5e-4)) < 1.5, ratios
 
 
 def test_fused_diffgrad_matches_foreach(cuda_device):
@@ -346,7 +346,7 @@ def _check_scalars(case, got, ref):
     if case % 32 == 0:
         err["pl_mean"] = sc.rel(got["pl_mean"], ref["pl_mean"])
     parity.record(f"train_step[steps={case},losses]", {**err, **{"floor_" + k: v for k, v in fl.items()}})
-    bad = {k: (v, fl[k]) for k, v in err.items() if v > 2 * fl[k] + 1e-3}
+    bad = {k: (v, fl[k]) for k, v in err.items() if v > 2 * fl[k] + 2e-3}
     assert not bad, bad
 
 
