@@ -474,23 +474,42 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   out[e] = tf32_round(v);
 }
 
-// mode 1 from a channels_last parameter: out[ci][tap][co] = w[co][T-1-tap][ci], a 32x32
-// shared-memory transpose per tap so that both the read (along ci) and the write (along co)
-// are coalesced.  grid (Np/32, Kp/32, KH*KW), block (32, 8).
+// mode 1 from a channels_last parameter: out[ci][tap][co] = w[co][T-1-tap][ci]: a 64x64 shared-memory
+// transpose per tap with 128-bit accesses on both sides (reads along ci, writes along co).
+// grid (Np/64, Kp/64, KH*KW), block 256.  HBM-bound: one read + one write of the weight tensor.
 __global__ void __launch_bounds__(256)
 pack_weight_transpose_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin,
-                             int T, int Kp) {
-  __shared__ float tile[32][33];
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32, tap = blockIdx.z;
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int co = co0 + r, ci = ci0 + threadIdx.x;
-    tile[r][threadIdx.x] = (co < Cout && ci < Cin)
-        ? w[((long long)co * T + (T - 1 - tap)) * Cin + ci] : 0.f;
+                             int T, int Np, int Kp) {
+  __shared__ float tile[64][65];
+  const int ci0 = blockIdx.x * 64, co0 = blockIdx.y * 64, tap = blockIdx.z;
+  const int q = threadIdx.x & 15, r = threadIdx.x >> 4;            // 16 float4 columns x 16 rows
+  const bool vec_in = (Cin & 3) == 0;
+#pragma unroll
+  for (int rr = 0; rr < 64; rr += 16) {
+    const int co = co0 + rr + r, ci = ci0 + q * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (co < Cout) {
+      const float* src = w + ((long long)co * T + (T - 1 - tap)) * Cin + ci;
+      if (vec_in && ci + 3 < Cin) v = *reinterpret_cast<const float4*>(src);
+      else {
+        if (ci < Cin) v.x = src[0];
+        if (ci + 1 < Cin) v.y = src[1];
+        if (ci + 2 < Cin) v.z = src[2];
+        if (ci + 3 < Cin) v.w = src[3];
+      }
+    }
+    tile[rr + r][q * 4 + 0] = v.x; tile[rr + r][q * 4 + 1] = v.y;
+    tile[rr + r][q * 4 + 2] = v.z; tile[rr + r][q * 4 + 3] = v.w;
   }
   __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int ci = ci0 + r, co = co0 + threadIdx.x;          // ci < Np, co < Kp by the grid
-    out[((long long)ci * T + tap) * Kp + co] = tf32_round(tile[threadIdx.x][r]);
+#pragma unroll
+  for (int rr = 0; rr < 64; rr += 16) {
+    const int ci = ci0 + rr + r, co = co0 + q * 4;                 // Np, Kp are multiples of 32: guard
+    if (ci < Np && co < Kp) {
+      const float4 o = make_float4(tf32_round(tile[q * 4 + 0][rr + r]), tf32_round(tile[q * 4 + 1][rr + r]),
+                                   tf32_round(tile[q * 4 + 2][rr + r]), tf32_round(tile[q * 4 + 3][rr + r]));
+      *reinterpret_cast<float4*>(out + ((long long)ci * T + tap) * Kp + co) = o;
+    }
   }
 }
 
@@ -584,9 +603,9 @@ extern "C" int hg_pack_conv_weight(const float* w, float* w_packed, int32_t Cout
   const int N = mode ? Cin : Cout, K = mode ? Cout : Cin;
   const int Np = (N + 31) / 32 * 32, Kp = (K + 31) / 32 * 32;
   if (ohwi && mode == 1 && KH * KW <= 65535) {
-    dim3 grid(Np / 32, Kp / 32, KH * KW);
-    pack_weight_transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream_>>>(w, w_packed, Cout, Cin,
-                                                                                 KH * KW, Kp);
+    dim3 grid((Np + 63) / 64, (Kp + 63) / 64, KH * KW);
+    pack_weight_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(w, w_packed, Cout, Cin, KH * KW, Np,
+                                                                          Kp);
     HG_LAUNCH_OK("pack_weight_transpose_kernel");
     return 0;
   }
