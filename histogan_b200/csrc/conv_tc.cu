@@ -57,6 +57,7 @@ struct ConvArgs {
   const float* residual;          // NHWC like y, added after the activation (or null)
   int noise_size;
   long long y_img, y_row, y_pix;  // output strides in floats (dense NHWC unless the caller says otherwise)
+  int tma_store;                  // TMAST kernels: 1 = stage + TMA-store the output tiles (0: direct stores)
   int desc_base_offset;           // HALO == 2: put (start >> 7) & 7 into the descriptor's base-offset field
   int ksplit;                     // > 1: the K loop (taps x 32-channel chunks) is split over ksplit work
                                   // items per output tile; each writes its raw partial sums to its own
@@ -92,33 +93,42 @@ constexpr int kResWBytes = 72 * 1024;
 constexpr int kHalo2ABytes = (16 + 2) * (8 + 2) * kBlockK * 4;     // 23040
 constexpr int kHalo2Stage = (kHalo2ABytes + 1023) / 1024 * 1024;   // ring slots stay 1024 B aligned
 
-template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false>
+// TMAST: the epilogue stages each 128-pixel x 32-channel chunk of the output tile in shared memory
+// (128 B rows, 128B-swizzled: conflict-free although every lane writes its own row) and ONE thread
+// stores it with cp.async.bulk.tensor (TMA): full 128 B lines leave the SM in one bulk operation.
+// The direct form (each lane 16 B of its own pixel row: 32 different lines per store instruction)
+// kept the LSU busy for ~256 cycles per warp and tile on the 32-channel layers.
+constexpr int kStoreStage = kBlockM * 128;         // 16 KB per epilogue set
+
+template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false, bool TMAST = false>
 struct ConvSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
   static constexpr int kAStage = HALO == 2 ? kHalo2Stage : (HALO ? kHaloABytes : kABytes);
   static constexpr int kStageBytes = kAStage + (RESW ? 0 : (HALO ? 3 : 1) * kBBytes);
   static constexpr int kRing = STAGES * kStageBytes;
-  static constexpr int kTotal = kRing + (RESW ? kResWBytes : 0) + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStore = TMAST ? kEpilogueSets * kStoreStage : 0;
+  static constexpr int kTotal = kRing + (RESW ? kResWBytes : 0) + kStore + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 // Persistent kernel: one CTA per SM walks output tiles (n fastest, so the CTAs running
 // together share A tiles through L2).  Two TMEM accumulator stages let the epilogue of
 // tile t overlap the main loop of tile t+1; the smem ring (STAGES deep) runs straight
 // through tile boundaries.
-template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false>
+template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false, bool TMAST = false>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmw,
-                 const ConvArgs a) {
+                 const __grid_constant__ CUtensorMap tmy, const ConvArgs a) {
   static_assert(!RESW || HALO, "resident weights: halo variants only");
   static_assert(HALO != 2 || RESW, "single-box halo: resident weights only");
-  using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW>;
+  using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW, TMAST>;
   constexpr uint32_t kAccCols = BLOCK_N < 32 ? 32 : BLOCK_N;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* wres = base + SM::kRing;                  // RESW: [tap][kc] filter tiles, kBBytes each
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + SM::kRing + (RESW ? kResWBytes : 0));
+  uint8_t* store_stage = base + SM::kRing + (RESW ? kResWBytes : 0);   // TMAST: [set][128 rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(base + SM::kRing + (RESW ? kResWBytes : 0) + SM::kStore);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -131,6 +141,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmx);
     ptx::prefetch_tmap(&tmw);
+    if (TMAST) ptx::prefetch_tmap(&tmy);
   }
   if (warp == 1) {
     if (ptx::elect_one()) {
@@ -322,6 +333,66 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (TMAST && a.tma_store) {
+          // every thread of the set takes part (named barriers); rows outside the image / channels
+          // beyond Cout are clipped by the TMA store, their parameter loads are guarded
+          const int n = n0 + c0;
+          const bool live = n < a.Cout;                  // warp-uniform
+          const int ncols = live ? min(32, a.Cout - n) : 0;
+          const float* ro = (a.residual && valid) ? a.residual + pix * a.Cout + n : nullptr;
+          const float* sc = (a.scale && valid) ? a.scale + (long long)b * a.Cout + n : nullptr;
+          uint8_t* stg = store_stage + set * kStoreStage;
+          const bool issuer = q == 2 && lane == 0;       // first warp of the set (warp & 3 == 2)
+          if (live) {
+            if (issuer) ptx::bulk_wait_group_read0();    // the previous store has read the staging tile
+            ptx::named_bar_sync(1 + set, 128);
+#define HG_EPILOGUE_ST(J)                                                                     \
+            {                                                                                 \
+              float4 o = make_float4(__uint_as_float(v[(J)]), __uint_as_float(v[(J) + 1]),    \
+                                     __uint_as_float(v[(J) + 2]), __uint_as_float(v[(J) + 3])); \
+              if ((J) < ncols) {                                                              \
+                if (sc) {                                                                     \
+                  const float4 s4 = __ldg(reinterpret_cast<const float4*>(sc + (J)));         \
+                  o.x *= s4.x; o.y *= s4.y; o.z *= s4.z; o.w *= s4.w;                         \
+                }                                                                             \
+                if (a.bias) {                                                                 \
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + n + (J))); \
+                  o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;                         \
+                }                                                                             \
+                if (a.noise) {                                                                \
+                  const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.noise_w + n + (J))); \
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.noise_b + n + (J))); \
+                  o.x = fmaf(nz, w4.x, o.x + b4.x); o.y = fmaf(nz, w4.y, o.y + b4.y);         \
+                  o.z = fmaf(nz, w4.z, o.z + b4.z); o.w = fmaf(nz, w4.w, o.w + b4.w);         \
+                }                                                                             \
+                if (a.flags & HG_CONV_LRELU) {                                                \
+                  o.x = o.x > 0.f ? o.x : o.x * a.slope; o.y = o.y > 0.f ? o.y : o.y * a.slope; \
+                  o.z = o.z > 0.f ? o.z : o.z * a.slope; o.w = o.w > 0.f ? o.w : o.w * a.slope; \
+                }                                                                             \
+                if (ro) {                                                                     \
+                  const float4 r4 = __ldg(reinterpret_cast<const float4*>(ro + (J)));         \
+                  o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;                         \
+                }                                                                             \
+                if (a.flags & HG_CONV_ROUND_TF32) {                                           \
+                  o.x = tf32_round(o.x); o.y = tf32_round(o.y);                               \
+                  o.z = tf32_round(o.z); o.w = tf32_round(o.w);                               \
+                }                                                                             \
+              }                                                                               \
+              /* 128B swizzle: 16-byte chunk j of row r sits at chunk j ^ (r & 7) */           \
+              *reinterpret_cast<float4*>(stg + row * 128 + ((((J) >> 2) ^ (row & 7)) << 4)) = o; \
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) HG_EPILOGUE_ST(j)
+#undef HG_EPILOGUE_ST
+            ptx::fence_proxy_async();                    // generic-proxy writes -> visible to the TMA engine
+            ptx::named_bar_sync(1 + set, 128);
+            if (issuer) {
+              ptx::tma_store_4d(&tmy, stg, n, tw_i * a.TW, th_i * a.TH, tb_i * a.TB);
+              ptx::bulk_commit_group();
+            }
+          }
+          continue;
+        }
         if (valid && n0 + c0 < a.Cout) {
           const int n = n0 + c0;
           const int ncols = min(32, a.Cout - n);       // Cout % 4 == 0
@@ -398,6 +469,7 @@ conv_tf32_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
   }
 
+  if (TMAST && warp >= 2 && (warp & 3) == 2 && lane == 0) ptx::bulk_wait_group0();   // stores landed
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, kTmemCols);
@@ -566,13 +638,14 @@ static float* splitk_workspace(size_t bytes, cudaStream_t stream) {
   return p;
 }
 
-template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false>
-static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const ConvArgs& a,
-                       int m_tiles, cudaStream_t stream) {
-  using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW>;
+template <int BLOCK_N, int STAGES, int HALO = 0, bool RESW = false, bool TMAST = false>
+static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tmy,
+                       const ConvArgs& a, int m_tiles, cudaStream_t stream) {
+  using SM = ConvSmem<BLOCK_N, STAGES, HALO, RESW, TMAST>;
+  static_assert(SM::kTotal <= 227 * 1024, "shared memory budget");
   static PerDeviceOnce attr_once;
   if (attr_once.need()) {
-    HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW>,
+    HG_CUDA_OK(cudaFuncSetAttribute(conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW, TMAST>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_once.mark();
   }
@@ -580,7 +653,7 @@ static int launch_conv(const CUtensorMap& tmx, const CUtensorMap& tmw, const Con
   const int sms = device_info().sm_count > 0 ? device_info().sm_count : 148;
   const int grid = total < sms ? total : sms;
   const bool split = !HALO && a.ksplit > 1;
-  conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, a);
+  conv_tf32_kernel<BLOCK_N, STAGES, HALO, RESW, TMAST><<<grid, kConvThreads, SM::kTotal, stream>>>(tmx, tmw, tmy, a);
   HG_LAUNCH_OK("conv_tf32_kernel");
   if (split) {
     const long long n4 = (long long)a.B * a.OH * a.OW * (a.Cout / 4);
@@ -734,10 +807,26 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     int rc = encode_map(&tmw, w_packed, 2, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     if (rc) return rc;
   }
+  // TMA-store epilogue for the narrow layers (BLOCK_N <= 64: little math per output byte, the epilogue
+  // dominates) whenever the output is expressible as a tensor map and the K loop is not split
+  static const bool tmast_enabled = [] {
+    const char* e = getenv("HG_CONV_TMA_STORE");
+    return e ? e[0] != '0' : true;
+  }();
+  alignas(64) CUtensorMap tmy = tmx;
+  a.tma_store = 0;
+  if (tmast_enabled && BN <= 64 && a.ksplit == 1) {
+    cuuint64_t dims[4] = {(cuuint64_t)p->Cout, (cuuint64_t)OW, (cuuint64_t)OH, (cuuint64_t)p->B};
+    cuuint64_t strides[3] = {(cuuint64_t)a.y_pix * 4, (cuuint64_t)a.y_row * 4, (cuuint64_t)a.y_img * 4};
+    cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (encode_map(&tmy, y, 4, dims, strides, box, estr, CU_TENSOR_MAP_L2_PROMOTION_NONE) == 0)
+      a.tma_store = 1;
+  }
   if (halo2) {
     a.ksplit = 1;
-    if (BN == 64) return launch_conv<64, 5, 2, true>(tmx, tmw, a, m_tiles, stream);
-    return launch_conv<32, 5, 2, true>(tmx, tmw, a, m_tiles, stream);
+    if (BN == 64) return launch_conv<64, 4, 2, true, true>(tmx, tmw, tmy, a, m_tiles, stream);
+    return launch_conv<32, 4, 2, true, true>(tmx, tmw, tmy, a, m_tiles, stream);
   }
   if (halo) {
     static const bool resw_enabled = [] {
@@ -750,14 +839,14 @@ extern "C" int hg_conv2d_fwd(const float* x, const float* w_packed, float* y,
     // loss -- 242 -> 255 us -- so one chunk per tap only)
     if (resw_enabled && a.n_tiles == 1 && a.kc_per_tap == 1 &&
         9 * a.kc_per_tap * BN * kBlockK * 4 <= kResWBytes && m_tiles >= 4 * 148) {
-      if (BN == 64) return launch_conv<64, 6, 1, true>(tmx, tmw, a, m_tiles, stream);
-      if (BN == 32) return launch_conv<32, 7, 1, true>(tmx, tmw, a, m_tiles, stream);
+      if (BN == 64) return launch_conv<64, 5, 1, true, true>(tmx, tmw, tmy, a, m_tiles, stream);
+      if (BN == 32) return launch_conv<32, 5, 1, true, true>(tmx, tmw, tmy, a, m_tiles, stream);
     }
-    if (BN == 128) return launch_conv<128, 3, 1>(tmx, tmw, a, m_tiles, stream);
-    if (BN == 64) return launch_conv<64, 4, 1>(tmx, tmw, a, m_tiles, stream);
-    return launch_conv<32, 6, 1>(tmx, tmw, a, m_tiles, stream);
+    if (BN == 128) return launch_conv<128, 3, 1>(tmx, tmw, tmy, a, m_tiles, stream);
+    if (BN == 64) return launch_conv<64, 4, 1, false, true>(tmx, tmw, tmy, a, m_tiles, stream);
+    return launch_conv<32, 5, 1, false, true>(tmx, tmw, tmy, a, m_tiles, stream);
   }
-  if (BN == 128) return launch_conv<128, 6>(tmx, tmw, a, m_tiles, stream);
-  if (BN == 64) return launch_conv<64, 8>(tmx, tmw, a, m_tiles, stream);
-  return launch_conv<32, 8>(tmx, tmw, a, m_tiles, stream);
+  if (BN == 128) return launch_conv<128, 6>(tmx, tmw, tmy, a, m_tiles, stream);
+  if (BN == 64) return launch_conv<64, 7, 0, false, true>(tmx, tmw, tmy, a, m_tiles, stream);
+  return launch_conv<32, 8, 0, false, true>(tmx, tmw, tmy, a, m_tiles, stream);
 }
