@@ -82,6 +82,12 @@ _SIGNATURES = {
     "hg_grouped_linear_bwd": (C.c_int, [C.c_int32] + [C.c_void_p] * 8 + [C.c_int32, C.c_int32, C.c_void_p]),
     "hg_weight_sqsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "hg_demod_bwd": (C.c_int, [C.c_void_p] * 8 + [C.c_int32] * 4 + [C.c_void_p]),
+    "hg_conv_small_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 7 + [C.c_int64] * 4 + [C.c_int32, C.c_float,
+                                                                                      C.c_void_p]),
+    "hg_conv_small_dgrad": (C.c_int, [C.c_void_p] * 3 + [C.c_int32] * 7 + [C.c_int64] * 4 + [C.c_void_p]),
+    "hg_conv_small_wgrad_workspace_bytes": (C.c_size_t, [C.c_int32] * 3),
+    "hg_conv_small_wgrad": (C.c_int, [C.c_void_p] * 4 + [C.c_size_t] + [C.c_int32] * 7 + [C.c_int64] * 4 +
+                            [C.c_void_p]),
     "hg_pad_round_nhwc": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_int32] * 5 + [C.c_int64] * 4 + [C.c_void_p]),
     "hg_upsample2x_planar": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        C.c_void_p]),

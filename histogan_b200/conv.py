@@ -166,3 +166,61 @@ def conv2d_wgrad_nhwc(dy: torch.Tensor, x: torch.Tensor, ksize: int, stride: int
     if dw.shape[1] != Cin:                           # drop the K padding (small-channel layers only)
         dw = dw[:, :Cin].contiguous(memory_format=torch.channels_last)
     return dw
+
+
+# ---------------------------------------------------------------- image-input convolutions ----
+def small_ok(cin: int, cout: int, k: int, stride: int, pad: int) -> bool:
+    """can this conv run on the direct (CUDA-core) kernels for 3/4-channel inputs (conv_small.cu)?"""
+    return cin <= 4 and cout % 4 == 0 and cout <= 64 and k in (1, 3) and stride == 1 and pad == k // 2
+
+
+def conv_small_fwd(x, w, cp, bias=None, residual=None, lrelu=False, slope=0.2, round_tf32=False):
+    """y (B,cp,H,W) channels_last = [round]([lrelu](conv(x, w) + bias) [+ residual]); x (B,Cin<=4,H,W)
+    float32 with any strides (the planar image as it is), w (Cout,Cin,k,k)."""
+    lib = _lib.load()
+    B, Cin, H, W = x.shape
+    Cout, _, k, _ = w.shape
+    wc = w.detach().float().contiguous()                      # OIHW (a few hundred floats)
+    y = torch.empty((B, cp, H, W), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
+    res = as_nhwc(residual) if residual is not None else None
+    if res is not None:
+        assert tuple(res.shape) == tuple(y.shape)
+    flags = (CONV_LRELU if lrelu else 0) | (CONV_ROUND_TF32 if round_tf32 else 0)
+    b = bias.detach().float().contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        rc = lib.hg_conv_small_fwd(_lib.ptr(x), _lib.ptr(wc), _lib.ptr(b), _lib.ptr(res), _lib.ptr(y), B, Cin, H, W,
+                                   Cout, cp, k, *x.stride(), flags, float(slope), _lib.current_stream_ptr(x.device))
+    _lib.check(rc, "hg_conv_small_fwd")
+    return y
+
+
+def conv_small_dgrad(dy, w, cin):
+    """dx (B,cin,H,W) contiguous = conv^T(dy, w); dy (B,Cp,H,W) channels_last, Cp >= Cout"""
+    lib = _lib.load()
+    dy = as_nhwc(dy)
+    B, Cp, H, W = dy.shape
+    Cout, _, k, _ = w.shape
+    wc = w.detach().float().contiguous()
+    dx = torch.empty((B, cin, H, W), dtype=torch.float32, device=dy.device)
+    with torch.cuda.device(dy.device):
+        rc = lib.hg_conv_small_dgrad(_lib.ptr(dy), _lib.ptr(wc), _lib.ptr(dx), B, cin, H, W, Cout, Cp, k,
+                                     *dx.stride(), _lib.current_stream_ptr(dy.device))
+    _lib.check(rc, "hg_conv_small_dgrad")
+    return dx
+
+
+def conv_small_wgrad(dy, x, wshape):
+    """dw (Cout,Cin,k,k) from dy (B,Cp,H,W) channels_last and the image x (B,Cin,H,W) (any strides)"""
+    lib = _lib.load()
+    dy = as_nhwc(dy)
+    B, Cp, H, W = dy.shape
+    Cout, Cin, k, _ = wshape
+    dw = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=dy.device)
+    nws = lib.hg_conv_small_wgrad_workspace_bytes(Cin, Cout, k)
+    ws = torch.empty(nws, dtype=torch.uint8, device=dy.device)
+    xf = x if x.dtype == torch.float32 else x.float()
+    with torch.cuda.device(dy.device):
+        rc = lib.hg_conv_small_wgrad(_lib.ptr(dy), _lib.ptr(xf), _lib.ptr(dw), _lib.ptr(ws), nws, B, Cin, H, W,
+                                     Cout, Cp, k, *xf.stride(), _lib.current_stream_ptr(dy.device))
+    _lib.check(rc, "hg_conv_small_wgrad")
+    return dw

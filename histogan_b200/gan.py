@@ -234,7 +234,9 @@ class DiscriminatorBlock(nn.Module):
 
     def forward(self, x):
         if USE_FUSED and x.is_cuda:
-            y = self.forward_padded(ops.round_pad(x), round_out=False)
+            small = ops.SMALL_CIN and ops._small(x.shape[1], self.net[0].weight, 1, 1) and \
+                ops._small(x.shape[1], self.conv_res.weight, 1, 0)
+            y = self.forward_padded(x if small else ops.round_pad(x), round_out=False)
             c = self.conv_res.out_channels
             return y if y.shape[1] == c else y[:, :c]
         res = self._conv(self.conv_res, x)
@@ -378,7 +380,11 @@ class Discriminator(nn.Module):
     def forward(self, x):
         quantize_loss = torch.zeros(1, device=x.device, dtype=x.dtype)
         if USE_FUSED and x.is_cuda:
-            x = ops.round_pad(x)                            # image: pad 3 -> 32 channels, round once
+            b0 = self.blocks[0]
+            if not (ops.SMALL_CIN and ops._small(x.shape[1], b0.net[0].weight, 1, 1)
+                    and ops._small(x.shape[1], b0.conv_res.weight, 1, 0)):
+                x = ops.round_pad(x)                        # image: pad 3 -> 32 channels, round once
+            # else: block 0's two image-input convs read the planar image directly (conv_small.cu)
             for i, block in enumerate(self.blocks):
                 x = block.forward_padded(x, round_out=i != len(self.blocks) - 1)
             c = self.blocks[-1].conv_res.out_channels

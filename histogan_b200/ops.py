@@ -40,6 +40,7 @@ from . import conv as _conv
 import os as _os
 
 _CH = int(_os.environ.get("HG_CH_PAD", "32"))      # 16 / 32 (experiment knob)
+SMALL_CIN = _os.environ.get("HG_SMALL_CIN", "1") != "0"   # image-input convs on the direct kernels
 
 
 def _round_up(n, m=_CH):
@@ -194,8 +195,15 @@ def _match_channels(y: torch.Tensor, c: int) -> torch.Tensor:
 
 # the three raw primitives (tests/emulation.py swaps these for torch stand-ins on CPU) ------
 
+def _small(x_channels, w, stride, pad):
+    """image-input conv (Cin <= 4, e.g. DiscriminatorBlock 0): direct CUDA-core kernels, no padding"""
+    return x_channels == w.shape[1] and _conv.small_ok(w.shape[1], w.shape[0], w.shape[2], stride, pad)
+
+
 def _raw_conv(x, w, stride, pad, x_rounded=False, padded_io=False):
     """padded_io: x / y carry round_up(C, 32) channels (zeros in the padding) instead of C"""
+    if _small(x.shape[1], w, stride, pad):
+        return _conv.conv_small_fwd(x, w, _round_up(w.shape[0]) if padded_io else w.shape[0])
     y = _conv.conv2d_nhwc(round_tf32_nhwc(x, x_rounded), _packs.get(w, 0), stride, pad,
                           cout=_round_up(w.shape[0]))
     return y if padded_io else _match_channels(y, w.shape[0])
@@ -203,6 +211,8 @@ def _raw_conv(x, w, stride, pad, x_rounded=False, padded_io=False):
 
 def _raw_grad_input(dy, w, stride, pad, in_hw, dy_rounded=False, padded_io=False):
     k = w.shape[2]
+    if _conv.small_ok(w.shape[1], w.shape[0], k, stride, pad) and tuple(in_hw) == tuple(dy.shape[2:]):
+        return _conv.conv_small_dgrad(dy, w, w.shape[1])          # true Cin channels, planar
     if (stride == 2 and k == 3 and pad == 1 and in_hw[0] == 2 * dy.shape[2]
             and in_hw[1] == 2 * dy.shape[3] and in_hw[0] * in_hw[1] >= _S2_MIN_PIXELS):
         # four parity classes of dx, each a 1..4-tap convolution over dy written straight into
@@ -253,6 +263,8 @@ def grad_slot(w):
 
 def _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=False, out=None):
     k = wshape[2]
+    if x.shape[1] == wshape[1] and _conv.small_ok(wshape[1], wshape[0], k, stride, pad):
+        return _conv.conv_small_wgrad(dy, x, wshape).contiguous(memory_format=torch.channels_last)
     dw = _conv.conv2d_wgrad_nhwc(round_tf32_nhwc(dy, dy_rounded), round_tf32_nhwc(x, x_rounded), k,
                                  stride, pad, out=out)
     if tuple(dw.shape[:2]) != tuple(wshape[:2]):
@@ -377,6 +389,13 @@ class _ConvBiasAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, res, stride, pad, act, slope, x_rounded, round_out):
         cout_p = _round_up(w.shape[0])
+        if x.is_cuda and _small(x.shape[1], w, stride, pad):
+            # the raw image: direct kernel with the same fused epilogue, nothing padded or rounded
+            y = _conv.conv_small_fwd(x, w, cout_p, bias=b, residual=res, lrelu=act, slope=slope,
+                                     round_tf32=round_out)
+            ctx.save_for_backward(x, w, y if act else None)
+            ctx.cfg = (stride, pad, act, slope, b is not None, res is not None, tuple(x.shape))
+            return y
         xr = round_tf32_nhwc(x, x_rounded)
         bp = None
         if b is not None:

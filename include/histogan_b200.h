@@ -287,6 +287,29 @@ int hg_demod_bwd(const float* gd, const float* d, const float* mod, const float*
                  const float* w, float* gmod_accum, float* dw_accum, float* t_ws, int32_t B,
                  int32_t Cout, int32_t T, int32_t Cin, hg_stream_t stream);
 
+/* ------------------------------------------------------------------------ *
+ * Convolutions whose INPUT is the 3/4-channel image (DiscriminatorBlock 0: conv_res 1x1, net[0] 3x3;
+ * histoGAN/histoGAN.py:507-511,520-523) on the CUDA cores, exact fp32, reading the planar image with
+ * its own strides (csrc/conv_small.cu).  k in {1,3}, stride 1, pad k/2, Cin <= 4, Cout % 4 == 0, <= 64.
+ * w: contiguous OIHW.  NHWC tensors (y, dy, residual) carry Cp >= Cout channels (Cp % 4 == 0; y's
+ * padding channels are written as zeros).  sb,sc,sh,sw: element strides of the planar tensor.
+ *   fwd   y = [round]( [lrelu](conv(x, w) + bias) [+ residual] )     flags: HG_CONV_LRELU | HG_CONV_ROUND_TF32
+ *   dgrad dx (planar, fully written) = conv^T(dy, w)
+ *   wgrad dw (contiguous OIHW) = sum over batch and pixels; deterministic (per-CTA partials in ws,
+ *         hg_conv_small_wgrad_workspace_bytes, added in index order)
+ * ------------------------------------------------------------------------ */
+int hg_conv_small_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                      int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t Cp, int32_t k,
+                      int64_t sb, int64_t sc, int64_t sh, int64_t sw, int32_t flags, float slope,
+                      hg_stream_t stream);
+int hg_conv_small_dgrad(const float* dy, const float* w, float* dx, int32_t B, int32_t Cin, int32_t H,
+                        int32_t W, int32_t Cout, int32_t Cp, int32_t k, int64_t sb, int64_t sc, int64_t sh,
+                        int64_t sw, hg_stream_t stream);
+size_t hg_conv_small_wgrad_workspace_bytes(int32_t Cin, int32_t Cout, int32_t k);
+int hg_conv_small_wgrad(const float* dy, const float* x, float* dw, void* ws, size_t ws_bytes, int32_t B,
+                        int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t Cp, int32_t k, int64_t sb,
+                        int64_t sc, int64_t sh, int64_t sw, hg_stream_t stream);
+
 /* Discriminator input staging (histoGAN/histoGAN.py:613-617): x (B,C,H,W) float32 with element
  * strides sb,sc,sh,sw -> out NHWC (B,H,W,Cp), channels zero-padded to Cp (multiple of 4),
  * TF32-rounded (round to nearest even), in one pass.                                   */

@@ -159,3 +159,44 @@ def test_wgrad_matches_torch(case, cuda_device):
     dw = conv.conv2d_wgrad_nhwc(dy, x, k, stride, pad)
     err = (dw - ref.float()).abs().max().item() / ref.abs().max().item()
     assert err < 2e-5, err
+
+
+SMALL_CASES = [
+    # B, Cin, H, W, Cout, k, Cp
+    (2, 3, 32, 32, 16, 3, 32),     # DiscriminatorBlock 0 net[0], channel-padded output
+    (2, 3, 32, 32, 16, 1, 32),     # ... conv_res
+    (3, 3, 19, 23, 24, 3, 24),     # odd sizes, Cout not a power of two, dense output
+    (1, 4, 16, 16, 64, 3, 64),     # transparent images (4 channels), widest supported layer
+    (5, 3, 64, 64, 16, 1, 16),
+]
+
+
+@pytest.mark.parametrize("case", SMALL_CASES, ids=[str(c) for c in SMALL_CASES])
+def test_image_input_conv_kernels_match_torch(case, cuda_device):
+    """conv_small.cu (the discriminator's image-input convolutions on the CUDA cores, exact fp32):
+    forward with the fused epilogue, input gradient, weight gradient -- against torch float64, on a
+    NON-contiguous planar image (the kernels take element strides)."""
+    from histogan_b200 import conv
+    B, Cin, H, W, Cout, k, Cp = case
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(B, Cin + 1, H, W + 3, generator=g).cuda()
+    x = big[:, :Cin, :, 2:2 + W]                                   # strided view
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).cuda()
+    bias = torch.randn(Cout, generator=g).cuda()
+    res = torch.randn(B, Cp, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    assert conv.small_ok(Cin, Cout, k, 1, k // 2)
+    y = conv.conv_small_fwd(x, w, Cp, bias=bias, residual=res, lrelu=True, slope=0.2)
+    ref = F.leaky_relu(F.conv2d(x.double(), w.double(), bias.double(), padding=k // 2), 0.2) + res[:, :Cout].double()
+    assert y.shape == (B, Cp, H, W) and y.is_contiguous(memory_format=torch.channels_last)
+    assert (y[:, :Cout].double() - ref).abs().max().item() < 1e-5 * ref.abs().max().item()
+    assert (y[:, Cout:] == 0).all()                                # padding channels are zeros
+    y2 = conv.conv_small_fwd(x, w, Cp, round_tf32=True)
+    assert torch.equal(y2, conv.tf32_round(conv.conv_small_fwd(x, w, Cp)))
+    dy = torch.randn(B, Cp, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    dx = conv.conv_small_dgrad(dy, w, Cin)
+    dx_ref = torch.nn.grad.conv2d_input((B, Cin, H, W), w.double(), dy[:, :Cout].double(), padding=k // 2)
+    assert (dx.double() - dx_ref).abs().max().item() < 1e-5 * dx_ref.abs().max().item()
+    dw = conv.conv_small_wgrad(dy, x, (Cout, Cin, k, k))
+    dw_ref = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, k, k), dy[:, :Cout].double(), padding=k // 2)
+    assert (dw.double() - dw_ref).abs().max().item() < 2e-5 * dw_ref.abs().max().item()
+    assert torch.equal(dw, conv.conv_small_wgrad(dy, x, (Cout, Cin, k, k)))      # deterministic
