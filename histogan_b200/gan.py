@@ -24,6 +24,10 @@ from . import fused, ops
 
 # fused generator layers (fused.py); False = compose torch ops around ops.conv2d
 USE_FUSED = True
+# precomputed modulations / demodulation factors for the whole generator pass (fused.style_mods,
+# demod_all); False = per-block nn.Linear + torch demodulation (debug switch)
+import os as _os
+STYLE_PATH = _os.environ.get("HG_STYLE_PATH", "1") != "0"
 
 EPS = 1e-8          # histoGAN/histoGAN.py:53
 
@@ -326,7 +330,7 @@ class Generator(nn.Module):
         # blocks 0..L-3 take the mapped latent, the last two the histogram latent (:561-563)
         per_block = torch.cat((styles.transpose(0, 1), hists.transpose(0, 1)), dim=0)
         rgb = None
-        if USE_FUSED and x.is_cuda and self._style_path_ok(x.shape, input_noise):
+        if USE_FUSED and STYLE_PATH and x.is_cuda and self._style_path_ok(x.shape, input_noise):
             # the 21 to_style Linears (+1) of all blocks in one launch, the 14 demodulation factors
             # in a second one (fused.style_mods / demod_all); the blocks then run on those
             linears = []

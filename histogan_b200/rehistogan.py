@@ -661,6 +661,8 @@ class recoloringTrainer():
 
     # ---------------------------------------------------------- CUDA-graph path --
     _graphed = Trainer._graphed          # capture once / replay / re-attach the graph's gradients
+    _capture = Trainer._capture
+    _replay = Trainer._replay
 
     def _phase_d(self, apply_gp):
         GAN, st = self.GAN, self._static

@@ -180,8 +180,9 @@ class HistoGAN(nn.Module):
         ma_p, cur_p = [], []
         for ma, cur in ((self.SE, self.S), (self.HE, self.H), (self.GE, self.G)):
             for a, c in zip(ma.parameters(), cur.parameters()):
+                dense = a.is_contiguous() or (a.dim() == 4 and a.is_contiguous(memory_format=torch.channels_last))
                 same = a.shape == c.shape and (a.stride() == c.stride()) and a.is_cuda and \
-                    a.dtype == c.dtype == torch.float32 and a.is_non_overlapping_and_dense()
+                    a.dtype == c.dtype == torch.float32 and dense
                 if same:
                     ma_p.append(a); cur_p.append(c)
                 else:               # layouts differ (e.g. a state_dict loaded into another format)

@@ -131,7 +131,18 @@ def emulated_step_tables(case, golden=None):
     return scal, td, tg
 
 
-def within_floor(tab, tab_emu, norm_margin=2e-2, cos_margin=1e-3):
-    """{tensor: (measured, floor)} for every tensor further from the golden than 2x the TF32 floor"""
+def rel_error(entry):
+    """|g - ref| / |ref| (on the stored entries) from a table entry (norm_rel, cosine, ...): with
+    r = |g|/|ref| = 1 +- norm_rel,  e^2 = 1 + r^2 - 2 r cos.  One number for "how far", so that a tensor
+    whose floor is mostly a direction error is not failed for a norm error of the same size."""
+    import math
+    nr, cos = float(entry[0]), float(entry[1])
+    return max(math.sqrt(max(1 + (1 + nr) ** 2 - 2 * (1 + nr) * cos, 0.0)),
+               math.sqrt(max(1 + (1 - nr) ** 2 - 2 * (1 - nr) * cos, 0.0)))
+
+
+def within_floor(tab, tab_emu, margin=3e-2):
+    """{tensor: (measured, floor)} for every tensor whose relative error vs the golden exceeds 2x the
+    relative error of the TF32 emulation of the same algorithm (+ margin)"""
     return {k: (v, tab_emu[k]) for k, v in tab.items()
-            if v[0] > 2 * tab_emu[k][0] + norm_margin or (1 - v[1]) > 2 * (1 - tab_emu[k][1]) + cos_margin}
+            if rel_error(v) > 2 * rel_error(tab_emu[k]) + margin}

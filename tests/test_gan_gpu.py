@@ -115,10 +115,8 @@ def test_generator_256_matches_reference(cuda_device):
 
 
 def _within_floor(tab_gpu, tab_emu):
-    """every tensor no further from the fp32 golden than 2x the TF32 emulation of the same algorithm
-    (norm: + 2e-2; direction: 1 - cos <= 2 (1 - cos_emu) + 1e-3)"""
-    return {k: (v, tab_emu[k]) for k, v in tab_gpu.items()
-            if v[0] > 2 * tab_emu[k][0] + 2e-2 or (1 - v[1]) > 2 * (1 - tab_emu[k][1]) + 1e-3}
+    from tests import step_checks as sc
+    return sc.within_floor(tab_gpu, tab_emu)
 
 
 def test_discriminator_256_matches_reference(cuda_device):
