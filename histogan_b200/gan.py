@@ -28,6 +28,7 @@ USE_FUSED = True
 # demod_all); False = per-block nn.Linear + torch demodulation (debug switch)
 import os as _os
 STYLE_PATH = _os.environ.get("HG_STYLE_PATH", "1") != "0"
+DEMOD_PATH = _os.environ.get("HG_DEMOD_PATH", "1") != "0"      # grouped demodulation + analytic backward
 
 EPS = 1e-8          # histoGAN/histoGAN.py:53
 
@@ -209,9 +210,14 @@ class GeneratorBlock(nn.Module):
         """forward on precomputed modulations (style + 1) and demodulation factors"""
         nz = inoise if inoise.is_contiguous() else inoise.contiguous()
         wsq1, wsq2 = ops._packs.get(self.conv1.weight, 'wsq'), ops._packs.get(self.conv2.weight, 'wsq')
-        x = fused.mod_conv_layer_pre(x, mod1, self.conv1.weight, d1, wsq1, nz, self.to_noise1,
+        if d1 is None:      # debug switch: demodulation by torch ops + autograd (style = mod - 1)
+            x = fused.mod_conv_layer(x, mod1 - 1, self.conv1.weight, True, nz, self.to_noise1,
                                      upsample=self.upsample is not None)
-        x = fused.mod_conv_layer_pre(x, mod2, self.conv2.weight, d2, wsq2, nz, self.to_noise2)
+            x = fused.mod_conv_layer(x, mod2 - 1, self.conv2.weight, True, nz, self.to_noise2)
+        else:
+            x = fused.mod_conv_layer_pre(x, mod1, self.conv1.weight, d1, wsq1, nz, self.to_noise1,
+                                         upsample=self.upsample is not None)
+            x = fused.mod_conv_layer_pre(x, mod2, self.conv2.weight, d2, wsq2, nz, self.to_noise2)
         rgb = fused.to_rgb_mod(x, mod_rgb, self.to_rgb.conv.weight, prev_rgb)
         if self.to_rgb.upsample is not None:
             rgb = fused.upsample2x_planar(rgb)
@@ -339,7 +345,7 @@ class Generator(nn.Module):
             mods = fused.style_mods(per_block, linears)
             conv_mods = [m for i in range(len(self.blocks)) for m in mods[3 * i:3 * i + 2]]
             wsqs = [ops._packs.get(c.weight, 'wsq') for b in self.blocks for c in (b.conv1, b.conv2)]
-            ds = fused.demod_all(conv_mods, wsqs, EPS)
+            ds = fused.demod_all(conv_mods, wsqs, EPS) if DEMOD_PATH else [None] * len(conv_mods)
             for i, block in enumerate(self.blocks):
                 # through __call__, so that forward hooks on the blocks keep firing
                 x, rgb = block(x, rgb, per_block[i], input_noise,

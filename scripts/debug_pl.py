@@ -23,10 +23,38 @@ def run(case, tag):
         print(f"[{tag}] case {case}: worst {sc.worst(tab)}\n   {len(bad)} tensors below 0.99: {dict(list(bad.items())[:8])}", flush=True)
 
 
-for case in (1, 32):
-    gan.USE_FUSED, gan.STYLE_PATH = True, True
-    run(case, "fused+style")
-    gan.STYLE_PATH = False
-    run(case, "fused, per-block styles")
-    gan.USE_FUSED = False
-    run(case, "composed torch ops")
+for case in (32,):
+    gan.USE_FUSED, gan.STYLE_PATH, gan.DEMOD_PATH = True, True, True
+    run(case, "fused+style+demod")
+    gan.DEMOD_PATH = False
+    run(case, "fused+style, torch demod")
+    gan.DEMOD_PATH = True
+    import histogan_b200.fused as fz
+    real_bwd = fz.grouped_linear_bwd
+    def torch_bwd(xs, ws, gys, gws, gbs, gxs, flags=0):
+        for x, w, gy, gw, gb, gx in zip(xs, ws, gys, gws, gbs, gxs):
+            xe = x * x if flags & fz.LIN_SQUARE_INPUT else x
+            if gw is not None: gw.copy_(gy.t() @ xe)
+            if gb is not None: gb.copy_(gy.sum(0))
+            if gx is not None:
+                v = gy @ w
+                if flags & fz.LIN_POST_2X: v = v * 2 * x
+                gx.copy_(gx + v if flags & fz.LIN_ACCUMULATE else v)
+    fz.grouped_linear_bwd = torch_bwd
+    run(case, "fused+style+demod, style-linear backward by torch")
+    fz.grouped_linear_bwd = real_bwd
+    real_fwd = fz.grouped_linear
+    def torch_fwd(xs, ws, bs, flags=0, slope=0.2, eps=1e-8):
+        out = []
+        for x, w, b in zip(xs, ws, bs):
+            xe = x * x if flags & fz.LIN_SQUARE_INPUT else x
+            v = xe @ w.t()
+            if b is not None: v = v + b
+            if flags & fz.LIN_RSQRT_EPS: v = torch.rsqrt(v + eps)
+            if flags & fz.LIN_LRELU: v = torch.nn.functional.leaky_relu(v, slope)
+            if flags & fz.LIN_ADD_ONE: v = v + 1
+            out.append(v.contiguous())
+        return out
+    fz.grouped_linear = torch_fwd
+    run(case, "fused+style+demod, grouped forward by torch")
+    fz.grouped_linear = real_fwd
