@@ -29,53 +29,68 @@ struct SmallConvArgs {
   float slope;
 };
 
-// thread = (pixel, channel quad of the NHWC output); the quads beyond Cout write zeros (padding channels)
+// thread = one pixel x 16 output channels (blockIdx.y selects the group of 16): the k*k*Cin image values
+// are loaded once per pixel, the weights come from shared memory as warp-wide broadcasts ([ci][tap][co]),
+// 32-bit index arithmetic throughout (B*H*W < 2^31).  Channels beyond Cout are written as zeros.
 __global__ void __launch_bounds__(256)
 conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ residual, float* __restrict__ y, const SmallConvArgs a,
-                      long long total) {
-  __shared__ float sw[kSmallMaxCout * kSmallMaxCin * kSmallMaxTaps];   // [co][ci][tap]
-  __shared__ float sb[kSmallMaxCout];
-  const int taps = a.k * a.k, wn = a.Cout * a.Cin * taps;
-  for (int i = threadIdx.x; i < wn; i += 256) sw[i] = w[i];
-  for (int i = threadIdx.x; i < a.Cout; i += 256) sb[i] = bias ? bias[i] : 0.f;
+                      int n_pix) {
+  __shared__ __align__(16) float sw[kSmallMaxCin * kSmallMaxTaps * 16];   // [ci][tap][16 co of this group]
+  __shared__ float sb[16];
+  const int taps = a.k * a.k;
+  const int cg = blockIdx.y * 16;                    // first output channel of this thread group
+  for (int i = threadIdx.x; i < a.Cin * taps * 16; i += 256) {
+    const int co = i & 15, t = (i >> 4) % taps, ci = (i >> 4) / taps;
+    sw[i] = cg + co < a.Cout ? w[((cg + co) * a.Cin + ci) * taps + t] : 0.f;
+  }
+  if (threadIdx.x < 16) sb[threadIdx.x] = (bias && cg + threadIdx.x < a.Cout) ? bias[cg + threadIdx.x] : 0.f;
   __syncthreads();
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= total) return;
-  const int q = a.Cp / 4;
-  const int c0 = (int)(i % q) * 4;
-  const long long p = i / q;
-  const int ow = (int)(p % a.W), oh = (int)((p / a.W) % a.H);
-  const long long b = p / ((long long)a.W * a.H);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  if (c0 < a.Cout) {
-    const int pad = a.k / 2;
-    const float* xb = x + b * a.sb;
-#pragma unroll 1
-    for (int ci = 0; ci < a.Cin; ++ci) {
-      for (int kh = 0; kh < a.k; ++kh) {
-        const int ih = oh + kh - pad;
-        if (ih < 0 || ih >= a.H) continue;
-        for (int kw = 0; kw < a.k; ++kw) {
-          const int iw = ow + kw - pad;
-          if (iw < 0 || iw >= a.W) continue;
-          const float xv = __ldg(xb + ci * a.sc + (long long)ih * a.sh + (long long)iw * a.sw);
-          const int t = kh * a.k + kw;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= n_pix) return;
+  const int ow = p % a.W, r = p / a.W, oh = r % a.H, b = r / a.H;
+  float acc[16];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) acc[e] = fmaf(xv, sw[((c0 + e) * a.Cin + ci) * taps + t], acc[e]);
+  for (int e = 0; e < 16; ++e) acc[e] = sb[e];
+  const int pad = a.k / 2;
+  const float* xb = x + (long long)b * a.sb;
+  for (int ci = 0; ci < a.Cin; ++ci) {
+    for (int kh = 0; kh < a.k; ++kh) {
+      const int ih = oh + kh - pad;
+      if (ih < 0 || ih >= a.H) continue;
+      for (int kw = 0; kw < a.k; ++kw) {
+        const int iw = ow + kw - pad;
+        if (iw < 0 || iw >= a.W) continue;
+        const float xv = __ldg(xb + ci * a.sc + (long long)ih * a.sh + (long long)iw * a.sw);
+        const float4* wp = reinterpret_cast<const float4*>(sw + (ci * taps + kh * a.k + kw) * 16);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const float4 wv = wp[qd];
+          acc[qd * 4 + 0] = fmaf(xv, wv.x, acc[qd * 4 + 0]); acc[qd * 4 + 1] = fmaf(xv, wv.y, acc[qd * 4 + 1]);
+          acc[qd * 4 + 2] = fmaf(xv, wv.z, acc[qd * 4 + 2]); acc[qd * 4 + 3] = fmaf(xv, wv.w, acc[qd * 4 + 3]);
         }
       }
     }
+  }
+  float* yo = y + (long long)p * a.Cp + cg;
+  const float* ro = residual ? residual + (long long)p * a.Cp + cg : nullptr;
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    if (cg + qd * 4 >= a.Cp) break;
+    float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      float v = acc[e] + sb[c0 + e];
-      if (a.flags & HG_CONV_LRELU) v = v > 0.f ? v : v * a.slope;
-      if (residual) v += residual[p * a.Cp + c0 + e];          // added after the activation (:523)
-      if (a.flags & HG_CONV_ROUND_TF32) v = tf32_round(v);
-      acc[e] = v;
+      float t = acc[qd * 4 + e];
+      if (cg + qd * 4 + e >= a.Cout) t = 0.f;
+      else {
+        if (a.flags & HG_CONV_LRELU) t = t > 0.f ? t : t * a.slope;
+        if (ro) t += ro[qd * 4 + e];                              // added after the activation (:523)
+        if (a.flags & HG_CONV_ROUND_TF32) t = tf32_round(t);
+      }
+      v[e] = t;
     }
+    *reinterpret_cast<float4*>(yo + qd * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  *reinterpret_cast<float4*>(y + p * a.Cp + c0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
 
 // thread = one input pixel: all Cin channels of dx (planar, strided)
@@ -89,10 +104,10 @@ conv_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ 
     sw[(t * a.Cin + ci) * a.Cout + co] = w[i];
   }
   __syncthreads();
-  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (p >= total) return;
-  const int iw = (int)(p % a.W), ih = (int)((p / a.W) % a.H);
-  const long long b = p / ((long long)a.W * a.H);
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= (int)total) return;
+  const int iw = p % a.W, r = p / a.W, ih = r % a.H;
+  const long long b = r / a.H;
   const int pad = a.k / 2;
   float acc[kSmallMaxCin] = {0.f, 0.f, 0.f, 0.f};
   for (int kh = 0; kh < a.k; ++kh) {
@@ -121,76 +136,62 @@ conv_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ 
     if (ci < a.Cin) o[ci * a.sc] = acc[ci];
 }
 
-// dw[co][ci][tap]: thread = (pixel lane, co quad) keeps 4 x Cin x taps accumulators in registers while it
-// walks its pixels; per CTA the lanes are summed through shared memory (fixed order), each CTA writes ONE
-// partial vector, conv_small_wgrad_finish adds the CTAs in index order.
+// dw[co][ci][tap]: thread = (pixel lane, co quad, ci) keeps 4 x taps accumulators in registers while it
+// walks its pixels (32-bit index arithmetic); per CTA the lanes are summed through shared memory in a
+// fixed order, each CTA writes ONE partial vector, conv_small_wgrad_finish adds the CTAs in index order.
 template <int K>
 __global__ void __launch_bounds__(256)
 conv_small_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ partial,
-                        const SmallConvArgs a, long long n_pix) {
+                        const SmallConvArgs a, long long n_pix_) {
   constexpr int T = K * K;
   __shared__ float red[256 * 4];
+  const int n_pix = (int)n_pix_;
   const int q = a.Cout / 4;                       // co quads (<= 16)
-  const int lanes = 256 / q;                      // pixel lanes per CTA
-  const int cq = threadIdx.x % q, pl = threadIdx.x / q;
-  float acc[4][kSmallMaxCin][T];
+  const int roles = q * a.Cin;                    // (co quad, ci) roles per pixel lane
+  const int lanes = 256 / roles;                  // pixel lanes per CTA
+  const int role = threadIdx.x % roles, pl = threadIdx.x / roles;
+  const int cq = role % q, ci = role / q;
+  float acc[4][T];
 #pragma unroll
   for (int e = 0; e < 4; ++e)
 #pragma unroll
-    for (int ci = 0; ci < kSmallMaxCin; ++ci)
-#pragma unroll
-      for (int t = 0; t < T; ++t) acc[e][ci][t] = 0.f;
-  const int pad = K / 2;
+    for (int t = 0; t < T; ++t) acc[e][t] = 0.f;
+  constexpr int pad = K / 2;
   if (pl < lanes) {
-    for (long long p = (long long)blockIdx.x * lanes + pl; p < n_pix; p += (long long)gridDim.x * lanes) {
-      const int ow = (int)(p % a.W), oh = (int)((p / a.W) % a.H);
-      const long long b = p / ((long long)a.W * a.H);
-      const float4 g = __ldg(reinterpret_cast<const float4*>(dy + p * a.Cp + cq * 4));
-      const float gv[4] = {g.x, g.y, g.z, g.w};
-      const float* xb = x + b * a.sb;
+    for (int p = blockIdx.x * lanes + pl; p < n_pix; p += gridDim.x * lanes) {
+      const int ow = p % a.W, r = p / a.W, oh = r % a.H, b = r / a.H;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(dy + (long long)p * a.Cp + cq * 4));
+      const float* xc = x + (long long)b * a.sb + ci * a.sc;
 #pragma unroll
-      for (int ci = 0; ci < kSmallMaxCin; ++ci) {
-        if (ci >= a.Cin) break;
+      for (int kh = 0; kh < K; ++kh) {
+        const int ih = oh + kh - pad;
 #pragma unroll
-        for (int kh = 0; kh < K; ++kh) {
-          const int ih = oh + kh - pad;
-#pragma unroll
-          for (int kw = 0; kw < K; ++kw) {
-            const int iw = ow + kw - pad;
-            float xv = 0.f;
-            if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W)
-              xv = __ldg(xb + ci * a.sc + (long long)ih * a.sh + (long long)iw * a.sw);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) acc[e][ci][kh * K + kw] = fmaf(gv[e], xv, acc[e][ci][kh * K + kw]);
-          }
+        for (int kw = 0; kw < K; ++kw) {
+          const int iw = ow + kw - pad;
+          float xv = 0.f;
+          if (ih >= 0 && ih < a.H && iw >= 0 && iw < a.W) xv = __ldg(xc + (long long)ih * a.sh + (long long)iw * a.sw);
+          acc[0][kh * K + kw] = fmaf(g.x, xv, acc[0][kh * K + kw]);
+          acc[1][kh * K + kw] = fmaf(g.y, xv, acc[1][kh * K + kw]);
+          acc[2][kh * K + kw] = fmaf(g.z, xv, acc[2][kh * K + kw]);
+          acc[3][kh * K + kw] = fmaf(g.w, xv, acc[3][kh * K + kw]);
         }
       }
     }
   }
-  // reduce over the pixel lanes, one (ci, tap) at a time: red[pl][cq][e]
+  // reduce over the pixel lanes, one tap at a time: red[thread][e]; output thread = (co, ci)
   float* out = partial + (long long)blockIdx.x * a.Cout * a.Cin * T;
-#pragma unroll 1
-  for (int ci = 0; ci < a.Cin; ++ci) {
-#pragma unroll 1
-    for (int t = 0; t < T; ++t) {
-      __syncthreads();
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        float v = 0.f;
+  for (int t = 0; t < T; ++t) {
+    __syncthreads();
 #pragma unroll
-        for (int c2 = 0; c2 < kSmallMaxCin; ++c2)
-#pragma unroll
-          for (int t2 = 0; t2 < T; ++t2)
-            if (c2 == ci && t2 == t) v = acc[e][c2][t2];      // constant indices keep acc in registers
-        red[threadIdx.x * 4 + e] = (pl < lanes) ? v : 0.f;
-      }
-      __syncthreads();
-      if (threadIdx.x < a.Cout) {                   // thread = co
-        const int co = threadIdx.x, cqq = co / 4, e = co % 4;
-        float s = 0.f;
-        for (int l = 0; l < lanes; ++l) s += red[(l * q + cqq) * 4 + e];
-        out[(co * a.Cin + ci) * T + t] = s;
-      }
+    for (int e = 0; e < 4; ++e) red[threadIdx.x * 4 + e] = pl < lanes ? acc[e][t] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < a.Cout * a.Cin) {
+      const int co = threadIdx.x % a.Cout, c2 = threadIdx.x / a.Cout;
+      const int rl = c2 * q + co / 4, e = co % 4;
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[(l * roles + rl) * 4 + e];
+      out[(co * a.Cin + c2) * T + t] = s;
     }
   }
 }
@@ -229,10 +230,11 @@ extern "C" int hg_conv_small_fwd(const float* x, const float* w, const float* bi
   int rc = small_args(a, B, Cin, H, W, Cout, Cp, k, sb, sc, sh, sw);
   if (rc) return rc;
   a.flags = flags; a.slope = slope;
-  const long long total = (long long)B * H * W * (Cp / 4);
-  if (total <= 0) return 0;
-  conv_small_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(x, w, bias, residual, y, a,
-                                                                                         total);
+  const long long n_pix = (long long)B * H * W;
+  if (n_pix <= 0) return 0;
+  if (n_pix >= (1LL << 31)) return set_error(HG_ENOSUP, "conv_small: too many pixels");
+  dim3 grid((unsigned)((n_pix + 255) / 256), (Cp + 15) / 16);
+  conv_small_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(x, w, bias, residual, y, a, (int)n_pix);
   HG_LAUNCH_OK("conv_small_fwd_kernel");
   return 0;
 }
