@@ -483,8 +483,9 @@ class Trainer:
     def _arena(self, kind):
         """the flat gradient arena of the D ('d') or G+S+H ('g') parameters, or None when off"""
         on = self.use_grad_arena
-        if on is None:
-            on = _ddp_active() or os.environ.get('HG_GRAD_ARENA', '0') != '0'
+        if on is None:                      # HG_GRAD_ARENA=1 / 0 forces it on / off; default: under DDP
+            env = os.environ.get('HG_GRAD_ARENA')
+            on = _ddp_active() if env is None else env != '0'
         if not on:
             return None
         if kind not in self._arenas:
@@ -873,7 +874,10 @@ class Trainer:
         g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
         overlapped = _GradOverlap([]).enabled       # the collectives then live inside the graphs
         divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp), d_params)
-        split_g = self.split_g_phase if self.split_g_phase is not None else _ddp_active()
+        split_g = self.split_g_phase
+        if split_g is None:                 # HG_SPLIT_G=1 / 0 forces it; default: under DDP
+            env = os.environ.get('HG_SPLIT_G')
+            split_g = _ddp_active() if env is None else env != '0'
         if split_g:
             # the generator side of the G phase (G1) does not depend on D: it runs while the D-side
             # gradient all-reduce is in flight; D's update and the rest of the phase (G2) follow

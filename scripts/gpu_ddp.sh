@@ -1,0 +1,20 @@
+#!/bin/bash
+# 2-GPU (or N-GPU) data-parallel bench.  usage: gpurun --gpus N -- 'bash scripts/gpu_ddp.sh <tag> <N>'
+TAG=$1; N=${2:-2}
+mkdir -p gpurun_out
+run() {  # name, env...
+  local name=$1; shift
+  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+      --master-port 29511 bench.py --gpus $N --steps 16 --warmup 3 > gpurun_out/bench_train_${N}gpu_${TAG}_$name.json 2> gpurun_out/bench_train_${N}gpu_${TAG}_$name.err
+  python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/bench_train_${N}gpu_${TAG}_$name.json'))
+    print('$name', {k: d[k] for k in ('value','ms_per_step','n_gpus')}, d['config'].get('step_ms'))
+except Exception as e:
+    print('$name FAILED', e); print(open('gpurun_out/bench_train_${N}gpu_${TAG}_$name.err').read()[-1500:])
+PY
+}
+run arena_overlap HG_X=1
+run arena_nooverlap HG_SPLIT_G=0
+run legacy HG_GRAD_ARENA=0 HG_SPLIT_G=0
