@@ -482,6 +482,14 @@ def run_train(args):
     tr_graphs = tr.cuda_graphs
     del tr
     torch.cuda.empty_cache()
+    if os.environ.get("HG_BENCH_LIGHT"):        # development runs: the step timing only
+        if dv.rank == 0:
+            emit({"metric": "training images/sec", "value": round(B_PER_GPU * dv.world * args.steps / t_dev, 2),
+                  "unit": "images/s", "n_gpus": dv.world, "steps": args.steps, "ms_per_step": round(t_dev / args.steps * 1e3, 3),
+                  "e2e": {"value": round(B_PER_GPU * dv.world * args.steps / t_e2e, 2)},
+                  "config": {"step_ms": step_ms, "light": True}, "clocks": sampler.stop() if sampler else {}})
+        dv.close()
+        return
     hist_info, _, _, _ = hist_section(dv, 5, 3)
     conv_agg, conv_rows = ({}, [])
     if dv.rank == 0:

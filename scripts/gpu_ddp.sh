@@ -4,7 +4,7 @@ TAG=$1; N=${2:-2}
 mkdir -p gpurun_out
 run() {  # name, env...
   local name=$1; shift
-  env "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
+  env HG_BENCH_LIGHT=1 "$@" timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 \
       --master-port 29511 bench.py --gpus $N --steps 16 --warmup 3 > gpurun_out/bench_train_${N}gpu_${TAG}_$name.json 2> gpurun_out/bench_train_${N}gpu_${TAG}_$name.err
   python - <<PY
 import json
