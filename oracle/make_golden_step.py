@@ -11,7 +11,13 @@ step's loss composition and every parameter gradient of both phases at one set o
 independently of the (parity-unpinned) optimiser.
 
 Cases: trainer.steps = 1 (plain step), 4 (gradient penalty), 32 (gradient penalty +
-path-length regulariser).  Image 64x64, network_capacity 16, batch 2, hist_insz 150
+path-length regulariser), each with alpha = 2 (the reference's histogram-loss weight) and with
+alpha = 0 (keys `c<steps>n_*`).  Why the second set: the histogram term's gradient carries a factor
+1/(I + 1e-6) per pixel (d log(I + eps)/dI, RGBuvHistBlock.py:112-115), so the few generated pixels
+that happen to lie at +1e-6..1e-4 dominate it, and whether a pixel sits at +1e-5 or -1e-5 (cut by the
+relu) is decided by rounding noise far below any parity tolerance.  The alpha = 0 gradients (adversarial
++ path-length terms) are well conditioned and pin the step; the alpha = 2 set is compared whenever
+the realisation at hand is not dominated by such a pixel (tests/test_trainer_gpu.py).  Image 64x64, network_capacity 16, batch 2, hist_insz 150
 'interpolation' (no resize at 64x64), alpha = 2.  Weights: gan_oracle.seeded_state_dict;
 inputs: seeded generators; the latents come from the global CPU RNGs seeded per case, which
 ``train_oracle.draw_step_inputs`` reproduces.
@@ -38,6 +44,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file
                           "tests", "golden")
 IMAGE_SIZE, CAPACITY, BATCH, ALPHA = 64, 16, 2, 2.0
 CASES = (1, 4, 32)
+ALPHAS = (("", 2.0), ("n", 0.0))          # key suffix, alpha
 N_SAMPLES = 256
 SEEDS = {"G": 21, "D": 22, "S": 23, "H": 24}
 
@@ -121,17 +128,19 @@ def main():
                        ["H." + k for k, _ in tr.GAN.H.named_parameters()])
             out["names_d"], out["names_g"] = json.dumps(names_d), json.dumps(names_g)
             for case in CASES:
+              for suffix, alpha in ALPHAS:
                 images, hists = step_inputs(case)
                 tr.loader = iter([{"images": images, "histograms": hists[0]},
                                   {"images": images, "histograms": hists[1]}])
                 tr.steps, tr.pl_mean = case, 0
                 seed_step(case)
-                tr.train(alpha=ALPHA)
+                tr.train(alpha=alpha)
                 assert tr.steps == case + 1
                 rec = {"d_loss": tr.d_loss, "g_loss": tr.g_loss, "h_loss": tr.h_loss,
                        "gp": tr.last_gp_loss if case % 4 == 0 else float("nan"),
                        "pl_mean": float(tr.pl_mean)}
-                out[f"c{case}_scalars"] = json.dumps(rec)
+                key = f"c{case}{suffix}"
+                out[f"{key}_scalars"] = json.dumps(rec)
                 for tag, opt, names in (("d", tr.GAN.D_opt, names_d), ("g", tr.GAN.G_opt, names_g)):
                     assert len(opt.recorded) == len(names)
                     norms, samples = [], []
@@ -140,9 +149,9 @@ def main():
                         n, s = fingerprint(g)
                         norms.append(n)
                         samples.append(s)
-                    out[f"c{case}_{tag}_norms"] = np.array(norms, dtype=np.float64)
-                    out[f"c{case}_{tag}_samples"] = np.concatenate(samples)
-                print(f"case steps={case}:", rec)
+                    out[f"{key}_{tag}_norms"] = np.array(norms, dtype=np.float64)
+                    out[f"{key}_{tag}_samples"] = np.concatenate(samples)
+                print(f"case steps={case} alpha={alpha}:", rec)
     finally:
         torch.Tensor.cuda, torch.nn.Module.cuda = saved
     np.savez_compressed(os.path.join(GOLDEN_DIR, "train_step_64.npz"), **out)

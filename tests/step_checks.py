@@ -18,8 +18,14 @@ def load_golden():
     g["names_d"] = json.loads(str(g["names_d"]))
     g["names_g"] = json.loads(str(g["names_g"]))
     for c in mgs.CASES:
-        g[f"c{c}_scalars"] = json.loads(str(g[f"c{c}_scalars"]))
+        for suffix, _ in mgs.ALPHAS:
+            g[f"c{c}{suffix}_scalars"] = json.loads(str(g[f"c{c}{suffix}_scalars"]))
     return g
+
+
+def key(case, alpha):
+    """golden key prefix of (trainer.steps, histogram-loss weight)"""
+    return f"c{case}" + {2.0: "", 0.0: "n"}[float(alpha)]
 
 
 def compare_grads(grads, names, norms, samples):
@@ -52,7 +58,7 @@ def rel(a, b):
     return abs(float(a) - float(b)) / max(abs(float(b)), 1e-30)
 
 
-def emulated_step_tables(case, golden=None):
+def emulated_step_tables(case, golden=None, alpha=None):
     """TF32 noise floor of ONE train step: the histogan_b200 modules (same algorithm as the CUDA path:
     activation-side modulation, shared weights) evaluated on the CPU with torch stand-ins for the
     conv primitives and TF32-rounded operands (tests/emulation.py), the histogram block replaced by
@@ -66,6 +72,8 @@ def emulated_step_tables(case, golden=None):
     from oracle import train_oracle as to
     from tests.emulation import emulated_conv
     g = golden or load_golden()
+    alpha = mgs.ALPHA if alpha is None else alpha
+    ck = key(case, alpha)
     S = mgs.IMAGE_SIZE
     with torch.device("cpu"):
         mods = {"G": gan.Generator(S, 512, mgs.CAPACITY), "D": gan.Discriminator(S, mgs.CAPACITY),
@@ -107,7 +115,7 @@ def emulated_step_tables(case, golden=None):
         w_styles, hw = w_of(dr["g_style"]), hw_of(hists[1])
         fake = Gm(w_styles, hw, dr["g_noise"])
         fo, _ = Dm(fake)
-        hl = ho.hellinger_loss(hists[1], ho.rgb_uv_hist(F.relu(fake), insz=150), mgs.ALPHA)
+        hl = ho.hellinger_loss(hists[1], ho.rgb_uv_hist(F.relu(fake), insz=150), alpha)
         gl = fo.mean()
         gen = gl + hl
         pl = None
@@ -119,15 +127,15 @@ def emulated_step_tables(case, golden=None):
             gen = gen + (pll ** 2).mean()
         gparams = list(Gm.parameters()) + list(Sm.parameters()) + list(Hm.parameters())
         ggr = torch.autograd.grad(gen, gparams)
-    ref = g[f"c{case}_scalars"]
+    ref = g[f"{ck}_scalars"]
     scal = {"d_loss": rel(div, ref["d_loss"]), "g_loss_abs_over_dscale": abs(gl.item() - ref["g_loss"]) / abs(ref["d_loss"]),
-            "h_loss": rel(hl, ref["h_loss"])}
+            "h_loss": rel(hl, ref["h_loss"]) if ref["h_loss"] else abs(float(hl))}
     if gp is not None:
         scal["gp"] = rel(gp, ref["gp"])
     if pl is not None:
         scal["pl_mean"] = rel(0.01 * pl, ref["pl_mean"])
-    td = compare_grads(list(dgr), g["names_d"], g[f"c{case}_d_norms"], g[f"c{case}_d_samples"])
-    tg = compare_grads(list(ggr), g["names_g"], g[f"c{case}_g_norms"], g[f"c{case}_g_samples"])
+    td = compare_grads(list(dgr), g["names_d"], g[f"{ck}_d_norms"], g[f"{ck}_d_samples"])
+    tg = compare_grads(list(ggr), g["names_g"], g[f"{ck}_g_norms"], g[f"{ck}_g_samples"])
     return scal, td, tg
 
 
