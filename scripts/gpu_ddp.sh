@@ -18,3 +18,7 @@ PY
 run arena_overlap HG_X=1
 run arena_nooverlap HG_SPLIT_G=0
 run legacy HG_GRAD_ARENA=0 HG_SPLIT_G=0
+# the same window on ONE GPU of the same box, for the efficiency denominator
+HG_BENCH_LIGHT=1 timeout 600 python bench.py --gpus 1 --steps 16 --warmup 3 > gpurun_out/bench_train_1gpu_${TAG}_samewindow.json 2> gpurun_out/bench_train_1gpu_${TAG}_samewindow.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_train_1gpu_${TAG}_samewindow.json')); print('1gpu', d['value'], d['ms_per_step'], d['config'].get('step_ms'))"
