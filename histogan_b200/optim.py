@@ -43,7 +43,10 @@ class DiffGrad(Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, only=None):
+        """`only`: update just these parameters (the trainer pipelines the update of one piece of the
+        gradient arena with the all-reduce of the next); each parameter keeps its own step count."""
+        only = None if only is None else {id(p) for p in only}
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -52,7 +55,7 @@ class DiffGrad(Optimizer):
             beta1, beta2 = group['betas']
             by_step = {}
             for p in group['params']:
-                if p.grad is None:
+                if p.grad is None or (only is not None and id(p) not in only):
                     continue
                 if p.grad.is_sparse:
                     raise RuntimeError('DiffGrad does not support sparse gradients')

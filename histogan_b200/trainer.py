@@ -261,6 +261,35 @@ class GradArena:
         if src:
             torch._foreach_copy_(dst, src)
 
+    def chunks(self, k):
+        """the arena cut into <= k contiguous pieces of about equal size at slot boundaries:
+        [(first float, one past the last float, [parameters])]"""
+        bounds, total = [], 0
+        for p in self.params:
+            bounds.append(total)
+            total += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        bounds.append(total)
+        out, first, want = [], 0, total / max(1, k)
+        for i in range(len(self.params)):
+            last = i == len(self.params) - 1
+            if last or (bounds[i + 1] >= want * (len(out) + 1) and len(out) < k - 1):
+                out.append((bounds[first], bounds[i + 1], self.params[first:i + 1]))
+                first = i + 1
+        return out
+
+    def all_reduce_mean_async(self, a, b):
+        """start averaging flat[a:b] over the ranks; returns the wait() of the collective"""
+        piece = self.flat[a:b]
+        if self.flat.is_cuda and dist.get_backend() == 'nccl':
+            return dist.all_reduce(piece, op=dist.ReduceOp.AVG, async_op=True).wait
+        w = dist.all_reduce(piece, op=dist.ReduceOp.SUM, async_op=True)
+        world = dist.get_world_size()
+
+        def wait():
+            w.wait()
+            piece.div_(world)
+        return wait
+
     def all_reduce_mean(self):
         world = dist.get_world_size()
         if self.flat.is_cuda and dist.get_backend() == 'nccl':
@@ -386,6 +415,8 @@ class Trainer:
         self._arenas = {}
         # flat gradient arenas (one all-reduce per phase): on under torch.distributed, or forced
         self.use_grad_arena = kwargs.pop('grad_arena', None)
+        # DDP: pieces of the G-side gradient arena whose all-reduce is pipelined with the optimiser
+        self.exchange_chunks = int(kwargs.pop('exchange_chunks', os.environ.get('HG_EXCHANGE_CHUNKS', 4)))
         # split the captured G phase into a D-independent part and the rest (overlaps the D-side
         # all-reduce); None = only under torch.distributed
         self.split_g_phase = kwargs.pop('split_g_phase', None)
@@ -508,6 +539,23 @@ class Trainer:
         w = dist.all_reduce(arena.flat, op=dist.ReduceOp.AVG, async_op=True)   # on NCCL's own stream
         return w.wait
 
+    def _exchange_and_step(self, kind, params, opt):
+        """gradient exchange + optimiser step of one parameter group.  Under DDP with a flat arena the
+        two are pipelined: the arena is reduced in `exchange_chunks` pieces on NCCL's stream and the
+        fused DiffGrad kernel of piece i runs while piece i+1 is still on the wire (the update is
+        element-wise, so the result is the one of exchange-then-step, bit for bit)."""
+        arena = self._arenas.get(kind)
+        k = self.exchange_chunks
+        if not _ddp_active() or arena is None or k <= 1 or any(v is None for v in arena.slots):
+            self._exchange(kind, params)
+            opt.step()
+            return
+        pieces = arena.chunks(k)
+        waits = [arena.all_reduce_mean_async(a, b) for a, b, _ in pieces]
+        for wait, (_, _, ps) in zip(waits, pieces):
+            wait()
+            opt.step(only=ps)
+
     def _exchange(self, kind, params):
         """average the gradients of one parameter group over the ranks (no-op on one GPU)"""
         arena = self._arenas.get(kind)
@@ -587,8 +635,7 @@ class Trainer:
         self.d_loss = float(total_disc_loss)
         if arena_d is not None:
             arena_d.finalize()
-        self._exchange('d', list(GAN.D.parameters()))
-        GAN.D_opt.step()
+        self._exchange_and_step('d', list(GAN.D.parameters()), GAN.D_opt)
 
         # -------------------------------------------------------- generator --
         GAN.G_opt.zero_grad()
@@ -633,8 +680,7 @@ class Trainer:
         self.h_loss = float(total_hist_loss)
         if arena_g is not None:
             arena_g.finalize()
-        self._exchange('g', g_params)
-        GAN.G_opt.step()
+        self._exchange_and_step('g', g_params, GAN.G_opt)
 
         return self._finish_step(total_disc_loss, total_gen_loss, total_hist_loss,
                                  apply_path_penalty, avg_pl_length)
@@ -896,17 +942,19 @@ class Trainer:
             GAN.D_opt.step()
             g_loss, h_loss, avg_pl = self._replay(k2)
         else:
-            if not overlapped:
-                self._exchange('d', d_params)
-            GAN.D_opt.step()
+            if overlapped:
+                GAN.D_opt.step()
+            else:
+                self._exchange_and_step('d', d_params, GAN.D_opt)
             stage(next(self.loader), 1)
             if apply_pl:
                 st['pl_mean'].fill_(float(self.pl_mean))
             g_loss, h_loss, avg_pl = self._graphed(('G', float(alpha), bool(apply_pl)),
                                                    lambda: self._phase_g(alpha, apply_pl), g_params)
-        if not overlapped:
-            self._exchange('g', g_params)
-        GAN.G_opt.step()
+        if overlapped:
+            GAN.G_opt.step()
+        else:
+            self._exchange_and_step('g', g_params, GAN.G_opt)
         # host reads once, after everything has been queued
         self.q_loss = 0.0
         if gp is not None:

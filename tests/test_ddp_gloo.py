@@ -85,6 +85,31 @@ def _worker(rank, world, port, q):
     for i, (p, e) in enumerate(zip(aps, expected)):
         want_i = torch.zeros_like(e) if i == 3 else e
         ok = ok and torch.allclose(p.grad, want_i, atol=1e-6)
+    # pipelined exchange + update (Trainer._exchange_and_step): the arena reduced in pieces cut at slot
+    # boundaries, each piece's parameters updated as soon as its piece has arrived == one all-reduce
+    # followed by one optimiser step
+    from histogan_b200.optim import DiffGrad
+    pieces = arena.chunks(3)
+    ok = ok and 1 < len(pieces) <= 3 and pieces[0][0] == 0 and pieces[-1][1] == arena.flat.numel()
+    ok = ok and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+    ok = ok and [id(q_) for _, _, ps in pieces for q_ in ps] == [id(q_) for q_ in aps]
+    bps = [torch.nn.Parameter(q_.detach().clone()) for q_ in aps]
+    ref_opt, pip_opt = DiffGrad(bps, lr=1e-2, betas=(0.5, 0.9)), DiffGrad(aps, lr=1e-2, betas=(0.5, 0.9))
+    for it in range(2):
+        gb = torch.Generator().manual_seed(500 + 10 * it + rank)
+        for q_, v in zip(aps, arena.slots):
+            v.copy_(torch.randn(q_.shape, generator=gb))
+            q_.grad = v
+        for q_, b_ in zip(aps, bps):
+            b_.grad = q_.grad.detach().clone()
+        _allreduce_mean_grads(bps)
+        ref_opt.step()
+        waits = [arena.all_reduce_mean_async(a, b) for a, b, _ in pieces]
+        for wait, (_, _, ps) in zip(waits, pieces):
+            wait()
+            pip_opt.step(only=ps)
+        ok = ok and all(torch.allclose(q_, b_, atol=1e-7) for q_, b_ in zip(aps, bps))
+        ok = ok and all(pip_opt.state[q_]['step'] == it + 1 for q_ in aps)
     # NaN flag agreement (Trainer.train): MAX-reduce of a per-rank flag
     f = torch.tensor([1.0 if rank == 1 else 0.0])
     dist.all_reduce(f, op=dist.ReduceOp.MAX)
