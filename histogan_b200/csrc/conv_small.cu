@@ -13,6 +13,8 @@
 //   conv_small_dgrad   dx[b,ci,ih,iw] = sum dy[b,ih-kh+p,iw-kw+p,co] w[co,ci,kh,kw]             (planar out)
 //   conv_small_wgrad   dw[co,ci,kh,kw] = sum_pix dy[pix,co] x[pix + tap, ci]   (deterministic two-stage sum)
 // k in {1, 3}, stride 1, pad k/2, Cin <= 4, Cout % 4 == 0 and <= 64.
+#include <mutex>
+
 #include "hg_common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -30,124 +32,270 @@ struct SmallConvArgs {
   float slope;
 };
 
-// thread = one pixel x 4 output channels, consecutive threads = consecutive channel quads, then
-// consecutive pixels: a warp's store (and its residual load) is 512 contiguous bytes of the NHWC tensor,
-// the k*k*Cin image values of a pixel are warp-level broadcasts / 32-byte segments that hit L1, the
-// weights come from shared memory ([ci][tap][Cp], one 16-byte read per multiply group).  Channels
-// beyond Cout are written as zeros.
+// thread = one pixel x 16 output channels (blockIdx.y selects the group of 16): the k*k*Cin image values
+// are loaded once per pixel, the weights come from shared memory as warp-wide broadcasts ([ci][tap][co]),
+// 32-bit index arithmetic throughout (B*H*W < 2^31).  Channels beyond Cout are written as zeros.
 __global__ void __launch_bounds__(256)
-conv_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+conv_small_fwd_generic_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                       const float* __restrict__ residual, float* __restrict__ y, const SmallConvArgs a,
-                      int n_items) {
-  __shared__ __align__(16) float sw[kSmallMaxCin * kSmallMaxTaps * kSmallMaxCout];   // [ci][tap][Cp]
-  __shared__ __align__(16) float sb[kSmallMaxCout];
+                      int n_pix) {
+  __shared__ __align__(16) float sw[kSmallMaxCin * kSmallMaxTaps * 16];   // [ci][tap][16 co of this group]
+  __shared__ float sb[16];
   const int taps = a.k * a.k;
-  for (int i = threadIdx.x; i < a.Cin * taps * a.Cp; i += 256) {
-    const int co = i % a.Cp, t = (i / a.Cp) % taps, ci = i / (a.Cp * taps);
-    sw[i] = co < a.Cout ? w[(co * a.Cin + ci) * taps + t] : 0.f;
+  const int cg = blockIdx.y * 16;                    // first output channel of this thread group
+  for (int i = threadIdx.x; i < a.Cin * taps * 16; i += 256) {
+    const int co = i & 15, t = (i >> 4) % taps, ci = (i >> 4) / taps;
+    sw[i] = cg + co < a.Cout ? w[((cg + co) * a.Cin + ci) * taps + t] : 0.f;
   }
-  if (threadIdx.x < a.Cp) sb[threadIdx.x] = (bias && threadIdx.x < a.Cout) ? bias[threadIdx.x] : 0.f;
+  if (threadIdx.x < 16) sb[threadIdx.x] = (bias && cg + threadIdx.x < a.Cout) ? bias[cg + threadIdx.x] : 0.f;
   __syncthreads();
-  const int item = blockIdx.x * 256 + threadIdx.x;
-  if (item >= n_items) return;
-  const int nq = a.Cp >> 2;
-  const int p = item / nq, c0 = (item - p * nq) * 4;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= n_pix) return;
   const int ow = p % a.W, r = p / a.W, oh = r % a.H, b = r / a.H;
-  float4 acc = *reinterpret_cast<const float4*>(sb + c0);
+  float acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = sb[e];
   const int pad = a.k / 2;
   const float* xb = x + (long long)b * a.sb;
-  const float* wq = sw + c0;
   for (int ci = 0; ci < a.Cin; ++ci) {
     for (int kh = 0; kh < a.k; ++kh) {
       const int ih = oh + kh - pad;
       if (ih < 0 || ih >= a.H) continue;
-      const float* xr = xb + ci * a.sc + (long long)ih * a.sh;
       for (int kw = 0; kw < a.k; ++kw) {
         const int iw = ow + kw - pad;
         if (iw < 0 || iw >= a.W) continue;
-        const float xv = __ldg(xr + (long long)iw * a.sw);
-        const float4 wv = *reinterpret_cast<const float4*>(wq + (ci * taps + kh * a.k + kw) * a.Cp);
-        acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y);
-        acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+        const float xv = __ldg(xb + ci * a.sc + (long long)ih * a.sh + (long long)iw * a.sw);
+        const float4* wp = reinterpret_cast<const float4*>(sw + (ci * taps + kh * a.k + kw) * 16);
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const float4 wv = wp[qd];
+          acc[qd * 4 + 0] = fmaf(xv, wv.x, acc[qd * 4 + 0]); acc[qd * 4 + 1] = fmaf(xv, wv.y, acc[qd * 4 + 1]);
+          acc[qd * 4 + 2] = fmaf(xv, wv.z, acc[qd * 4 + 2]); acc[qd * 4 + 3] = fmaf(xv, wv.w, acc[qd * 4 + 3]);
+        }
       }
     }
   }
-  float v[4] = {acc.x, acc.y, acc.z, acc.w};
-  float rv[4] = {0.f, 0.f, 0.f, 0.f};
-  if (residual) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(residual) + item);
-    rv[0] = t.x; rv[1] = t.y; rv[2] = t.z; rv[3] = t.w;
-  }
+  float* yo = y + (long long)p * a.Cp + cg;
+  const float* ro = residual ? residual + (long long)p * a.Cp + cg : nullptr;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float t = v[e];
-    if (c0 + e >= a.Cout) t = 0.f;
-    else {
-      if (a.flags & HG_CONV_LRELU) t = t > 0.f ? t : t * a.slope;
-      t += rv[e];                                                 // added after the activation (:523)
-      if (a.flags & HG_CONV_ROUND_TF32) t = tf32_round(t);
+  for (int qd = 0; qd < 4; ++qd) {
+    if (cg + qd * 4 >= a.Cp) break;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float t = acc[qd * 4 + e];
+      if (cg + qd * 4 + e >= a.Cout) t = 0.f;
+      else {
+        if (a.flags & HG_CONV_LRELU) t = t > 0.f ? t : t * a.slope;
+        if (ro) t += ro[qd * 4 + e];                              // added after the activation (:523)
+        if (a.flags & HG_CONV_ROUND_TF32) t = tf32_round(t);
+      }
+      v[e] = t;
     }
-    v[e] = t;
+    *reinterpret_cast<float4*>(yo + qd * 4) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  reinterpret_cast<float4*>(y)[item] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
-// thread = one input pixel x 4 upstream channels (consecutive threads = consecutive quads, then pixels:
-// every dy load of a warp is 512 contiguous bytes); the Cout/4 partial sums of a pixel are added in a
-// fixed order through shared memory by the threads (pixel, ci), which write the planar (strided) dx.
+// thread = one input pixel: all Cin channels of dx (planar, strided)
 __global__ void __launch_bounds__(256)
-conv_small_dgrad_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                        const SmallConvArgs a, int n_pix) {
-  __shared__ __align__(16) float sw[kSmallMaxCout * kSmallMaxCin * kSmallMaxTaps];   // [tap][ci][co]
-  __shared__ float red[kSmallMaxCin * 256];
+conv_small_dgrad_generic_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                        const SmallConvArgs a, long long total) {
+  __shared__ float sw[kSmallMaxCout * kSmallMaxCin * kSmallMaxTaps];   // [tap][ci][co]  (co contiguous)
   const int taps = a.k * a.k;
   for (int i = threadIdx.x; i < a.Cout * a.Cin * taps; i += 256) {
     const int t = i % taps, ci = (i / taps) % a.Cin, co = i / (taps * a.Cin);
     sw[(t * a.Cin + ci) * a.Cout + co] = w[i];
   }
   __syncthreads();
-  const int q = a.Cout >> 2;                       // quads that carry information (<= 16)
-  const int pix_cta = 256 / q;                     // pixels per CTA
-  const int pl = threadIdx.x / q, cq = threadIdx.x - pl * q;
-  const int p = blockIdx.x * pix_cta + pl;
-  const bool live = pl < pix_cta && p < n_pix;
-  float acc[kSmallMaxCin] = {0.f, 0.f, 0.f, 0.f};
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= (int)total) return;
+  const int iw = p % a.W, r = p / a.W, ih = r % a.H;
+  const long long b = r / a.H;
   const int pad = a.k / 2;
-  if (live) {
-    const int iw = p % a.W, r = p / a.W, ih = r % a.H;
-    for (int kh = 0; kh < a.k; ++kh) {
-      const int oh = ih - kh + pad;
-      if (oh < 0 || oh >= a.H) continue;
-      for (int kw = 0; kw < a.k; ++kw) {
-        const int ow = iw - kw + pad;
-        if (ow < 0 || ow >= a.W) continue;
-        const int po = p + (oh - ih) * a.W + (ow - iw);
-        const float4 gv = __ldg(reinterpret_cast<const float4*>(dy + (long long)po * a.Cp + cq * 4));
-        const float* wt = sw + (kh * a.k + kw) * a.Cin * a.Cout + cq * 4;
+  float acc[kSmallMaxCin] = {0.f, 0.f, 0.f, 0.f};
+  for (int kh = 0; kh < a.k; ++kh) {
+    const int oh = ih - kh + pad;
+    if (oh < 0 || oh >= a.H) continue;
+    for (int kw = 0; kw < a.k; ++kw) {
+      const int ow = iw - kw + pad;
+      if (ow < 0 || ow >= a.W) continue;
+      const float* g = dy + ((b * a.H + oh) * a.W + ow) * a.Cp;
+      const float* wt = sw + (kh * a.k + kw) * a.Cin * a.Cout;
+      for (int co = 0; co < a.Cout; co += 4) {
+        const float4 gv = __ldg(reinterpret_cast<const float4*>(g + co));
 #pragma unroll
         for (int ci = 0; ci < kSmallMaxCin; ++ci) {
           if (ci < a.Cin) {
-            const float4 wv = *reinterpret_cast<const float4*>(wt + ci * a.Cout);
-            acc[ci] = fmaf(gv.x, wv.x, fmaf(gv.y, wv.y, fmaf(gv.z, wv.z, fmaf(gv.w, wv.w, acc[ci]))));
+            const float* wc = wt + ci * a.Cout + co;
+            acc[ci] = fmaf(gv.x, wc[0], fmaf(gv.y, wc[1], fmaf(gv.z, wc[2], fmaf(gv.w, wc[3], acc[ci]))));
           }
         }
       }
     }
   }
+  float* o = dx + b * a.sb + (long long)ih * a.sh + (long long)iw * a.sw;
 #pragma unroll
   for (int ci = 0; ci < kSmallMaxCin; ++ci)
-    if (ci < a.Cin) red[ci * 256 + threadIdx.x] = acc[ci];
-  __syncthreads();
-  // output thread = (ci, local pixel): consecutive threads -> consecutive pixels of one plane
-  for (int o = threadIdx.x; o < a.Cin * pix_cta; o += 256) {
-    const int ci = o / pix_cta, l = o - ci * pix_cta;
-    const int po = blockIdx.x * pix_cta + l;
-    if (po >= n_pix) continue;
-    float s = 0.f;
-    for (int j = 0; j < q; ++j) s += red[ci * 256 + l * q + j];
-    const int iw = po % a.W, r = po / a.W, ih = r % a.H, b = r / a.H;
-    dx[(long long)b * a.sb + ci * a.sc + (long long)ih * a.sh + (long long)iw * a.sw] = s;
+    if (ci < a.Cin) o[ci * a.sc] = acc[ci];
+}
+
+// ---------------------------------------------------------------------------------------------
+// The layer that matters (DiscriminatorBlock 0 at network_capacity 16: 3 -> 16 channels, dense 16-channel
+// NHWC output) has its own kernels.  Measured on the generic ones (ncu, 32 x 256^2): issue slots 84 % busy,
+// DRAM at 3 % -- the weights came from shared memory, one LDS.128 per four multiply-adds, and the
+// address arithmetic was per tap.  Here the 432 weights sit in CONSTANT memory (a device-to-device copy
+// node in front of the kernel, capturable) and, with every loop unrolled, each multiply-add names its
+// weight as an immediate constant-bank operand: no load instruction at all.
+constexpr int kFastCin = 3, kFastCout = 16;
+__constant__ __align__(16) float c_small_w[kFastCin * kSmallMaxTaps * kFastCout + kFastCout];   // [ci][tap][co], then bias
+#define C_SMALL_B (c_small_w + kFastCin * kSmallMaxTaps * kFastCout)
+
+// OIHW filter (+ bias or zeros) -> the constant-memory layout, into a per-device scratch
+__global__ void small_pack_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ out, int T) {
+  const int i = threadIdx.x;
+  if (i < kFastCin * T * kFastCout) {
+    const int co = i % kFastCout, t = (i / kFastCout) % T, ci = i / (kFastCout * T);
+    out[(ci * kSmallMaxTaps + t) * kFastCout + co] = w[(co * kFastCin + ci) * T + t];
   }
+  if (i < kFastCout) out[kFastCin * kSmallMaxTaps * kFastCout + i] = bias ? bias[i] : 0.f;
+}
+
+// thread = one pixel x 16 channels
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_small_fwd16_kernel(const float* __restrict__ x, const float* __restrict__ residual, float* __restrict__ y,
+                        const SmallConvArgs a, int n_pix) {
+  constexpr int pad = K / 2;
+  const int p = blockIdx.x * 256 + threadIdx.x;
+  if (p >= n_pix) return;
+  const int ow = p % a.W, r = p / a.W, oh = r % a.H, b = r / a.H;
+  float acc[kFastCout];
+#pragma unroll
+  for (int e = 0; e < kFastCout; ++e) acc[e] = C_SMALL_B[e];
+  const float* xb = x + (long long)b * a.sb;
+  long long offw[K];
+  bool okw[K];
+#pragma unroll
+  for (int kw = 0; kw < K; ++kw) {
+    const int iw = ow + kw - pad;
+    okw[kw] = iw >= 0 && iw < a.W;
+    offw[kw] = (long long)iw * a.sw;
+  }
+#pragma unroll
+  for (int kh = 0; kh < K; ++kh) {
+    const int ih = oh + kh - pad;
+    const bool okh = ih >= 0 && ih < a.H;
+    const float* xr = xb + (long long)ih * a.sh;
+#pragma unroll
+    for (int ci = 0; ci < kFastCin; ++ci) {
+#pragma unroll
+      for (int kw = 0; kw < K; ++kw) {
+        const float xv = (okh && okw[kw]) ? __ldg(xr + ci * a.sc + offw[kw]) : 0.f;
+#pragma unroll
+        for (int co = 0; co < kFastCout; ++co)
+          acc[co] = fmaf(xv, c_small_w[(ci * kSmallMaxTaps + kh * K + kw) * kFastCout + co], acc[co]);
+      }
+    }
+  }
+  float4* yo = reinterpret_cast<float4*>(y + (long long)p * kFastCout);
+  const float4* ro = residual ? reinterpret_cast<const float4*>(residual + (long long)p * kFastCout) : nullptr;
+#pragma unroll
+  for (int qd = 0; qd < 4; ++qd) {
+    float v[4] = {acc[qd * 4], acc[qd * 4 + 1], acc[qd * 4 + 2], acc[qd * 4 + 3]};
+    float rv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ro) { const float4 t = __ldg(ro + qd); rv[0] = t.x; rv[1] = t.y; rv[2] = t.z; rv[3] = t.w; }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float t = v[e];
+      if (a.flags & HG_CONV_LRELU) t = t > 0.f ? t : t * a.slope;
+      t += rv[e];                                                  // added after the activation (:523)
+      if (a.flags & HG_CONV_ROUND_TF32) t = tf32_round(t);
+      v[e] = t;
+    }
+    yo[qd] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// CTA = a 32 x 8 tile of input pixels of one image.  The (32 + 2 pad) x (8 + 2 pad) x 16-channel patch of
+// dy it needs is staged in shared memory with fully coalesced loads (pixel stride 20 floats: the 16-byte
+// reads of 8 consecutive lanes then fall into 8 different bank groups); thread = one pixel, 3 sums.
+constexpr int kDgTW = 32, kDgTH = 8, kDgStride = 20;
+template <int K>
+__global__ void __launch_bounds__(256)
+conv_small_dgrad16_kernel(const float* __restrict__ dy, float* __restrict__ dx, const SmallConvArgs a) {
+  constexpr int pad = K / 2, PW = kDgTW + 2 * pad, PH = kDgTH + 2 * pad;
+  __shared__ __align__(16) float tile[PH * PW * kDgStride];
+  const int b = blockIdx.z, w0 = blockIdx.x * kDgTW, h0 = blockIdx.y * kDgTH;
+  const float* dyb = dy + (long long)b * a.H * a.W * kFastCout;
+  for (int i = threadIdx.x; i < PH * PW * 4; i += 256) {
+    const int q = i & 3, px = (i >> 2) % PW, py = (i >> 2) / PW;
+    const int gh = h0 + py - pad, gw = w0 + px - pad;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gh >= 0 && gh < a.H && gw >= 0 && gw < a.W)
+      v = __ldg(reinterpret_cast<const float4*>(dyb + ((long long)gh * a.W + gw) * kFastCout) + q);
+    *reinterpret_cast<float4*>(tile + (py * PW + px) * kDgStride + q * 4) = v;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int iw = w0 + tx, ih = h0 + ty;
+  float acc[kFastCin] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int kh = 0; kh < K; ++kh) {
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) {
+      // dx[ih, iw] takes dy[ih - kh + pad, iw - kw + pad] = patch (ty + 2 pad - kh, tx + 2 pad - kw)
+      const float* g = tile + ((ty + 2 * pad - kh) * PW + (tx + 2 * pad - kw)) * kDgStride;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 gv = *reinterpret_cast<const float4*>(g + q * 4);
+#pragma unroll
+        for (int ci = 0; ci < kFastCin; ++ci) {
+          acc[ci] = fmaf(gv.x, c_small_w[(ci * kSmallMaxTaps + kh * K + kw) * kFastCout + q * 4 + 0], acc[ci]);
+          acc[ci] = fmaf(gv.y, c_small_w[(ci * kSmallMaxTaps + kh * K + kw) * kFastCout + q * 4 + 1], acc[ci]);
+          acc[ci] = fmaf(gv.z, c_small_w[(ci * kSmallMaxTaps + kh * K + kw) * kFastCout + q * 4 + 2], acc[ci]);
+          acc[ci] = fmaf(gv.w, c_small_w[(ci * kSmallMaxTaps + kh * K + kw) * kFastCout + q * 4 + 3], acc[ci]);
+        }
+      }
+    }
+  }
+  if (iw < a.W && ih < a.H) {
+    float* o = dx + (long long)b * a.sb + (long long)ih * a.sh + (long long)iw * a.sw;
+#pragma unroll
+    for (int ci = 0; ci < kFastCin; ++ci) o[ci * a.sc] = acc[ci];
+  }
+}
+
+static bool small_fast(const SmallConvArgs& a) {
+  static const bool off = [] { const char* e = getenv("HG_SMALL_GENERIC"); return e && e[0] == '1'; }();
+  return !off && a.Cin == kFastCin && a.Cout == kFastCout && a.Cp == kFastCout;
+}
+
+// the filter (and bias) into constant memory, in stream order: a pack kernel into a per-device scratch
+// and a device-to-device copy into the symbol (both capturable).  Returns 1 when the fast path is not
+// available (first use inside a capture: the scratch cannot be allocated), < 0 on error.
+static int small_fast_upload(const float* w, const float* bias, int k, cudaStream_t stream) {
+  static float* scratch[64] = {};
+  static std::mutex mu;
+  constexpr size_t bytes = sizeof(float) * (kFastCin * kSmallMaxTaps * kFastCout + kFastCout);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+  float* buf;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!scratch[dev]) {
+      cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+      if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return 1;
+      float* p = nullptr;
+      if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return 1; }
+      scratch[dev] = p;
+    }
+    buf = scratch[dev];
+  }
+  small_pack_kernel<<<1, 512, 0, stream>>>(w, bias, buf, k * k);
+  HG_LAUNCH_OK("small_pack_kernel");
+  HG_CUDA_OK(cudaMemcpyToSymbolAsync(c_small_w, buf, bytes, 0, cudaMemcpyDeviceToDevice, stream));
+  return 0;
 }
 
 // dw[co][ci][tap]: thread = (ci, pixel lane, co quad) -- quads fastest, so a warp's dy load is
@@ -259,10 +407,17 @@ extern "C" int hg_conv_small_fwd(const float* x, const float* w, const float* bi
   const long long n_pix = (long long)B * H * W;
   if (n_pix <= 0) return 0;
   if (n_pix >= (1LL << 31)) return set_error(HG_ENOSUP, "conv_small: too many pixels");
-  const long long n_items = n_pix * (Cp / 4);
-  if (n_items >= (1LL << 31)) return set_error(HG_ENOSUP, "conv_small: too many outputs");
-  conv_small_fwd_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(x, w, bias, residual, y,
-                                                                                            a, (int)n_items);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (small_fast(a) && (rc = small_fast_upload(w, bias, k, stream)) <= 0) {
+    if (rc) return rc;
+    const unsigned grid = (unsigned)((n_pix + 255) / 256);
+    if (k == 3) conv_small_fwd16_kernel<3><<<grid, 256, 0, stream>>>(x, residual, y, a, (int)n_pix);
+    else conv_small_fwd16_kernel<1><<<grid, 256, 0, stream>>>(x, residual, y, a, (int)n_pix);
+    HG_LAUNCH_OK("conv_small_fwd16_kernel");
+    return 0;
+  }
+  dim3 grid((unsigned)((n_pix + 255) / 256), (Cp + 15) / 16);
+  conv_small_fwd_generic_kernel<<<grid, 256, 0, stream>>>(x, w, bias, residual, y, a, (int)n_pix);
   HG_LAUNCH_OK("conv_small_fwd_kernel");
   return 0;
 }
@@ -277,9 +432,16 @@ extern "C" int hg_conv_small_dgrad(const float* dy, const float* w, float* dx, i
   const long long total = (long long)B * H * W;
   if (total <= 0) return 0;
   if (total >= (1LL << 31)) return set_error(HG_ENOSUP, "conv_small: too many pixels");
-  const int pix_cta = 256 / (Cout / 4);
-  conv_small_dgrad_kernel<<<(unsigned)((total + pix_cta - 1) / pix_cta), 256, 0, (cudaStream_t)stream_>>>(
-      dy, w, dx, a, (int)total);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (small_fast(a) && B <= 65535 && (rc = small_fast_upload(w, nullptr, k, stream)) <= 0) {
+    if (rc) return rc;
+    dim3 grid((W + kDgTW - 1) / kDgTW, (H + kDgTH - 1) / kDgTH, B);
+    if (k == 3) conv_small_dgrad16_kernel<3><<<grid, 256, 0, stream>>>(dy, dx, a);
+    else conv_small_dgrad16_kernel<1><<<grid, 256, 0, stream>>>(dy, dx, a);
+    HG_LAUNCH_OK("conv_small_dgrad16_kernel");
+    return 0;
+  }
+  conv_small_dgrad_generic_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dy, w, dx, a, total);
   HG_LAUNCH_OK("conv_small_dgrad_kernel");
   return 0;
 }

@@ -356,15 +356,25 @@ conv_wgrad_col_kernel(const __grid_constant__ CUtensorMap tmdy, const __grid_con
 // randomly initialised networks amplify a 1e-7 reordering to percents in later gradients)
 __global__ void __launch_bounds__(256)
 wgrad_finish_kernel(const float* __restrict__ partial, float* __restrict__ dw, long long n4, long long slice,
-                    int splits) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n4) return;
-  float4 s = *reinterpret_cast<const float4*>(partial + i * 4);
-  for (int k = 1; k < splits; ++k) {
-    const float4 v = *reinterpret_cast<const float4*>(partial + k * slice + i * 4);
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+                    int splits, int G) {
+  // G (a power of two <= 32, fixed by the shape) consecutive lanes share one float4 of dW: lane `sub`
+  // adds the slices sub, sub + G, ... and a fixed xor tree adds the G sums.  Small filters with many
+  // slices (one CTA walking 100+ slices took 46 us) become wide; large ones keep G = 1.
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long i = t / G;
+  const int sub = (int)(t - i * G);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+    for (int k = sub; k < splits; k += G) {
+      const float4 v = *reinterpret_cast<const float4*>(partial + k * slice + i * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
   }
-  *reinterpret_cast<float4*>(dw + i * 4) = s;
+  for (int o = G >> 1; o; o >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+  }
+  if (i < n4 && sub == 0) *reinterpret_cast<float4*>(dw + i * 4) = s;
 }
 
 // Per-device scratch for the split-K slices: one fixed allocation made on first use (never inside a
@@ -410,7 +420,9 @@ static int setup_split(WgradArgs& a, float* dw_packed, size_t out_bytes, cudaStr
 static int finish_split(const WgradArgs& a, size_t out_bytes, cudaStream_t stream) {
   if (!a.partial) return 0;
   const long long n4 = (long long)(out_bytes / 16);
-  wgrad_finish_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a.partial, a.dw, n4, a.slice, a.splits);
+  int G = 1;
+  while (G < 32 && G * 2 <= a.splits && n4 * G < 148LL * 256 * 4) G <<= 1;
+  wgrad_finish_kernel<<<(unsigned)((n4 * G + 255) / 256), 256, 0, stream>>>(a.partial, a.dw, n4, a.slice, a.splits, G);
   HG_LAUNCH_OK("wgrad_finish_kernel");
   return 0;
 }

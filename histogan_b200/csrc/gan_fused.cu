@@ -120,56 +120,78 @@ modulate_bwd_kernel(float* __restrict__ dxm, const float* __restrict__ x,
 
 // ---------------------------------------------------------------------------
 // rgb[b,o,p] = sum_c x[b,p,c] * wmod[b,o,c] (+ prev[b,o,p]);  x NHWC, rgb/prev planar NCHW.
-// One warp per pixel group: 8 channel lanes x float4, 4 pixels per warp pass.
-__global__ void __launch_bounds__(kFusedThreads)
+// G consecutive threads (a power of two, 4 channels each) share one pixel; a CTA takes U x (256 / G)
+// pixels in ONE pass -- every load of a thread (U pixels, the previous rgb values) is issued before
+// the first multiply, nothing loops over pixels: the earlier version (7 dependent load -> shuffle ->
+// load -> store rounds per CTA at 4 CTAs per SM) ran at 2 TB/s, and its 4x4 / 8x8 levels on 32 CTAs.
+// G > 32 (C >= 256, the low-resolution levels): the warps of a pixel meet in shared memory.
+template <int U>
+__global__ void __launch_bounds__(kFusedThreads, 4)
 torgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wmod,
-                 const float* __restrict__ prev, float* __restrict__ rgb, int HW, int C,
-                 int pix_per_cta) {
+                 const float* __restrict__ prev, float* __restrict__ rgb, int HW, int C, int G) {
   extern __shared__ float sw[];                     // [3][C]
+  __shared__ float red[8][U][3];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 3 * C; i += kFusedThreads) sw[i] = wmod[(long long)b * 3 * C + i];
   __syncthreads();
-  const int cl = threadIdx.x & 7, pl = threadIdx.x >> 3;
-  const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
-  // 4 pixels per thread and step, their loads issued together: at C = 32 a pixel is ONE float4 per
-  // lane, and a single load in flight per thread ran this kernel at 2 TB/s (ncu, round 1)
-  constexpr int kU = 4;
-  for (int p = p0 + pl; p < p1; p += kU * kPixLanes) {
-    float a0[kU], a1[kU], a2[kU];
+  const int sub = threadIdx.x % G, pl = threadIdx.x / G, npl = kFusedThreads / G;
+  const int p = blockIdx.x * (U * npl) + pl;        // pixels p + u * npl
+  float a0[U], a1[U], a2[U], pv[U];
 #pragma unroll
-    for (int u = 0; u < kU; ++u) a0[u] = a1[u] = a2[u] = 0.f;
-    for (int c = cl * 4; c < C; c += 32) {
-      float4 v[kU];
+  for (int u = 0; u < U; ++u) {
+    a0[u] = a1[u] = a2[u] = 0.f;
+    const int pu = p + u * npl;
+    pv[u] = (prev && sub < 3 && pu < HW) ? __ldg(prev + ((long long)b * 3 + sub) * HW + pu) : 0.f;
+  }
+  for (int c = sub * 4; c < C; c += G * 4) {
+    float4 v[U];
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int pu = p + u * kPixLanes;
-        v[u] = pu < p1 ? __ldcs(reinterpret_cast<const float4*>(x + ((long long)b * HW + pu) * C + c))
-                       : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const float4 w0 = *reinterpret_cast<const float4*>(sw + c);
-      const float4 w1 = *reinterpret_cast<const float4*>(sw + C + c);
-      const float4 w2 = *reinterpret_cast<const float4*>(sw + 2 * C + c);
+    for (int u = 0; u < U; ++u) {
+      const int pu = p + u * npl;
+      v[u] = pu < HW ? __ldcs(reinterpret_cast<const float4*>(x + ((long long)b * HW + pu) * C + c))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4 w0 = *reinterpret_cast<const float4*>(sw + c);
+    const float4 w1 = *reinterpret_cast<const float4*>(sw + C + c);
+    const float4 w2 = *reinterpret_cast<const float4*>(sw + 2 * C + c);
 #pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        a0[u] += v[u].x * w0.x + v[u].y * w0.y + v[u].z * w0.z + v[u].w * w0.w;
-        a1[u] += v[u].x * w1.x + v[u].y * w1.y + v[u].z * w1.z + v[u].w * w1.w;
-        a2[u] += v[u].x * w2.x + v[u].y * w2.y + v[u].z * w2.z + v[u].w * w2.w;
+    for (int u = 0; u < U; ++u) {
+      a0[u] += v[u].x * w0.x + v[u].y * w0.y + v[u].z * w0.z + v[u].w * w0.w;
+      a1[u] += v[u].x * w1.x + v[u].y * w1.y + v[u].z * w1.z + v[u].w * w1.w;
+      a2[u] += v[u].x * w2.x + v[u].y * w2.y + v[u].z * w2.z + v[u].w * w2.w;
+    }
+  }
+  const int gw = G < 32 ? G : 32;                   // lanes of this pixel inside the warp
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    for (int o = gw >> 1; o > 0; o >>= 1) {
+      a0[u] += __shfl_xor_sync(0xffffffffu, a0[u], o);
+      a1[u] += __shfl_xor_sync(0xffffffffu, a1[u], o);
+      a2[u] += __shfl_xor_sync(0xffffffffu, a2[u], o);
+    }
+  if (G > 32) {                                     // block-uniform: G / 32 warps per pixel, fixed order
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpp = G >> 5;
+    if (lane == 0)
+#pragma unroll
+      for (int u = 0; u < U; ++u) { red[warp][u][0] = a0[u]; red[warp][u][1] = a1[u]; red[warp][u][2] = a2[u]; }
+    __syncthreads();
+    if (sub < 3) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float s = 0.f;
+        for (int w = 0; w < wpp; ++w) s += red[pl * wpp + w][u][sub];
+        a0[u] = s;                                  // lane `sub` now holds output channel `sub`
       }
     }
+  } else {
 #pragma unroll
-    for (int u = 0; u < kU; ++u) {
+    for (int u = 0; u < U; ++u) a0[u] = sub == 0 ? a0[u] : (sub == 1 ? a1[u] : a2[u]);
+  }
+  if (sub < 3) {
 #pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {             // reduce over the 8 channel lanes
-        a0[u] += __shfl_xor_sync(0xffffffffu, a0[u], o);
-        a1[u] += __shfl_xor_sync(0xffffffffu, a1[u], o);
-        a2[u] += __shfl_xor_sync(0xffffffffu, a2[u], o);
-      }
-      const int pu = p + u * kPixLanes;
-      if (cl < 3 && pu < p1) {
-        const float v = cl == 0 ? a0[u] : (cl == 1 ? a1[u] : a2[u]);
-        const long long o = ((long long)b * 3 + cl) * HW + pu;
-        rgb[o] = prev ? v + prev[o] : v;
-      }
+    for (int u = 0; u < U; ++u) {
+      const int pu = p + u * npl;
+      if (pu < HW) rgb[((long long)b * 3 + sub) * HW + pu] = a0[u] + pv[u];
     }
   }
 }
@@ -581,11 +603,17 @@ extern "C" int hg_torgb_fwd(const float* x, const float* wmod, const float* prev
   if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
   if (B <= 0) return 0;
   const size_t smem = sizeof(float) * 3 * (size_t)C;
-  if (smem > 48 * 1024)
-    HG_CUDA_OK(cudaFuncSetAttribute(torgb_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int per = pick_pix_per_cta(HW, B, 1);
-  dim3 grid((HW + per - 1) / per, B);
-  torgb_fwd_kernel<<<grid, kFusedThreads, smem, stream>>>(x, wmod, prev, rgb, HW, C, per);
+  if (smem > 40 * 1024) return set_error(HG_ENOSUP, "torgb_fwd: C=%d too wide", C);
+  int G = 1;
+  while (G * 2 <= C / 4 && G < kFusedThreads) G <<= 1;
+  const int npl = kFusedThreads / G;
+  // 4 pixels per thread where that still leaves >= 2 CTAs per SM, else 1 (the low-resolution levels)
+  const bool wide = (long long)((HW + 4 * npl - 1) / (4 * npl)) * B >= 2 * 148;
+  if (wide)
+    torgb_fwd_kernel<4><<<dim3((HW + 4 * npl - 1) / (4 * npl), B), kFusedThreads, smem, stream>>>(x, wmod, prev, rgb,
+                                                                                               HW, C, G);
+  else
+    torgb_fwd_kernel<1><<<dim3((HW + npl - 1) / npl, B), kFusedThreads, smem, stream>>>(x, wmod, prev, rgb, HW, C, G);
   HG_LAUNCH_OK("torgb_fwd_kernel");
   return 0;
 }

@@ -39,6 +39,8 @@ struct LinearGroups {
   int flags;                               // HG_LIN_*
   float slope, eps;
   int pairs_per_warp;                      // 1..4 row pairs per warp: rows per CTA = 16 * pairs_per_warp
+  int ksplit;                              // > 1 (one group, long K): gridDim.z CTAs share the K range;
+  float* partial;                          //   their raw sums land in partial[z][B][J], ordered finish
 };
 
 constexpr int kRowsPerCta = 64;            // 8 warps x 4 row pairs
@@ -77,10 +79,14 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
   const float* __restrict__ x = t.x[gi] + (long long)b0 * K;
   const float* __restrict__ w = t.w[gi];
   const bool sq = t.flags & HG_LIN_SQUARE_INPUT;
-  const bool multi = K > kKC;                          // several K chunks: partial sums go through smem
+  // this CTA's K range: whole chunks of kKC
+  const int nchunks = (K + kKC - 1) / kKC;
+  const int cper = (nchunks + t.ksplit - 1) / t.ksplit;
+  const int kbeg = min(K, (int)blockIdx.z * cper * kKC), kend = min(K, kbeg + cper * kKC);
+  const bool multi = kend - kbeg > kKC;                // several K chunks: partial sums go through smem
 
-  for (int k0 = 0; k0 < K; k0 += kKC) {
-    const int kc = min(kKC, K - k0);                   // multiple of 4
+  for (int k0 = kbeg; k0 < kend; k0 += kKC) {
+    const int kc = min(kKC, kend - k0);                // multiple of 4
     __syncthreads();
     for (int e = threadIdx.x; e < 32 * (kKC / 4); e += kStyleThreads) {
       const int b = e / (kKC / 4), q = e - b * (kKC / 4);
@@ -122,8 +128,8 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
       float v1 = warp_reduce_scatter(a1, lane);        //         row j0 + 1
       float* pp = part + ((warp * ppw + pr) * 2) * 32 + lane;
       if (multi) {
-        if (k0 > 0) { v0 += pp[0]; v1 += pp[32]; }
-        if (k0 + kKC < K) { pp[0] = v0; pp[32] = v1; continue; }
+        if (k0 > kbeg) { v0 += pp[0]; v1 += pp[32]; }
+        if (k0 + kKC < kend) { pp[0] = v0; pp[32] = v1; continue; }
       }
       if (lane >= nb) continue;
 #pragma unroll
@@ -131,6 +137,10 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
         const int j = j0 + r;
         if (j >= J) break;
         float v = r ? v1 : v0;
+        if (t.ksplit > 1) {                            // raw partial sum; epilogue in the finish kernel
+          t.partial[((long long)blockIdx.z * t.B + b0 + lane) * J + j] = v;
+          continue;
+        }
         if (t.bias[gi]) v += t.bias[gi][j];
         if (t.flags & HG_LIN_RSQRT_EPS) v = rsqrtf(v + t.eps);
         if (t.flags & HG_LIN_LRELU) v = v > 0.f ? v : v * t.slope;
@@ -139,6 +149,21 @@ grouped_linear_fwd_kernel(const LinearGroups t) {
       }
     }
   }
+}
+
+// y[b][j] = f(sum over the K splits, in index order, + bias)
+__global__ void __launch_bounds__(256)
+grouped_linear_fwd_finish_kernel(const LinearGroups t) {
+  const long long n = (long long)t.B * t.J[0];
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  float v = t.partial[i];
+  for (int z = 1; z < t.ksplit; ++z) v += t.partial[z * n + i];
+  if (t.bias[0]) v += t.bias[0][i % t.J[0]];
+  if (t.flags & HG_LIN_RSQRT_EPS) v = rsqrtf(v + t.eps);
+  if (t.flags & HG_LIN_LRELU) v = v > 0.f ? v : v * t.slope;
+  if (t.flags & HG_LIN_ADD_ONE) v += 1.f;
+  t.y[0][i] = v;
 }
 
 // ------------------------------------------------------------------ backward --
@@ -422,14 +447,32 @@ extern "C" int hg_grouped_linear_fwd(int32_t count, const float* const* x, const
   }
   t.first_block[count] = blocks;
   t.count = count; t.B = B; t.flags = flags; t.slope = slope; t.eps = eps;
+  // one layer with a long K (the 12288-wide first layer of the histogram MLP: 50 MB of weights on
+  // J/16 = 64 CTAs ran at 0.36 TB/s): the K chunks are divided over gridDim.z, ordered finish
+  t.ksplit = 1; t.partial = nullptr;
+  if (count == 1 && K[0] >= 8 * kKC) {
+    int ks = 1;
+    const int nchunks = (K[0] + kKC - 1) / kKC;
+    while (ks * 2 <= 16 && ks * 2 <= nchunks / 2 && (long long)blocks * ((B + 31) / 32) * ks < 4LL * sms) ks *= 2;
+    ks = (nchunks + (nchunks + ks - 1) / ks - 1) / ((nchunks + ks - 1) / ks);      // no empty split
+    if (ks > 1) {
+      float* ws = style_workspace(sizeof(float) * (size_t)ks * B * J[0], (cudaStream_t)stream_);
+      if (ws) { t.ksplit = ks; t.partial = ws; }
+    }
+  }
   const size_t smem = sizeof(float) * (32 * kXS + kRowsPerCta * 32);
   static PerDeviceOnce once;
   if (once.need()) {
     HG_CUDA_OK(cudaFuncSetAttribute(grouped_linear_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     once.mark();
   }
-  grouped_linear_fwd_kernel<<<dim3(blocks, (B + 31) / 32), kStyleThreads, smem, (cudaStream_t)stream_>>>(t);
+  grouped_linear_fwd_kernel<<<dim3(blocks, (B + 31) / 32, t.ksplit), kStyleThreads, smem, (cudaStream_t)stream_>>>(t);
   HG_LAUNCH_OK("grouped_linear_fwd_kernel");
+  if (t.ksplit > 1) {
+    const long long n = (long long)B * J[0];
+    grouped_linear_fwd_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(t);
+    HG_LAUNCH_OK("grouped_linear_fwd_finish_kernel");
+  }
   return 0;
 }
 

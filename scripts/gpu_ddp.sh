@@ -15,9 +15,16 @@ except Exception as e:
     print('$name FAILED', e); print(open('gpurun_out/bench_train_${N}gpu_${TAG}_$name.err').read()[-1500:])
 PY
 }
-run arena_overlap HG_X=1
-run arena_nooverlap HG_SPLIT_G=0
-run legacy HG_GRAD_ARENA=0 HG_SPLIT_G=0
+MODES=${3:-"pipelined4 pipelined8 unpipelined"}
+for m in $MODES; do
+  case $m in
+    pipelined4) run pipelined4 HG_EXCHANGE_CHUNKS=4 ;;
+    pipelined8) run pipelined8 HG_EXCHANGE_CHUNKS=8 ;;
+    unpipelined) run unpipelined HG_EXCHANGE_CHUNKS=1 ;;
+    nosplit) run nosplit HG_SPLIT_G=0 ;;
+    legacy) run legacy HG_GRAD_ARENA=0 HG_SPLIT_G=0 HG_EXCHANGE_CHUNKS=1 ;;
+  esac
+done
 # the same window on ONE GPU of the same box, for the efficiency denominator
 HG_BENCH_LIGHT=1 timeout 600 python bench.py --gpus 1 --steps 16 --warmup 3 > gpurun_out/bench_train_1gpu_${TAG}_samewindow.json 2> gpurun_out/bench_train_1gpu_${TAG}_samewindow.err
 python -c "

@@ -49,10 +49,14 @@ def test_mod_conv_layer_fwd_bwd(upsample, cuda_device):
         assert _rel(a, b) < 2e-3, (name, _rel(a, b))
 
 
-def test_to_rgb_fwd_bwd(cuda_device):
+@pytest.mark.parametrize("shape", [(3, 64, 16), (2, 32, 64), (2, 2048, 4), (3, 1024, 8), (2, 512, 16),
+                                   (2, 256, 32), (1, 128, 5), (2, 48, 7), (33, 32, 128), (40, 256, 16), (2, 8, 6)])
+def test_to_rgb_fwd_bwd(shape, cuda_device):
+    """every lane-group width of torgb_fwd (8..256 threads per pixel, 1 and 4 pixels per thread), odd
+    sizes, a channel count that is not a power of two"""
     from histogan_b200 import fused
     torch.manual_seed(1)
-    B, Cc, S = 3, 64, 16
+    B, Cc, S = shape
     x = torch.randn(B, Cc, S, S, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
     style = torch.randn(B, Cc, device="cuda", requires_grad=True)
     w = torch.randn(3, Cc, 1, 1, device="cuda", requires_grad=True)
@@ -162,6 +166,24 @@ def test_grouped_linear_forward_and_backward(cuda_device):
         for x, w, gy, a, a0 in zip(xs, ws, gys, acc, acc0):
             ref = a0.double() + 2 * x.double() * (gy.double() @ w.double())
             assert (a.double() - ref).abs().max().item() < 2e-4
+
+
+def test_grouped_linear_long_k_split(cuda_device):
+    """one layer with a long K (the 12288-wide first layer of the histogram MLP, histoGAN.py:384-398):
+    the K chunks are divided over several CTAs per row block, ordered finish with the epilogue;
+    deterministic."""
+    import torch.nn.functional as F
+    from histogan_b200 import fused as fz
+    torch.manual_seed(1)
+    for B, J, K in [(32, 1024, 12288), (7, 100, 4100), (32, 512, 4096)]:
+        x = torch.randn(B, K, device="cuda")
+        w = torch.randn(J, K, device="cuda") / K ** 0.5
+        b = torch.randn(J, device="cuda")
+        y, = fz.grouped_linear([x], [w], [b], fz.LIN_LRELU, slope=0.2)
+        ref = F.leaky_relu(F.linear(x.double(), w.double(), b.double()), 0.2)
+        assert (y.double() - ref).abs().max().item() < 2e-5, (B, J, K)
+        y2, = fz.grouped_linear([x], [w], [b], fz.LIN_LRELU, slope=0.2)
+        assert torch.equal(y, y2)
 
 
 def test_analytic_demodulation_matches_autograd(cuda_device):
