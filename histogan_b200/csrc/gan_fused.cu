@@ -604,7 +604,7 @@ extern "C" int hg_torgb_fwd(const float* x, const float* wmod, const float* prev
   if (B <= 0) return 0;
   const size_t smem = sizeof(float) * 3 * (size_t)C;
   if (smem > 40 * 1024) return set_error(HG_ENOSUP, "torgb_fwd: C=%d too wide", C);
-  int G = 1;
+  int G = 4;                                        // >= 3: lanes 0..2 of a pixel write the three outputs
   while (G * 2 <= C / 4 && G < kFusedThreads) G <<= 1;
   const int npl = kFusedThreads / G;
   // 4 pixels per thread where that still leaves >= 2 CTAs per SM, else 1 (the low-resolution levels)

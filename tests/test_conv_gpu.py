@@ -168,6 +168,9 @@ SMALL_CASES = [
     (3, 3, 19, 23, 24, 3, 24),     # odd sizes, Cout not a power of two, dense output
     (1, 4, 16, 16, 64, 3, 64),     # transparent images (4 channels), widest supported layer
     (5, 3, 64, 64, 16, 1, 16),
+    (2, 3, 48, 80, 16, 3, 16),     # 3 -> 16, dense 16-channel output: the constant-memory kernels (k = 3)
+    (3, 3, 19, 23, 16, 3, 16),     # ... odd sizes (partial 32 x 8 dgrad tiles)
+    (2, 3, 21, 37, 16, 1, 16),     # ... k = 1
 ]
 
 
