@@ -366,6 +366,122 @@ conv_small_wgrad_kernel(const float* __restrict__ dy, const float* __restrict__ 
   }
 }
 
+// 3 -> 16, 3x3: thread = (row-segment lane, input channel, output quad) walks 32 consecutive pixels of one
+// image row with the 3x3 window of its input plane sliding in registers: per pixel ONE 16-byte dy load and
+// THREE new image values feed 36 multiply-adds (the generic kernel: 10 loads with their own bounds checks).
+// 21 segment lanes x 12 roles per CTA; per-CTA partial vectors, fixed-order finish as above.
+constexpr int kWgSeg = 32;
+__global__ void __launch_bounds__(256, 2)
+conv_small_wgrad16_k3_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ partial,
+                             const SmallConvArgs a, int n_units, int segs) {
+  constexpr int T = 9, ROLES = 12, LANES = 256 / ROLES;          // 21 lanes, 4 idle threads
+  __shared__ float red[256 * 4];
+  const int sl = threadIdx.x / ROLES, role = threadIdx.x - sl * ROLES;
+  const int cq = role & 3, ci = role >> 2;
+  const bool live = sl < LANES;
+  float acc[4][T];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int t = 0; t < T; ++t) acc[e][t] = 0.f;
+  if (live) {
+    for (int u = blockIdx.x * LANES + sl; u < n_units; u += gridDim.x * LANES) {
+      const int s = u % segs, r = u / segs, h = r % a.H, b = r / a.H;
+      const int w0 = s * kWgSeg, w1 = min(a.W, w0 + kWgSeg);
+      const float* xc = x + (long long)b * a.sb + ci * a.sc;
+      const float* xr[3];
+      bool ok[3];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ih = h + kh - 1;
+        ok[kh] = ih >= 0 && ih < a.H;
+        xr[kh] = xc + (long long)ih * a.sh;
+      }
+      float c0[3], c1[3], c2[3];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        c0[kh] = (ok[kh] && w0 > 0) ? __ldg(xr[kh] + (long long)(w0 - 1) * a.sw) : 0.f;
+        c1[kh] = ok[kh] ? __ldg(xr[kh] + (long long)w0 * a.sw) : 0.f;
+      }
+      const float4* g4 = reinterpret_cast<const float4*>(dy + ((long long)r * a.W + w0) * kFastCout) + cq;
+#pragma unroll 4
+      for (int w = w0; w < w1; ++w) {
+        const float4 g = __ldg(g4 + (w - w0) * 4);
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+          c2[kh] = (ok[kh] && w + 1 < a.W) ? __ldg(xr[kh] + (long long)(w + 1) * a.sw) : 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float xv[3] = {c0[kh], c1[kh], c2[kh]};
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            acc[0][kh * 3 + kw] = fmaf(g.x, xv[kw], acc[0][kh * 3 + kw]);
+            acc[1][kh * 3 + kw] = fmaf(g.y, xv[kw], acc[1][kh * 3 + kw]);
+            acc[2][kh * 3 + kw] = fmaf(g.z, xv[kw], acc[2][kh * 3 + kw]);
+            acc[3][kh * 3 + kw] = fmaf(g.w, xv[kw], acc[3][kh * 3 + kw]);
+          }
+          c0[kh] = c1[kh]; c1[kh] = c2[kh];
+        }
+      }
+    }
+  }
+  float* out = partial + (long long)blockIdx.x * kFastCout * kFastCin * T;
+#pragma unroll
+  for (int t = 0; t < T; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[threadIdx.x * 4 + e] = live ? acc[e][t] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < kFastCout * kFastCin) {
+      const int co = threadIdx.x % kFastCout, c2i = threadIdx.x / kFastCout;
+      const int rl = c2i * 4 + co / 4, e = co % 4;                 // role (ci, cq) of this output
+      float sum = 0.f;
+      for (int l = 0; l < LANES; ++l) sum += red[(l * ROLES + rl) * 4 + e];
+      out[(co * kFastCin + c2i) * T + t] = sum;
+    }
+  }
+}
+
+// 3 -> 16, 1x1: thread = (pixel lane, output quad), consecutive threads = consecutive quads then pixels: the dy
+// loads of a warp are 512 contiguous bytes, the three image values of a pixel feed 12 multiply-adds.
+__global__ void __launch_bounds__(256)
+conv_small_wgrad16_k1_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ partial,
+                             const SmallConvArgs a, int n_pix) {
+  __shared__ float red[256 * 12];
+  const int pl = threadIdx.x >> 2, cq = threadIdx.x & 3;
+  float acc[4][3];
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) acc[e][c] = 0.f;
+  const int chunk = (n_pix + gridDim.x - 1) / gridDim.x;
+  const int p_begin = blockIdx.x * chunk, p_end = min(n_pix, p_begin + chunk);
+#pragma unroll 2
+  for (int p = p_begin + pl; p < p_end; p += 64) {
+    const int ow = p % a.W, r = p / a.W, oh = r % a.H, b = r / a.H;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(dy + (long long)p * kFastCout) + cq);
+    const float* xp = x + (long long)b * a.sb + (long long)oh * a.sh + (long long)ow * a.sw;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float xv = __ldg(xp + c * a.sc);
+      acc[0][c] = fmaf(g.x, xv, acc[0][c]); acc[1][c] = fmaf(g.y, xv, acc[1][c]);
+      acc[2][c] = fmaf(g.z, xv, acc[2][c]); acc[3][c] = fmaf(g.w, xv, acc[3][c]);
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) red[(e * 3 + c) * 256 + threadIdx.x] = acc[e][c];
+  __syncthreads();
+  if (threadIdx.x < kFastCout * kFastCin) {
+    const int co = threadIdx.x % kFastCout, c = threadIdx.x / kFastCout;
+    const float* col = red + ((co & 3) * 3 + c) * 256 + (co >> 2);
+    float sum = 0.f;
+    for (int l = 0; l < 64; ++l) sum += col[l * 4];
+    partial[(long long)blockIdx.x * kFastCout * kFastCin + co * kFastCin + c] = sum;
+  }
+}
+
 // one warp per weight: lanes stride over the CTA partials, then a fixed xor tree
 __global__ void conv_small_wgrad_finish_kernel(const float* __restrict__ partial, float* __restrict__ dw, int n,
                                                int ctas) {
@@ -466,8 +582,18 @@ extern "C" int hg_conv_small_wgrad(const float* dy, const float* x, float* dw, v
   if (n_pix >= (1LL << 31)) return set_error(HG_ENOSUP, "conv_small: too many pixels");
   if (ws_bytes < hg_conv_small_wgrad_workspace_bytes(Cin, Cout, k))
     return set_error(HG_EWS, "conv_small_wgrad: workspace too small");
-  if (k == 3) conv_small_wgrad_kernel<3><<<ctas, 256, 0, stream>>>(dy, x, (float*)ws, a, (int)n_pix);
-  else conv_small_wgrad_kernel<1><<<ctas, 256, 0, stream>>>(dy, x, (float*)ws, a, (int)n_pix);
+  if (small_fast(a) && k == 3) {
+    const int segs = (W + kWgSeg - 1) / kWgSeg;
+    const long long units = (long long)B * H * segs;
+    if (units >= (1LL << 31)) return set_error(HG_ENOSUP, "conv_small: too many pixels");
+    conv_small_wgrad16_k3_kernel<<<ctas, 256, 0, stream>>>(dy, x, (float*)ws, a, (int)units, segs);
+  } else if (small_fast(a) && k == 1) {
+    conv_small_wgrad16_k1_kernel<<<ctas, 256, 0, stream>>>(dy, x, (float*)ws, a, (int)n_pix);
+  } else if (k == 3) {
+    conv_small_wgrad_kernel<3><<<ctas, 256, 0, stream>>>(dy, x, (float*)ws, a, (int)n_pix);
+  } else {
+    conv_small_wgrad_kernel<1><<<ctas, 256, 0, stream>>>(dy, x, (float*)ws, a, (int)n_pix);
+  }
   HG_LAUNCH_OK("conv_small_wgrad_kernel");
   conv_small_wgrad_finish_kernel<<<(n + 7) / 8, 256, 0, stream>>>((const float*)ws, dw, n, ctas);
   HG_LAUNCH_OK("conv_small_wgrad_finish_kernel");
