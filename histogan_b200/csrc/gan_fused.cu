@@ -120,78 +120,114 @@ modulate_bwd_kernel(float* __restrict__ dxm, const float* __restrict__ x,
 
 // ---------------------------------------------------------------------------
 // rgb[b,o,p] = sum_c x[b,p,c] * wmod[b,o,c] (+ prev[b,o,p]);  x NHWC, rgb/prev planar NCHW.
-// G consecutive threads (a power of two, 4 channels each) share one pixel; a CTA takes U x (256 / G)
-// pixels in ONE pass -- every load of a thread (U pixels, the previous rgb values) is issued before
-// the first multiply, nothing loops over pixels: the earlier version (7 dependent load -> shuffle ->
-// load -> store rounds per CTA at 4 CTAs per SM) ran at 2 TB/s, and its 4x4 / 8x8 levels on 32 CTAs.
+// G consecutive threads (a power of two >= 4, 4 channels each) share one pixel; a tile = U x (256 / G)
+// consecutive pixels = ONE contiguous piece of x (16 KB at U = 4).  A CTA walks gridDim.x-strided tiles of
+// one image; the tiles arrive through a 3-stage ring of 1-D bulk copies (cp.async.bulk + mbarrier, issued
+// by one thread): the bytes in flight no longer depend on registers or on where the CTA is in its
+// load -> shuffle -> store chain.  History (ncu --set full, profiles/r02_torgb_fwd_ncu.md): 7 dependent
+// rounds per CTA with register loads ran at 1.9 TB/s; one tile per CTA, everything issued up front, at
+// 2.2 TB/s (filter load, sync, pixel loads, store: three serial latencies per CTA lifetime, loads in
+// flight for a third of it; 43 % issue slots, long-scoreboard stalls).
 // G > 32 (C >= 256, the low-resolution levels): the warps of a pixel meet in shared memory.
+constexpr int kRgbStages = 3;
 template <int U>
-__global__ void __launch_bounds__(kFusedThreads, 4)
+__global__ void __launch_bounds__(kFusedThreads)
 torgb_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wmod,
-                 const float* __restrict__ prev, float* __restrict__ rgb, int HW, int C, int G) {
-  extern __shared__ float sw[];                     // [3][C]
+                 const float* __restrict__ prev, float* __restrict__ rgb, int HW, int C, int G, int tiles) {
+  extern __shared__ __align__(128) float smem[];    // ring [stages][tile_pix * C], then sw [3][C]
   __shared__ float red[8][U][3];
+  __shared__ __align__(8) uint64_t full[kRgbStages];
   const int b = blockIdx.y;
+  const int sub = threadIdx.x % G, pl = threadIdx.x / G, npl = kFusedThreads / G;
+  const int tile_pix = U * npl;
+  const int tile_floats = tile_pix * C;
+  float* sw = smem + kRgbStages * tile_floats;
+  const float* xb = x + (long long)b * HW * C;
+  auto fetch = [&](int it) {                        // thread 0: tile of iteration `it` into its stage
+    const int tile = blockIdx.x + it * gridDim.x;
+    if (tile >= tiles) return;
+    const int p0 = tile * tile_pix;
+    const uint32_t bytes = (uint32_t)(min(HW - p0, tile_pix) * C) * 4u;
+    const int st = it % kRgbStages;
+    ptx::mbar_expect_tx(&full[st], bytes);
+    ptx::bulk_load_1d(smem + st * tile_floats, xb + (long long)p0 * C, bytes, &full[st]);
+  };
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kRgbStages; ++st) ptx::mbar_init(&full[st], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int it = 0; it < kRgbStages; ++it) fetch(it);
   for (int i = threadIdx.x; i < 3 * C; i += kFusedThreads) sw[i] = wmod[(long long)b * 3 * C + i];
   __syncthreads();
-  const int sub = threadIdx.x % G, pl = threadIdx.x / G, npl = kFusedThreads / G;
-  const int p = blockIdx.x * (U * npl) + pl;        // pixels p + u * npl
-  float a0[U], a1[U], a2[U], pv[U];
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    a0[u] = a1[u] = a2[u] = 0.f;
-    const int pu = p + u * npl;
-    pv[u] = (prev && sub < 3 && pu < HW) ? __ldg(prev + ((long long)b * 3 + sub) * HW + pu) : 0.f;
-  }
-  for (int c = sub * 4; c < C; c += G * 4) {
-    float4 v[U];
+  int it = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int st = it % kRgbStages;
+    const int p = tile * tile_pix + pl;
+    float pv[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int pu = p + u * npl;
-      v[u] = pu < HW ? __ldcs(reinterpret_cast<const float4*>(x + ((long long)b * HW + pu) * C + c))
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      pv[u] = (prev && sub < 3 && pu < HW) ? __ldg(prev + ((long long)b * 3 + sub) * HW + pu) : 0.f;
     }
-    const float4 w0 = *reinterpret_cast<const float4*>(sw + c);
-    const float4 w1 = *reinterpret_cast<const float4*>(sw + C + c);
-    const float4 w2 = *reinterpret_cast<const float4*>(sw + 2 * C + c);
+    ptx::mbar_wait(&full[st], (uint32_t)((it / kRgbStages) & 1));
+    const float* xt = smem + st * tile_floats;
+    float a0[U], a1[U], a2[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      a0[u] += v[u].x * w0.x + v[u].y * w0.y + v[u].z * w0.z + v[u].w * w0.w;
-      a1[u] += v[u].x * w1.x + v[u].y * w1.y + v[u].z * w1.z + v[u].w * w1.w;
-      a2[u] += v[u].x * w2.x + v[u].y * w2.y + v[u].z * w2.z + v[u].w * w2.w;
+    for (int u = 0; u < U; ++u) a0[u] = a1[u] = a2[u] = 0.f;
+    for (int c = sub * 4; c < C; c += G * 4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(sw + c);
+      const float4 w1 = *reinterpret_cast<const float4*>(sw + C + c);
+      const float4 w2 = *reinterpret_cast<const float4*>(sw + 2 * C + c);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pu = p + u * npl;
+        if (pu < HW) {                              // pixels beyond the image were not copied
+          const float4 v = *reinterpret_cast<const float4*>(xt + (pl + u * npl) * C + c);
+          a0[u] += v.x * w0.x + v.y * w0.y + v.z * w0.z + v.w * w0.w;
+          a1[u] += v.x * w1.x + v.y * w1.y + v.z * w1.z + v.w * w1.w;
+          a2[u] += v.x * w2.x + v.y * w2.y + v.z * w2.z + v.w * w2.w;
+        }
+      }
     }
-  }
-  const int gw = G < 32 ? G : 32;                   // lanes of this pixel inside the warp
+    const int gw = G < 32 ? G : 32;                 // lanes of this pixel inside the warp
 #pragma unroll
-  for (int u = 0; u < U; ++u)
-    for (int o = gw >> 1; o > 0; o >>= 1) {
-      a0[u] += __shfl_xor_sync(0xffffffffu, a0[u], o);
-      a1[u] += __shfl_xor_sync(0xffffffffu, a1[u], o);
-      a2[u] += __shfl_xor_sync(0xffffffffu, a2[u], o);
+    for (int u = 0; u < U; ++u)
+      for (int o = gw >> 1; o > 0; o >>= 1) {
+        a0[u] += __shfl_xor_sync(0xffffffffu, a0[u], o);
+        a1[u] += __shfl_xor_sync(0xffffffffu, a1[u], o);
+        a2[u] += __shfl_xor_sync(0xffffffffu, a2[u], o);
+      }
+    if (G > 32) {                                   // block-uniform: G / 32 warps per pixel, fixed order
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      if (lane == 0)
+#pragma unroll
+        for (int u = 0; u < U; ++u) { red[warp][u][0] = a0[u]; red[warp][u][1] = a1[u]; red[warp][u][2] = a2[u]; }
     }
-  if (G > 32) {                                     // block-uniform: G / 32 warps per pixel, fixed order
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpp = G >> 5;
-    if (lane == 0)
+    __syncthreads();                                // every thread is done with this stage (and `red` is written)
+    if (threadIdx.x == 0) fetch(it + kRgbStages);   // refill the stage just consumed
+    if (G > 32) {
+      const int wpp = G >> 5;
+      if (sub < 3) {
 #pragma unroll
-      for (int u = 0; u < U; ++u) { red[warp][u][0] = a0[u]; red[warp][u][1] = a1[u]; red[warp][u][2] = a2[u]; }
-    __syncthreads();
+        for (int u = 0; u < U; ++u) {
+          float s = 0.f;
+          for (int w = 0; w < wpp; ++w) s += red[pl * wpp + w][u][sub];
+          a0[u] = s;                                // lane `sub` now holds output channel `sub`
+        }
+      }
+      __syncthreads();                              // `red` may be rewritten by the next tile
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) a0[u] = sub == 0 ? a0[u] : (sub == 1 ? a1[u] : a2[u]);
+    }
     if (sub < 3) {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        float s = 0.f;
-        for (int w = 0; w < wpp; ++w) s += red[pl * wpp + w][u][sub];
-        a0[u] = s;                                  // lane `sub` now holds output channel `sub`
+        const int pu = p + u * npl;
+        if (pu < HW) rgb[((long long)b * 3 + sub) * HW + pu] = a0[u] + pv[u];
       }
-    }
-  } else {
-#pragma unroll
-    for (int u = 0; u < U; ++u) a0[u] = sub == 0 ? a0[u] : (sub == 1 ? a1[u] : a2[u]);
-  }
-  if (sub < 3) {
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pu = p + u * npl;
-      if (pu < HW) rgb[((long long)b * 3 + sub) * HW + pu] = a0[u] + pv[u];
     }
   }
 }
@@ -602,18 +638,28 @@ extern "C" int hg_torgb_fwd(const float* x, const float* wmod, const float* prev
   if (!x || !wmod || !rgb) return set_error(HG_EINVAL, "null tensor pointer");
   if (C % 4) return set_error(HG_ENOSUP, "C=%d must be a multiple of 4", C);
   if (B <= 0) return 0;
-  const size_t smem = sizeof(float) * 3 * (size_t)C;
-  if (smem > 40 * 1024) return set_error(HG_ENOSUP, "torgb_fwd: C=%d too wide", C);
+  if (C > 4096) return set_error(HG_ENOSUP, "torgb_fwd: C=%d too wide", C);
+  if ((uintptr_t)x & 15) return set_error(HG_EINVAL, "torgb_fwd: x must be 16-byte aligned");
   int G = 4;                                        // >= 3: lanes 0..2 of a pixel write the three outputs
   while (G * 2 <= C / 4 && G < kFusedThreads) G <<= 1;
   const int npl = kFusedThreads / G;
-  // 4 pixels per thread where that still leaves >= 2 CTAs per SM, else 1 (the low-resolution levels)
+  // 4 pixels per thread where that still leaves >= 2 CTAs per SM, else 1 (the low-resolution levels);
+  // about 4 CTAs per SM in all, each walking its share of the image's tiles through a 3-stage ring
   const bool wide = (long long)((HW + 4 * npl - 1) / (4 * npl)) * B >= 2 * 148;
-  if (wide)
-    torgb_fwd_kernel<4><<<dim3((HW + 4 * npl - 1) / (4 * npl), B), kFusedThreads, smem, stream>>>(x, wmod, prev, rgb,
-                                                                                               HW, C, G);
-  else
-    torgb_fwd_kernel<1><<<dim3((HW + npl - 1) / npl, B), kFusedThreads, smem, stream>>>(x, wmod, prev, rgb, HW, C, G);
+  const int U = wide ? 4 : 1;
+  const int tiles = (HW + U * npl - 1) / (U * npl);
+  int gx = (148 * 4 + B - 1) / B;
+  if (gx > tiles) gx = tiles;
+  const size_t smem = sizeof(float) * ((size_t)kRgbStages * U * npl * C + 3 * (size_t)C);
+  static PerDeviceOnce once;
+  if (once.need()) {
+    HG_CUDA_OK(cudaFuncSetAttribute(torgb_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    HG_CUDA_OK(cudaFuncSetAttribute(torgb_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    once.mark();
+  }
+  if (smem > 160 * 1024) return set_error(HG_ENOSUP, "torgb_fwd: C=%d too wide", C);
+  if (wide) torgb_fwd_kernel<4><<<dim3(gx, B), kFusedThreads, smem, stream>>>(x, wmod, prev, rgb, HW, C, G, tiles);
+  else torgb_fwd_kernel<1><<<dim3(gx, B), kFusedThreads, smem, stream>>>(x, wmod, prev, rgb, HW, C, G, tiles);
   HG_LAUNCH_OK("torgb_fwd_kernel");
   return 0;
 }
