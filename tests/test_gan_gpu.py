@@ -131,7 +131,13 @@ def test_discriminator_256_matches_reference(cuda_device):
     _report("discriminator_256[+gradient-penalty]", e, t2)
     print("CPU TF32 emulation vs golden:", {k: f"{v:.2e}" for k, v in e_emu.items()})
     print("  first-order worst:", sc.worst(t1_emu), "\n  +gp worst:", sc.worst(t2_emu))
-    assert e["logits"] < ACT_TOL and e["gp"] < 5e-3
+    # the two logits of this fixture (49.2 and -739.7, seeded untrained weights) are a 2-sample statistic of
+    # TF32 rounding noise: the CPU emulation lands at 6.4e-4, and two first-layer kernels that are BOTH within
+    # 1e-7 of fp64 on that layer (conv_small generic / constant-memory, scripts/debug_small2.py) at 7.9e-4
+    # and 1.37e-3 -- the gate is 3x the measured floor, not a fixed 1e-3
+    from tests import parity
+    parity.record("discriminator_256[logits]", {"logits": e["logits"], "floor_logits": e_emu["logits"]})
+    assert e["logits"] < 3 * e_emu["logits"] and e["gp"] < 5e-3
     assert e["g1_images_norm"] < 1e-2 and e["g1_images_samples"] < 2 * e_emu["g1_images_samples"] + 1e-2
     # strict where the arithmetic allows it: cosine >= 0.999 unless the reference's own algorithm
     # with TF32-rounded operands (what cuDNN runs for the reference on a GPU) is below that itself
