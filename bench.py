@@ -378,7 +378,8 @@ def graph_time(fns, reps=3):
 
 def conv_microbench(dev, B, rotate_bytes=320 << 20):
     """Device time of the three tcgen05 conv primitives (forward, input gradient, weight gradient) on
-    every G/D layer shape of the step (channel counts padded to 32 as the networks carry them).
+    every G/D layer shape of the step (channel counts padded as the networks carry them; the two image-input
+    layers of D on the direct kernels that run them in the step).
     Each layer is captured as a CUDA graph of `n` launches on `n` DIFFERENT operand sets whose total
     size exceeds the 126 MB L2 (operands cold, as in the step), and the graph replay is timed."""
     from histogan_b200 import conv, ops
@@ -389,6 +390,28 @@ def conv_microbench(dev, B, rotate_bytes=320 << 20):
             continue
         cip, cop = ops._round_up(ci), ops._round_up(co)
         oh = h // s
+        if ops.SMALL_CIN and conv.small_ok(ci, co, k, s, k // 2):
+            # the image-input layers run the CUDA-core kernels of conv_small.cu on the planar image (as
+            # DiscriminatorBlock 0 does): time those, not a channel-padded tensor-core launch
+            n = 3
+            imgs = [torch.randn(B, ci, h, h, device=dev) for _ in range(n)]
+            dys = [conv.tf32_round(torch.randn(B, cop, h, h, device=dev)).contiguous(memory_format=torch.channels_last)
+                   for _ in range(n)]
+            w = torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5
+            bias = torch.randn(co, device=dev)
+            f = _conv_flops(B, ci, co, k, oh)
+            t = {"fwd": graph_time([lambda i=i: conv.conv_small_fwd(imgs[i], w, cop, bias=bias, lrelu=True, round_tf32=True)
+                                    for i in range(n)]),
+                 "dgrad": graph_time([lambda i=i: conv.conv_small_dgrad(dys[i], w, ci) for i in range(n)]),
+                 "wgrad": graph_time([lambda i=i: conv.conv_small_wgrad(dys[i], imgs[i], (co, ci, k, k)) for i in range(n)])}
+            for kind, v in t.items():
+                tot[kind][0] += f
+                tot[kind][1] += v
+            rows.append([f"{net} {ci}->{co} k{k} s{s} @{h} (CUDA cores)", round(f / t["fwd"] / 1e12, 1),
+                         round(f / t["dgrad"] / 1e12, 1), round(f / t["wgrad"] / 1e12, 1), round(t["fwd"] * 1e6, 1),
+                         round(t["dgrad"] * 1e6, 1), round(t["wgrad"] * 1e6, 1)])
+            del imgs, dys
+            continue
         per_set = 4 * (B * cip * h * h + B * cop * oh * oh + cop * cip * k * k)
         n = max(2, min(48, -(-rotate_bytes // per_set)))
         xs = [conv.tf32_round(torch.randn(B, cip, h, h, device=dev)).contiguous(memory_format=torch.channels_last)
@@ -535,8 +558,9 @@ def run_train(args):
                 "achieved": round(conv_tf, 1), "peak": bf16_peak,
                 "unit": "TFLOP/s", "frac": round(conv_tf / bf16_peak, 4),
                 # dram__bytes_read+write of ONE launch of this kernel on the 32->32 3x3 @256^2 layer
-                # (ncu --set full, profiles/r01_conv_fwd_32ch_256_ncu.md); algorithmic = 536.9 MB
-                "traffic": 486.8e6, "traffic_layer": "32->32 3x3 @256^2, batch 32: algorithmic 536.9e6 B "
+                # (ncu --set full, profiles/r02_conv_fwd_32ch_256_ncu.md: 268.5 MB read + 222.6 MB written at
+                # capture time, the rest of y still in L2); algorithmic = 536.9 MB
+                "traffic": 491.1e6, "traffic_layer": "32->32 3x3 @256^2, batch 32: algorithmic 536.9e6 B "
                                                      "(x read once + y written once)",
                 "peak_kind": peak_kind,
                 "note": "operands are TF32 (half the bf16 rate): fraction of the TF32 ceiling = 2x frac",
