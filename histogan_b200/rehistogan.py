@@ -759,7 +759,8 @@ class recoloringTrainer():
         if self.GAN is None:
             self.init_GAN()
         GAN = self.GAN
-        GAN.train()
+        if not GAN.training:
+            GAN.train()
         if self.cuda_graphs and self.gradient_accumulate_every == 1:
             return self._finish_step(*self._train_graphed(alpha, beta, gamma, self.steps % 4 == 0))
         dev = torch.device('cuda', torch.cuda.current_device())

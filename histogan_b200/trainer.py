@@ -209,6 +209,59 @@ class HistoGAN(nn.Module):
         return x
 
 
+class _PendingScalars:
+    """the scalar read-outs of one graph-replayed step on their way to the host: ONE stack kernel, ONE
+    device-to-host copy into pinned memory and an event -- the host does not wait.  `get()` blocks until the
+    copy has landed.  (Four `.item()` calls at the end of every step kept the GPU idle during the whole
+    host prologue of the next step: 0.8-1.0 ms of a 25 ms step, scripts/ddp_timeline.py.)"""
+
+    _pool = []
+
+    def __init__(self, named):
+        self.names = list(named)
+        dev = next(iter(named.values())).device
+        stacked = torch.stack([t.detach().reshape(()).float() for t in named.values()])
+        # slot 0: "the discriminator or the generator loss is NaN" (histoGAN.py:1003), max over the ranks
+        flag = torch.isnan(stacked[:2]).any().float().reshape(1)
+        if _ddp_active():
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        stacked = torch.cat((flag, stacked))
+        self.buf = self._pool.pop() if self._pool else torch.empty(16, dtype=torch.float32).pin_memory()
+        self.n = stacked.numel()
+        self.buf[:self.n].copy_(stacked, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record()
+        self.values = None
+
+    def get(self):
+        """{'nan': bool, name: float, ...}"""
+        if self.values is None:
+            self.event.synchronize()
+            v = self.buf[:self.n].tolist()
+            self.values = dict(zip(self.names, v[1:]))
+            self.values['nan'] = v[0] > 0
+            self._pool.append(self.buf)
+            self.buf = None
+        return self.values
+
+
+def _lazy_scalar(name):
+    """attribute `name` of the Trainer: a plain float, except that after a graph-replayed step the value is
+    still in flight (Trainer._pending) and is fetched on first access"""
+    slot = '_lazy_' + name
+
+    def get(self):
+        pend = self.__dict__.get('_pending')
+        if pend is not None and name in pend.names:
+            self._adopt(pend)
+        return self.__dict__.get(slot, 0)
+
+    def set(self, value):
+        self.__dict__[slot] = value
+
+    return property(get, set)
+
+
 class GradArena:
     """ONE contiguous float32 buffer holding the gradients of a parameter group (D, or G+S+H), so that
     the data-parallel exchange is a single all-reduce instead of ~100-200 small ones.
@@ -397,6 +450,22 @@ class Trainer:
     """Same constructor / attributes / methods as the reference Trainer
     (histoGAN/histoGAN.py:718-1139)."""
 
+    # the step's scalar read-outs (histoGAN.py:930,982-983 assign floats): same values, fetched lazily
+    d_loss = _lazy_scalar('d_loss')
+    g_loss = _lazy_scalar('g_loss')
+    h_loss = _lazy_scalar('h_loss')
+    last_gp_loss = _lazy_scalar('last_gp_loss')
+
+    def _adopt(self, pend):
+        """the values of a finished step become the attributes"""
+        vals = pend.get()
+        if self.__dict__.get('_pending') is pend:
+            self._pending = None
+        for k in ('d_loss', 'g_loss', 'h_loss', 'last_gp_loss'):
+            if k in vals:
+                self.__dict__['_lazy_' + k] = vals[k]
+        return vals
+
     def __init__(self, name, results_dir, models_dir, image_size, network_capacity,
                  transparent=False, batch_size=4, mixed_prob=0.9, gradient_accumulate_every=1,
                  lr=2e-4, num_workers=None, save_every=1000, trunc_psi=0.6, fp16=False,
@@ -411,10 +480,18 @@ class Trainer:
         # path-length regulariser
         self.cuda_graphs = bool(kwargs.pop('cuda_graphs', False))
         self._graphs = {}
+        self._param_lists = None
+        self._pending = None
         self._static = None
         self._arenas = {}
         # flat gradient arenas (one all-reduce per phase): on under torch.distributed, or forced
         self.use_grad_arena = kwargs.pop('grad_arena', None)
+        # 'deferred' (default on the CUDA-graph path): train() returns without waiting for the GPU; a NaN loss
+        # of step N raises NanException from the train() call of step N+1 (from the same call on
+        # checkpoint / evaluation / path-length steps).  'immediate': the reference's timing, one host
+        # sync per step.
+        self.nan_check = kwargs.pop('nan_check', os.environ.get('HG_NAN_CHECK', 'deferred'))
+        self._pending = None
         # DDP: pieces of the G-side gradient arena whose all-reduce is pipelined with the optimiser
         self.exchange_chunks = int(kwargs.pop('exchange_chunks', os.environ.get('HG_EXCHANGE_CHUNKS', 4)))
         # split the captured G phase into a D-independent part and the rest (overlaps the D-side
@@ -473,6 +550,8 @@ class Trainer:
         # captured graphs hold the OLD parameter / gradient tensors: a new GAN (first call, or
         # load() -> load_config() after a NaN) must be captured afresh
         self._graphs = {}
+        self._param_lists = None
+        self._pending = None
         self._static = None
         self._arenas = {}
         self.GAN = HistoGAN(lr=self.lr, image_size=self.image_size,
@@ -585,10 +664,8 @@ class Trainer:
         if self.GAN is None:
             self.init_GAN()
         GAN = self.GAN
-        GAN.train()
-        total_disc_loss = torch.tensor(0.0).cuda()
-        total_gen_loss = torch.tensor(0.0).cuda()
-        total_hist_loss = torch.tensor(0.0).cuda()
+        if not GAN.training:                 # the walk over ~600 modules costs 0.2 ms of GPU-idle host time
+            GAN.train()
         batch_size = self.batch_size
         image_size, latent_dim, num_layers = GAN.G.image_size, GAN.G.latent_dim, GAN.G.num_layers
         accum = self.gradient_accumulate_every
@@ -596,13 +673,12 @@ class Trainer:
         apply_path_penalty = self.steps % 32 == 0
         avg_pl_length = self.pl_mean
         if self.cuda_graphs and accum == 1:
-            total_disc_loss, total_gen_loss, total_hist_loss, pl = self._train_graphed(
-                alpha, apply_gradient_penalty, apply_path_penalty)
-            if pl is not None:
-                avg_pl_length = pl
-            return self._finish_step(total_disc_loss, total_gen_loss, total_hist_loss,
-                                     apply_path_penalty, avg_pl_length)
+            previous, pending = self._train_graphed(alpha, apply_gradient_penalty, apply_path_penalty)
+            return self._finish_graphed_step(previous, pending, apply_path_penalty)
 
+        total_disc_loss = torch.tensor(0.0).cuda()
+        total_gen_loss = torch.tensor(0.0).cuda()
+        total_hist_loss = torch.tensor(0.0).cuda()
         # ---------------------------------------------------- discriminator --
         GAN.D_opt.zero_grad()
         arena_d = self._arena('d')
@@ -685,8 +761,26 @@ class Trainer:
         return self._finish_step(total_disc_loss, total_gen_loss, total_hist_loss,
                                  apply_path_penalty, avg_pl_length)
 
+    def _finish_graphed_step(self, previous, pending, apply_path_penalty):
+        """bookkeeping of a graph-replayed step.  The host waits for THIS step's read-outs only when it needs
+        them now (path-length mean, checkpoint, evaluation, nan_check='immediate'); otherwise it checks the
+        PREVIOUS step's NaN flag -- by now long on the host -- and returns while the GPU still works."""
+        save_now = self.steps % self.save_every == 0
+        eval_now = self.steps % 1000 == 0 or (self.steps % 100 == 0 and self.steps < 2500)
+        nan, nan_step = False, self.steps
+        if previous is not None and previous.get()['nan']:
+            nan, nan_step = True, self.steps - 1
+        if apply_path_penalty or save_now or eval_now or self.nan_check != 'deferred' or nan:
+            vals = self._adopt(pending)
+            nan = nan or vals['nan']
+            avg_pl = vals.get('avg_pl', self.pl_mean)
+        else:
+            avg_pl = self.pl_mean
+        return self._finish_step(float('nan') if nan else 0.0, 0.0, 0.0, apply_path_penalty, avg_pl,
+                                 nan_reduced=True, nan_step=nan_step)
+
     def _finish_step(self, total_disc_loss, total_gen_loss, total_hist_loss, apply_path_penalty,
-                     avg_pl_length):
+                     avg_pl_length, nan_reduced=False, nan_step=None):
         GAN = self.GAN
         # ------------------------------------------------------ bookkeeping --
         if apply_path_penalty and not np.isnan(avg_pl_length):
@@ -697,12 +791,19 @@ class Trainer:
             GAN.reset_parameter_averaging()
 
         checkpoint_num = floor(self.steps / self.save_every)
-        nan_flag = torch.isnan(total_gen_loss) | torch.isnan(total_disc_loss)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if isinstance(total_gen_loss, float):        # graph path: the losses are already on the host
+            nan_flag = total_gen_loss != total_gen_loss or total_disc_loss != total_disc_loss
+            if _ddp_active() and not nan_reduced:
+                nan_flag = torch.tensor(float(nan_flag), device='cuda')
+        else:
+            nan_flag = torch.isnan(total_gen_loss) | torch.isnan(total_disc_loss)
+        if _ddp_active() and not nan_reduced:
             f = nan_flag.float()
             dist.all_reduce(f, op=dist.ReduceOp.MAX)               # all ranks retry together
             nan_flag = f > 0
         if bool(nan_flag):
+            if nan_step is not None:                  # deferred detection: the step that produced the NaN
+                checkpoint_num = floor(nan_step / self.save_every)
             print(f'NaN detected for generator or discriminator. Loading from checkpoint '
                   f'#{checkpoint_num}')
             self.load(checkpoint_num)
@@ -916,8 +1017,10 @@ class Trainer:
                 st['images'].copy_(batch['images'], non_blocking=True)
 
         stage(next(self.loader), 0)
-        d_params = list(GAN.D.parameters())
-        g_params = [p for grp in GAN.G_opt.param_groups for p in grp['params']]
+        if self._param_lists is None:
+            self._param_lists = (list(GAN.D.parameters()),
+                                 [p for grp in GAN.G_opt.param_groups for p in grp['params']])
+        d_params, g_params = self._param_lists
         overlapped = _GradOverlap([]).enabled       # the collectives then live inside the graphs
         divergence, gp = self._graphed(('D', apply_gp), lambda: self._phase_d(apply_gp), d_params)
         split_g = self.split_g_phase
@@ -955,15 +1058,15 @@ class Trainer:
             GAN.G_opt.step()
         else:
             self._exchange_and_step('g', g_params, GAN.G_opt)
-        # host reads once, after everything has been queued
+        # one stacked device-to-host copy of the read-outs, after everything has been queued
         self.q_loss = 0.0
+        named = {'d_loss': divergence, 'g_loss': g_loss, 'h_loss': h_loss}
         if gp is not None:
-            self.last_gp_loss = gp.item()
-        self.d_loss = float(divergence.item())
-        self.g_loss = float(g_loss.item())
-        self.h_loss = float(h_loss.item())
-        return divergence.clone(), g_loss.clone(), h_loss.clone(), \
-            (float(avg_pl.item()) if avg_pl is not None else None)
+            named['last_gp_loss'] = gp
+        if avg_pl is not None:
+            named['avg_pl'] = avg_pl
+        previous, self._pending = self._pending, _PendingScalars(named)
+        return previous, self._pending
 
     # ------------------------------------------------------------ evaluate --
     @torch.no_grad()

@@ -242,6 +242,49 @@ def test_cuda_graph_training_path(tmp_path, cuda_device):
     assert sum(not torch.equal(a, b) for a, b in zip(before, tg.GAN.D.parameters())) > 10
 
 
+@pytest.mark.parametrize("mode", ["deferred", "immediate"])
+def test_readouts_and_nan_detection_on_the_graph_path(mode, tmp_path, cuda_device):
+    """graph path: train() queues the step and returns; d_loss / g_loss / h_loss / last_gp_loss are fetched on
+    first access (one stacked device-to-host copy).  A NaN loss reloads the checkpoint and raises
+    NanException (histoGAN.py:1003-1006) -- from the same call with nan_check='immediate', from the NEXT
+    train() call with 'deferred' (default), and from the same call on a checkpoint step either way."""
+    from histogan_b200.trainer import NanException
+    torch.manual_seed(0)
+    tr = _trainer(tmp_path, cuda_graphs=True, fast_rng=True, nan_check=mode)
+    tr.init_GAN()
+    tr.steps = 2501
+    tr.train(alpha=2)
+    assert (tr._pending is not None) == (mode == "deferred")          # nothing fetched yet / already adopted
+    d, g, h = tr.d_loss, tr.g_loss, tr.h_loss
+    assert tr._pending is None and all(isinstance(v, float) and v == v for v in (d, g, h))
+    tr.steps = 2504
+    tr.train(alpha=2)
+    assert tr.last_gp_loss >= 0
+    tr.save(2)                                                        # model_2.pt: floor(2505 / 1000)
+    good = [p.detach().clone() for p in tr.GAN.D.parameters()]
+    with torch.no_grad():
+        next(iter(tr.GAN.D.parameters())).fill_(float("nan"))
+    if mode == "immediate":
+        with pytest.raises(NanException):
+            tr.train(alpha=2)
+    else:
+        tr.train(alpha=2)                                             # the NaN step itself returns
+        with pytest.raises(NanException):
+            tr.train(alpha=2)
+    assert tr.steps == 2000 and tr._pending is None and tr._graphs == {}
+    assert all(torch.equal(a, b) for a, b in zip(good, tr.GAN.D.parameters()))
+    tr.steps = 2509
+    tr.train(alpha=2)                                                 # trains again after the reload
+    assert tr.d_loss == tr.d_loss
+    # a checkpoint step detects its own NaN (it must not save a poisoned model)
+    tr.save(3)
+    with torch.no_grad():
+        next(iter(tr.GAN.D.parameters())).fill_(float("nan"))
+    tr.steps = 3000
+    with pytest.raises(NanException):
+        tr.train(alpha=2)
+
+
 def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
     """the captured D phase (with gradient penalty) and G phase reproduce the eager phases:
     same losses and same parameter gradients when fed the same latents / noise."""
