@@ -285,6 +285,45 @@ def test_readouts_and_nan_detection_on_the_graph_path(mode, tmp_path, cuda_devic
         tr.train(alpha=2)
 
 
+def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
+    """graph path with batches in pinned HOST memory (the e2e data path): the images / histograms travel
+    through the copy stream and the two staging buffers into the fixed-address graph inputs; every step must
+    see ITS batch although train() returns before the GPU is done."""
+    torch.manual_seed(0)
+    tr = _trainer(tmp_path, cuda_graphs=True, fast_rng=True)
+    tr.init_GAN()
+    tr.steps = 2501
+
+    class Loader:
+        def __init__(self):
+            self.n, self.last = 0, None
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            self.n += 1
+            g = torch.Generator().manual_seed(self.n)
+            h = torch.rand(4, 3, 64, 64, generator=g)
+            self.last = {"images": torch.rand(4, 3, 32, 32, generator=g).pin_memory(),
+                         "histograms": (h / h.sum(dim=(1, 2, 3), keepdim=True)).pin_memory()}
+            return self.last
+
+    tr.loader = Loader()
+    seen = []
+    for _ in range(4):
+        tr.train(alpha=2)
+        first = tr.loader.n - 1                 # two batches per step: D phase (images + hists), G phase (hists)
+        g = torch.Generator().manual_seed(first)
+        torch.rand(4, 3, 64, 64, generator=g)
+        seen.append((torch.rand(4, 3, 32, 32, generator=g), tr.loader.last["histograms"].clone()))
+    torch.cuda.synchronize()
+    assert tr.loader.n == 8
+    assert torch.equal(tr._static["images"].cpu(), seen[-1][0])
+    assert torch.equal(tr._static["hists"].cpu(), seen[-1][1])
+    assert tr.d_loss == tr.d_loss and "copy_stream" in tr._static
+
+
 def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
     """the captured D phase (with gradient penalty) and G phase reproduce the eager phases:
     same losses and same parameter gradients when fed the same latents / noise."""
