@@ -288,15 +288,12 @@ def test_readouts_and_nan_detection_on_the_graph_path(mode, tmp_path, cuda_devic
 def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
     """graph path with batches in pinned HOST memory (the e2e data path): the images / histograms travel
     through the copy stream and the two staging buffers into the fixed-address graph inputs; every step must
-    see ITS batch although train() returns before the GPU is done."""
-    torch.manual_seed(0)
-    tr = _trainer(tmp_path, cuda_graphs=True, fast_rng=True)
-    tr.init_GAN()
-    tr.steps = 2501
+    see ITS batch although train() returns before the GPU is done -- the losses of four steps are bit-identical
+    to a trainer fed the same batches already on the device."""
 
     class Loader:
-        def __init__(self):
-            self.n, self.last = 0, None
+        def __init__(self, device):
+            self.n, self.device = 0, device
 
         def __iter__(self):
             return self
@@ -305,23 +302,27 @@ def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
             self.n += 1
             g = torch.Generator().manual_seed(self.n)
             h = torch.rand(4, 3, 64, 64, generator=g)
-            self.last = {"images": torch.rand(4, 3, 32, 32, generator=g).pin_memory(),
-                         "histograms": (h / h.sum(dim=(1, 2, 3), keepdim=True)).pin_memory()}
-            return self.last
+            b = {"images": torch.rand(4, 3, 32, 32, generator=g), "histograms": h / h.sum(dim=(1, 2, 3), keepdim=True)}
+            return {k: (v.pin_memory() if self.device == "host" else v.cuda()) for k, v in b.items()}
 
-    tr.loader = Loader()
-    seen = []
-    for _ in range(4):
-        tr.train(alpha=2)
-        first = tr.loader.n - 1                 # two batches per step: D phase (images + hists), G phase (hists)
-        g = torch.Generator().manual_seed(first)
+    losses = {}
+    for where in ("host", "device"):
+        torch.manual_seed(0)
+        tr = _trainer(tmp_path / where, cuda_graphs=True, fast_rng=True)
+        tr.init_GAN()
+        tr.steps = 2501
+        tr.loader = Loader(where)
+        out = []
+        for _ in range(4):
+            tr.train(alpha=2)
+            out.append(tr._pending)                # read later: the host must not wait between the steps
+        losses[where] = [(p.get()["d_loss"], p.get()["g_loss"], p.get()["h_loss"]) for p in out]
+        assert tr.loader.n == 8 and ("copy_stream" in tr._static) == (where == "host")
+        g = torch.Generator().manual_seed(7)        # the last D-phase batch
         torch.rand(4, 3, 64, 64, generator=g)
-        seen.append((torch.rand(4, 3, 32, 32, generator=g), tr.loader.last["histograms"].clone()))
-    torch.cuda.synchronize()
-    assert tr.loader.n == 8
-    assert torch.equal(tr._static["images"].cpu(), seen[-1][0])
-    assert torch.equal(tr._static["hists"].cpu(), seen[-1][1])
-    assert tr.d_loss == tr.d_loss and "copy_stream" in tr._static
+        assert torch.equal(tr._static["images"].cpu(), torch.rand(4, 3, 32, 32, generator=g))
+    assert losses["host"] == losses["device"], losses
+    assert all(v == v for step in losses["host"] for v in step)
 
 
 def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
