@@ -288,8 +288,8 @@ def test_readouts_and_nan_detection_on_the_graph_path(mode, tmp_path, cuda_devic
 def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
     """graph path with batches in pinned HOST memory (the e2e data path): the images / histograms travel
     through the copy stream and the two staging buffers into the fixed-address graph inputs; every step must
-    see ITS batch although train() returns before the GPU is done -- the losses of four steps are bit-identical
-    to a trainer fed the same batches already on the device."""
+    see ITS batch although train() returns before the GPU is done -- the losses of four steps equal those of a
+    trainer fed the same batches already on the device."""
 
     class Loader:
         def __init__(self, device):
@@ -302,7 +302,9 @@ def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
             self.n += 1
             g = torch.Generator().manual_seed(self.n)
             h = torch.rand(4, 3, 64, 64, generator=g)
-            b = {"images": torch.rand(4, 3, 32, 32, generator=g), "histograms": h / h.sum(dim=(1, 2, 3), keepdim=True)}
+            # brightness grows with the batch index: a stale batch moves the losses by percents
+            b = {"images": torch.rand(4, 3, 32, 32, generator=g) * min(1.0, 0.2 + 0.1 * self.n),
+                 "histograms": h / h.sum(dim=(1, 2, 3), keepdim=True)}
             return {k: (v.pin_memory() if self.device == "host" else v.cuda()) for k, v in b.items()}
 
     losses = {}
@@ -320,8 +322,11 @@ def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
         assert tr.loader.n == 8 and ("copy_stream" in tr._static) == (where == "host")
         g = torch.Generator().manual_seed(7)        # the last D-phase batch
         torch.rand(4, 3, 64, 64, generator=g)
-        assert torch.equal(tr._static["images"].cpu(), torch.rand(4, 3, 32, 32, generator=g))
-    assert losses["host"] == losses["device"], losses
+        assert torch.equal(tr._static["images"].cpu(), torch.rand(4, 3, 32, 32, generator=g) * 0.9)
+    # same batches, same seeds: equal up to the reduction-order noise of the few atomically summed gradients
+    for a, b in zip(losses["host"], losses["device"]):
+        assert all(abs(x - y) <= 2e-3 * max(abs(x), abs(y), 1e-3) for x, y in zip(a, b)), losses
+    assert losses["host"][0] == losses["device"][0]          # the first step has no history: bit-identical
     assert all(v == v for step in losses["host"] for v in step)
 
 
