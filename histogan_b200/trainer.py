@@ -768,8 +768,12 @@ class Trainer:
         save_now = self.steps % self.save_every == 0
         eval_now = self.steps % 1000 == 0 or (self.steps % 100 == 0 and self.steps < 2500)
         nan, nan_step = False, self.steps
-        if previous is not None and previous.get()['nan']:
-            nan, nan_step = True, self.steps - 1
+        if previous is not None:
+            pv = previous.get()
+            if 'last_gp_loss' in pv:                  # persists over the non-penalty steps (:922)
+                self.__dict__['_lazy_last_gp_loss'] = pv['last_gp_loss']
+            if pv['nan']:
+                nan, nan_step = True, self.steps - 1
         if apply_path_penalty or save_now or eval_now or self.nan_check != 'deferred' or nan:
             vals = self._adopt(pending)
             nan = nan or vals['nan']
