@@ -768,8 +768,12 @@ class Trainer:
         save_now = self.steps % self.save_every == 0
         eval_now = self.steps % 1000 == 0 or (self.steps % 100 == 0 and self.steps < 2500)
         nan, nan_step = False, self.steps
-        if previous is not None and previous.get()['nan']:
-            nan, nan_step = True, self.steps - 1
+        if previous is not None:
+            pv = previous.get()
+            if 'last_gp_loss' in pv:                  # persists over the non-penalty steps (:922)
+                self.__dict__['_lazy_last_gp_loss'] = pv['last_gp_loss']
+            if pv['nan']:
+                nan, nan_step = True, self.steps - 1
         if apply_path_penalty or save_now or eval_now or self.nan_check != 'deferred' or nan:
             vals = self._adopt(pending)
             nan = nan or vals['nan']
@@ -984,6 +988,35 @@ class Trainer:
             self._capture([key], [fn], [params])
         return self._replay(key)
 
+    def _to_static(self, key, src):
+        """batch tensor -> the fixed-address graph input `key`.  A HOST batch goes through a copy stream and
+        two device staging buffers: train() returns before the GPU has finished the step, so the copy of
+        step N+1's batch is issued while step N still computes -- on the main stream it would queue behind
+        it (25 MB of images per step: 0.5-1 ms of PCIe time on the critical path)."""
+        st = self._static
+        dst = st[key]
+        if src.is_cuda:
+            dst.copy_(src, non_blocking=True)
+            return
+        ring = st.get('ring_' + key)
+        if ring is None:
+            ring = st['ring_' + key] = {'buf': [torch.empty_like(dst) for _ in range(2)], 'free': [None, None], 'i': 0}
+        if 'copy_stream' not in st:
+            st['copy_stream'] = torch.cuda.Stream()
+        cs, i = st['copy_stream'], ring['i']
+        ring['i'] ^= 1
+        with torch.cuda.stream(cs):
+            if ring['free'][i] is not None:
+                cs.wait_event(ring['free'][i])           # the step that read this staging buffer has copied it out
+            ring['buf'][i].copy_(src, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        main = torch.cuda.current_stream()
+        main.wait_event(ready)
+        dst.copy_(ring['buf'][i], non_blocking=True)
+        ring['free'][i] = torch.cuda.Event()
+        ring['free'][i].record(main)
+
     def _train_graphed(self, alpha, apply_gp, apply_pl=False):
         GAN = self.GAN
         B, S_, L = self.batch_size, GAN.G.image_size, GAN.G.num_layers - 2
@@ -1012,9 +1045,9 @@ class Trainer:
             st['mask'].copy_(st['mask_host'][phase], non_blocking=True)
             st['mask_event'][phase] = torch.cuda.Event()
             st['mask_event'][phase].record()
-            st['hists'].copy_(batch['histograms'], non_blocking=True)
+            self._to_static('hists', batch['histograms'])
             if phase == 0:
-                st['images'].copy_(batch['images'], non_blocking=True)
+                self._to_static('images', batch['images'])
 
         stage(next(self.loader), 0)
         if self._param_lists is None:

@@ -285,6 +285,51 @@ def test_readouts_and_nan_detection_on_the_graph_path(mode, tmp_path, cuda_devic
         tr.train(alpha=2)
 
 
+def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
+    """graph path with batches in pinned HOST memory (the e2e data path): the images / histograms travel
+    through the copy stream and the two staging buffers into the fixed-address graph inputs; every step must
+    see ITS batch although train() returns before the GPU is done -- the losses of four steps equal those of a
+    trainer fed the same batches already on the device."""
+
+    class Loader:
+        def __init__(self, device):
+            self.n, self.device = 0, device
+
+        def __iter__(self):
+            return self
+
+        def __next__(self):
+            self.n += 1
+            g = torch.Generator().manual_seed(self.n)
+            h = torch.rand(4, 3, 64, 64, generator=g)
+            # brightness grows with the batch index: a stale batch moves the losses by percents
+            b = {"images": torch.rand(4, 3, 32, 32, generator=g) * min(1.0, 0.2 + 0.1 * self.n),
+                 "histograms": h / h.sum(dim=(1, 2, 3), keepdim=True)}
+            return {k: (v.pin_memory() if self.device == "host" else v.cuda()) for k, v in b.items()}
+
+    losses = {}
+    for where in ("host", "device"):
+        torch.manual_seed(0)
+        tr = _trainer(tmp_path / where, cuda_graphs=True, fast_rng=True)
+        tr.init_GAN()
+        tr.steps = 2501
+        tr.loader = Loader(where)
+        out = []
+        for _ in range(4):
+            tr.train(alpha=2)
+            out.append(tr._pending)                # read later: the host must not wait between the steps
+        losses[where] = [(p.get()["d_loss"], p.get()["g_loss"], p.get()["h_loss"]) for p in out]
+        assert tr.loader.n == 8 and ("copy_stream" in tr._static) == (where == "host")
+        g = torch.Generator().manual_seed(7)        # the last D-phase batch
+        torch.rand(4, 3, 64, 64, generator=g)
+        assert torch.equal(tr._static["images"].cpu(), torch.rand(4, 3, 32, 32, generator=g) * 0.9)
+    # same batches, same seeds: equal up to the reduction-order noise of the few atomically summed gradients
+    for a, b in zip(losses["host"], losses["device"]):
+        assert all(abs(x - y) <= 2e-3 * max(abs(x), abs(y), 1e-3) for x, y in zip(a, b)), losses
+    assert losses["host"][0] == losses["device"][0]          # the first step has no history: bit-identical
+    assert all(v == v for step in losses["host"] for v in step)
+
+
 def test_graph_replay_equals_eager_phase(tmp_path, cuda_device, monkeypatch):
     """the captured D phase (with gradient penalty) and G phase reproduce the eager phases:
     same losses and same parameter gradients when fed the same latents / noise."""
