@@ -326,7 +326,7 @@ def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
     # same batches, same seeds: equal up to the reduction-order noise of the few atomically summed gradients
     for a, b in zip(losses["host"], losses["device"]):
         assert all(abs(x - y) <= 2e-3 * max(abs(x), abs(y), 1e-3) for x, y in zip(a, b)), losses
-    assert losses["host"][0] == losses["device"][0]          # the first step has no history: bit-identical
+    assert losses["host"][0][0] == losses["device"][0][0]    # first D phase: no history, no atomics: bit-identical
     assert all(v == v for step in losses["host"] for v in step)
 
 
