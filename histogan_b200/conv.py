@@ -20,9 +20,10 @@ CONV_ROUND_TF32 = 2
 def tf32_round(t: torch.Tensor) -> torch.Tensor:
     """round-to-nearest-even to TF32 (10-bit mantissa); torch-side twin of
     hg::tf32_round used for small host-prepared tensors and in tests."""
-    i = t.contiguous().view(torch.int32)
+    tc = t.contiguous()
+    i = tc.view(torch.int32)
     r = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
-    return r.view(torch.float32).view_as(t)
+    return torch.where(torch.isfinite(tc), r.view(torch.float32), tc).view_as(t)       # Inf / NaN pass through
 
 
 def as_nhwc(x: torch.Tensor) -> torch.Tensor:

@@ -205,14 +205,18 @@ __device__ __forceinline__ void red_add_f32x4(float* p, float a, float b, float 
 // round-to-nearest(-even) of the 13 low mantissa bits: the value tcgen05 kind::tf32
 // would otherwise TRUNCATE.  Unbiased rounding keeps the generator within 3e-4 of the
 // fp32 reference across all 14 conv layers; truncation drifts to 1.6e-3.
+// Inf / NaN pass through unchanged: the integer add would carry the hardware's canonical NaN
+// (0x7FFFFFFF) over into -0.0, and the trainer's NaN recovery (histoGAN.py:1003-1006) depends on NaNs
+// surviving every rounding point (tests/test_trainer_gpu.py::test_readouts_and_nan_detection...).
 __host__ __device__ __forceinline__ float tf32_round(float v) {
 #ifdef __CUDA_ARCH__
-  uint32_t i = __float_as_uint(v);
-  i = (i + 0x0FFFu + ((i >> 13) & 1u)) & 0xFFFFE000u;
-  return __uint_as_float(i);
+  const uint32_t i = __float_as_uint(v);
+  const uint32_t r = (i + 0x0FFFu + ((i >> 13) & 1u)) & 0xFFFFE000u;
+  return (i & 0x7F800000u) == 0x7F800000u ? v : __uint_as_float(r);
 #else
   union { float f; uint32_t u; } c;
   c.f = v;
+  if ((c.u & 0x7F800000u) == 0x7F800000u) return v;
   c.u = (c.u + 0x0FFFu + ((c.u >> 13) & 1u)) & 0xFFFFE000u;
   return c.f;
 #endif

@@ -14,8 +14,10 @@ from histogan_b200 import _lib, ops
 
 
 def tf32(t):
-    i = t.contiguous().view(torch.int32)
-    return ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32).view_as(t)
+    tc = t.contiguous()
+    i = tc.view(torch.int32)
+    r = ((i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF).view(torch.float32)
+    return torch.where(torch.isfinite(tc), r, tc).view_as(t)
 
 
 @contextlib.contextmanager

@@ -54,6 +54,27 @@ def test_conv_matches_torch(case, cuda_device):
     assert err < 2e-5, err
 
 
+def test_tf32_rounding_keeps_nan_and_inf(cuda_device):
+    """hg::tf32_round and its torch twin: round-to-nearest-even on finite values; Inf / NaN -- including the
+    hardware's canonical NaN 0x7FFFFFFF, which a bare integer add carries over into -0.0 -- pass through, so
+    a NaN weight still reaches the loss (Trainer's NaN recovery, histoGAN.py:1003-1006)."""
+    from histogan_b200 import conv, ops
+    bits = torch.tensor([0x7FFFFFFF, 0x7FC00000, -1, 0x7F800000, -8388608, 0x3F801000, 0x3F803000, 0x3F800FFF],
+                        dtype=torch.int32)
+    x = bits.view(torch.float32).reshape(1, 8, 1, 1).repeat(2, 1, 3, 3).cuda()
+    for y in (ops.round_tf32_nhwc(x), conv.tf32_round(x)):
+        y = y.cpu()[0, :, 0, 0]
+        assert torch.isnan(y[:3]).all() and y[3] == float("inf") and y[4] == -float("inf")
+        assert y[5:].view(torch.int32).tolist() == [0x3F800000, 0x3F804000, 0x3F800000]     # ties to even
+    # a NaN in one input element poisons its receptive field and nothing else
+    w = torch.randn(32, 32, 3, 3).cuda()
+    xx = conv.tf32_round(torch.randn(1, 32, 8, 8)).cuda().contiguous(memory_format=torch.channels_last)
+    xx[0, 5, 4, 4] = float("nan")
+    y = conv.conv2d_nhwc(xx, conv.pack_weight(w, 0), 1, 1, cout=32, round_tf32=True)
+    nan = torch.isnan(y[0, 0])
+    assert nan[3:6, 3:6].all() and int(nan.sum()) == 9
+
+
 def test_conv_epilogue(cuda_device):
     from histogan_b200 import conv
     B, Cin, S, Cout = 2, 64, 16, 64
