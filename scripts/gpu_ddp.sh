@@ -25,7 +25,9 @@ for m in $MODES; do
     legacy) run legacy HG_GRAD_ARENA=0 HG_SPLIT_G=0 HG_EXCHANGE_CHUNKS=1 ;;
   esac
 done
-# the same window on ONE GPU of the same box, for the efficiency denominator
+# the same window on ONE GPU of the same box, for the efficiency denominator (skipped with a 4th argument "no1":
+# under gpurun --gpus 8 a single-GPU minute is charged eight times)
+[ "$4" = "no1" ] && exit 0
 HG_BENCH_LIGHT=1 timeout 600 python bench.py --gpus 1 --steps 16 --warmup 3 > gpurun_out/bench_train_1gpu_${TAG}_samewindow.json 2> gpurun_out/bench_train_1gpu_${TAG}_samewindow.err
 python -c "
 import json; d=json.load(open('gpurun_out/bench_train_1gpu_${TAG}_samewindow.json')); print('1gpu', d['value'], d['ms_per_step'], d['config'].get('step_ms'))"
