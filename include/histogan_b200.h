@@ -297,6 +297,9 @@ int hg_demod_bwd(const float* gd, const float* d, const float* mod, const float*
  *   dgrad dx (planar, fully written) = conv^T(dy, w)
  *   wgrad dw (contiguous OIHW) = sum over batch and pixels; deterministic (per-CTA partials in ws,
  *         hg_conv_small_wgrad_workspace_bytes, added in index order)
+ * Cin == 3, Cout == Cp == 16 (network_capacity 16) runs specialised kernels whose filter lives in constant
+ * memory: the calls of one device must then be issued on ONE stream (each call rewrites the constant bank
+ * in stream order); HG_SMALL_GENERIC=1 selects the generic kernels.
  * ------------------------------------------------------------------------ */
 int hg_conv_small_fwd(const float* x, const float* w, const float* bias, const float* residual, float* y,
                       int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t Cp, int32_t k,
