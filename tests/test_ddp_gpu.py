@@ -65,7 +65,7 @@ def test_two_rank_training_keeps_replicas_identical(tmp_path, cuda_device):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in procs)
+    res = sorted(q.get(timeout=300) for _ in procs)
     for p in procs:
         p.join(timeout=120)
     for rank, ok, arenas, finite, raised, steps in res:
