@@ -27,6 +27,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import contextlib
+
 import torch
 
 from . import _lib
@@ -275,6 +277,25 @@ def _raw_grad_weight(dy, x, wshape, stride, pad, dy_rounded=False, x_rounded=Fal
     return dw
 
 
+# torch.autograd.grad(outputs, inputs=images, create_graph=True) -- the first half of the gradient penalty
+# (histoGAN.py:156-163) -- needs d out / d x of every layer and nothing else, but a Python autograd.Function
+# only sees the static `needs_input_grad` (the weights DO require grad) and would compute a weight and a bias
+# gradient per layer that the engine then throws away: one discarded weight-gradient pass of the whole
+# discriminator per penalty step.  The caller says so:
+_INPUT_GRADS_ONLY = False
+
+
+@contextlib.contextmanager
+def input_grads_only():
+    """inside: the backward of the conv ops returns gradients for their activations only"""
+    global _INPUT_GRADS_ONLY
+    prev, _INPUT_GRADS_ONLY = _INPUT_GRADS_ONLY, True
+    try:
+        yield
+    finally:
+        _INPUT_GRADS_ONLY = prev
+
+
 class _Conv2d(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride, pad, x_rounded=False, padded_io=False):
@@ -289,7 +310,7 @@ class _Conv2d(torch.autograd.Function):
         dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = _Conv2dGradInput.apply(dy, w, stride, pad, tuple(x.shape[2:]), False, padded_io)
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[1] and not _INPUT_GRADS_ONLY:
             dw = _Conv2dGradWeight.apply(dy, x, tuple(w.shape), stride, pad, False, x_rounded,
                                          None if torch.is_grad_enabled() else grad_slot(w))
         return dx, dw, None, None, None, None
@@ -417,6 +438,8 @@ class _ConvBiasAct(torch.autograd.Function):
         stride, pad, act, slope, has_b, has_res, xshape = ctx.cfg
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], \
             has_b and ctx.needs_input_grad[2]
+        if _INPUT_GRADS_ONLY:
+            need_w = need_b = False
         dx = dw = db = None
         if need_x or need_w or need_b:
             dpre, dbp = _BiasActBwd.apply(dy, y if act else None, slope if act else 1.0, need_b)

@@ -117,9 +117,11 @@ def evaluate_in_chunks(max_batch_size, model, *args):
 def gradient_penalty(images, output, weight=10):
     """R1-style penalty on d D(x)/d x (histoGAN/histoGAN.py:156-163); needs the
     second-order gradients the conv ops provide."""
-    (gradients,) = torch.autograd.grad(outputs=output, inputs=images,
-                                       grad_outputs=torch.ones_like(output),
-                                       create_graph=True, retain_graph=True, only_inputs=True)
+    from . import ops
+    with ops.input_grads_only():             # d out / d images: no weight / bias gradients on the way
+        (gradients,) = torch.autograd.grad(outputs=output, inputs=images,
+                                           grad_outputs=torch.ones_like(output),
+                                           create_graph=True, retain_graph=True, only_inputs=True)
     gradients = gradients.reshape(images.shape[0], -1)
     return weight * ((gradients.norm(2, dim=1) - 1) ** 2).mean()
 
