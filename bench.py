@@ -407,9 +407,10 @@ def conv_microbench(dev, B, rotate_bytes=320 << 20):
             for kind, v in t.items():
                 tot[kind][0] += f
                 tot[kind][1] += v
+            byt = 4 * (B * ci * h * h + B * cop * oh * oh)
             rows.append([f"{net} {ci}->{co} k{k} s{s} @{h} (CUDA cores)", round(f / t["fwd"] / 1e12, 1),
                          round(f / t["dgrad"] / 1e12, 1), round(f / t["wgrad"] / 1e12, 1), round(t["fwd"] * 1e6, 1),
-                         round(t["dgrad"] * 1e6, 1), round(t["wgrad"] * 1e6, 1)])
+                         round(t["dgrad"] * 1e6, 1), round(t["wgrad"] * 1e6, 1), round(byt / t["fwd"] / 1e9)])
             del imgs, dys
             continue
         per_set = 4 * (B * cip * h * h + B * cop * oh * oh + cop * cip * k * k)
@@ -433,7 +434,7 @@ def conv_microbench(dev, B, rotate_bytes=320 << 20):
             tot[kind][1] += v
         rows.append([f"{net} {ci}->{co} k{k} s{s} @{h}", round(f / t["fwd"] / 1e12, 1), round(f / t["dgrad"] / 1e12, 1),
                      round(f / t["wgrad"] / 1e12, 1), round(t["fwd"] * 1e6, 1), round(t["dgrad"] * 1e6, 1),
-                     round(t["wgrad"] * 1e6, 1)])
+                     round(t["wgrad"] * 1e6, 1), round(per_set / t["fwd"] / 1e9)])
         del xs, dys, ws, wp
         torch.cuda.empty_cache()
     agg = {k: v[0] / v[1] / 1e12 for k, v in tot.items()}
@@ -567,7 +568,8 @@ def run_train(args):
                 "dgrad_tflops": round(conv_agg["dgrad"], 1), "wgrad_tflops": round(conv_agg["wgrad"], 1),
                 "all_three_tflops": round(conv_agg["all"], 1), "pass_us": conv_agg["pass_us"],
                 "per_layer_columns": ["layer", "fwd TF/s", "dgrad TF/s", "wgrad TF/s", "fwd us", "dgrad us",
-                                      "wgrad us"],
+                                      "wgrad us", "fwd algorithmic GB/s (x + y + w once; HBM peak in hbm_peak_gbs)"],
+                "hbm_peak_gbs": hbm_peak,
                 "per_layer_tflops": conv_rows,
                 "step_algorithmic_conv_tflop": round(step_flops / 1e12, 3),
                 "step_achieved_tflops": round(step_flops / step_s / 1e12, 1)},
