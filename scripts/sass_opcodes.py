@@ -8,10 +8,10 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "histogan_b200", "build")
-KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "SYNCS", "FFMA", "MUFU", "RED", "ATOM", "LDGSTS", "HMMA"]
+KEYS = ["UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "LDTM", "UTCBAR", "SYNCS", "FFMA", "MUFU", "RED", "ATOM", "LDGSTS", "HMMA"]
 
 print("# SASS opcode counts per kernel (cuobjdump -sass of histogan_b200/build/*.o, sm_100a)\n")
-print("`UTCHMMA` = tcgen05.mma, `UTMALDG` / `UTMASTG` = TMA tensor load / store, `LDTM` = tcgen05.ld, "
+print("`UTCHMMA` = tcgen05.mma, `UTMALDG` / `UTMASTG` = TMA tensor load / store, `UBLKCP` = 1-D bulk copy (cp.async.bulk), `LDTM` = tcgen05.ld, "
       "`UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops, `HMMA` would be the legacy mma.sync path (absent).\n")
 print("| object | kernel | " + " | ".join(KEYS) + " | instructions |")
 print("|---|---|" + "---|" * (len(KEYS) + 1))
@@ -40,6 +40,6 @@ for f in sorted(os.listdir(OBJ)):
     for name, c in rows:
         dem = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip()
         dem = re.sub(r"\(.*", "", dem).replace("void ", "")
-        if c["_n"] < 40 and not any(c[k] for k in KEYS[:4]):
+        if c["_n"] < 40 and not any(c[k] for k in KEYS[:5]):
             continue
         print(f"| {f} | `{dem[:70]}` | " + " | ".join(str(c[k]) if c[k] else "" for k in KEYS) + f" | {c['_n']} |")
