@@ -173,25 +173,42 @@ conv_small_fwd16_kernel(const float* __restrict__ x, const float* __restrict__ r
   float acc[kFastCout];
 #pragma unroll
   for (int e = 0; e < kFastCout; ++e) acc[e] = C_SMALL_B[e];
-  const float* xb = x + (long long)b * a.sb;
-  long long offw[K];
-  bool okw[K];
+  // taps outside the image read a clamped (valid) address and are zeroed by a select: no divergence, and
+  // the nine tap pointers are formed once and advanced by one plane stride per input channel (the first
+  // version spent 850 of its 1280 instructions per pixel on per-tap bounds checks and 64-bit address math)
+  const float* tap[K][K];
+  bool ok[K][K];
+  {
+    const float* xb = x + (long long)b * a.sb;
+    const float* row[K];
+    bool okh[K];
 #pragma unroll
-  for (int kw = 0; kw < K; ++kw) {
-    const int iw = ow + kw - pad;
-    okw[kw] = iw >= 0 && iw < a.W;
-    offw[kw] = (long long)iw * a.sw;
+    for (int kh = 0; kh < K; ++kh) {
+      const int ih = oh + kh - pad;
+      okh[kh] = ih >= 0 && ih < a.H;
+      row[kh] = xb + (long long)min(max(ih, 0), a.H - 1) * a.sh;
+    }
+#pragma unroll
+    for (int kw = 0; kw < K; ++kw) {
+      const int iw = ow + kw - pad;
+      const bool okw = iw >= 0 && iw < a.W;
+      const long long off = (long long)min(max(iw, 0), a.W - 1) * a.sw;
+#pragma unroll
+      for (int kh = 0; kh < K; ++kh) {
+        tap[kh][kw] = row[kh] + off;
+        ok[kh][kw] = okh[kh] && okw;
+      }
+    }
   }
 #pragma unroll
-  for (int kh = 0; kh < K; ++kh) {
-    const int ih = oh + kh - pad;
-    const bool okh = ih >= 0 && ih < a.H;
-    const float* xr = xb + (long long)ih * a.sh;
+  for (int ci = 0; ci < kFastCin; ++ci) {
 #pragma unroll
-    for (int ci = 0; ci < kFastCin; ++ci) {
+    for (int kh = 0; kh < K; ++kh) {
 #pragma unroll
       for (int kw = 0; kw < K; ++kw) {
-        const float xv = (okh && okw[kw]) ? __ldg(xr + ci * a.sc + offw[kw]) : 0.f;
+        const float v = __ldg(tap[kh][kw]);
+        const float xv = ok[kh][kw] ? v : 0.f;
+        tap[kh][kw] += a.sc;
 #pragma unroll
         for (int co = 0; co < kFastCout; ++co)
           acc[co] = fmaf(xv, c_small_w[(ci * kSmallMaxTaps + kh * K + kw) * kFastCout + co], acc[co]);
