@@ -312,9 +312,11 @@ def test_host_batches_reach_the_captured_graphs(tmp_path, cuda_device):
         h = torch.rand(4, 3, 64, 64, generator=g)
         return torch.rand(4, 3, 32, 32, generator=g) * min(1.0, 0.2 + 0.1 * n), h / h.sum(dim=(1, 2, 3), keepdim=True)
 
+    import random
     first = {}
     for where in ("host", "device"):
         torch.manual_seed(0)
+        random.seed(0)                 # the mixed-style decision (histoGAN.py:891) comes from Python's generator
         tr = _trainer(tmp_path / where, cuda_graphs=True, fast_rng=True)
         tr.init_GAN()
         tr.steps = 2501
